@@ -1,0 +1,794 @@
+// C ABI of the flexgsea sm_100a library: context management, uploads and the
+// orchestration of the per-block pipeline
+//   permute labels -> gene scores -> rank -> ES        (fgs_perm_null)
+//   per-set null reductions -> NES -> pooled FDR        (fgs_calc_sig / staged)
+// See include/flexgsea_b200.h for the contract and the reference citations.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <climits>
+
+#include "fgs_common.cuh"
+
+namespace fgs {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int launch_sig_means(fgs_ctx *c, const double *d_sums_parts, int nparts, const long long *d_counts,
+                     const double *d_es, int S, long long P_total, int split_p, int calc_nes,
+                     int abs_flag, double *d_p, double *d_ph, double *d_pl, double *d_mpos,
+                     double *d_mneg, double *d_nes, double *d_fwer);
+int launch_bh(fgs_ctx *c, const double *d_p, int S, double *d_fdr);
+
+static int use_device(fgs_ctx *c) {
+  FGS_CUDA(cudaSetDevice(c->device));
+  return FGS_OK;
+}
+
+template <typename T>
+static int h2d(fgs_ctx *c, T *dst, const T *src, size_t n) {
+  if (n == 0) return FGS_OK;
+  FGS_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  return FGS_OK;
+}
+template <typename T>
+static int d2h(fgs_ctx *c, T *dst, const T *src, size_t n) {
+  if (n == 0 || dst == nullptr) return FGS_OK;
+  FGS_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+  return FGS_OK;
+}
+static int sync(fgs_ctx *c) {
+  FGS_CUDA(cudaStreamSynchronize(c->stream));
+  return FGS_OK;
+}
+
+// Householder QR of the [n x q] design (column-major), then H = R^-1 Q^T.
+// Returns false when rank deficient (tolerance as LINPACK dqrdc2 in lm.fit).
+static bool design_pinv(const std::vector<double> &D, int n, int q, std::vector<double> &H) {
+  std::vector<double> a(D), qraux(q, 0.0), norm0(q, 0.0);
+  for (int j = 0; j < q; j++) {
+    double s = 0;
+    for (int i = 0; i < n; i++) s += a[(size_t)j * n + i] * a[(size_t)j * n + i];
+    norm0[j] = std::sqrt(s);
+  }
+  if (q > n) return false;
+  for (int l = 0; l < q; l++) {
+    double *cl = &a[(size_t)l * n];
+    double nrm = 0;
+    for (int i = l; i < n; i++) nrm += cl[i] * cl[i];
+    nrm = std::sqrt(nrm);
+    if (norm0[l] == 0.0 || nrm < 1e-7 * norm0[l]) return false;
+    if (cl[l] != 0.0) nrm = std::copysign(nrm, cl[l]);
+    for (int i = l; i < n; i++) cl[i] /= nrm;
+    cl[l] += 1.0;
+    for (int j = l + 1; j < q; j++) {
+      double *cj = &a[(size_t)j * n];
+      double t = 0;
+      for (int i = l; i < n; i++) t -= cl[i] * cj[i];
+      t /= cl[l];
+      for (int i = l; i < n; i++) cj[i] += t * cl[i];
+    }
+    qraux[l] = cl[l];
+    cl[l] = -nrm;
+  }
+  H.assign((size_t)q * n, 0.0);  // H[c * n + i]
+  std::vector<double> w(n), b(q);
+  for (int e = 0; e < n; e++) {  // column e of H = coefficients of lm.fit(D, unit_e)
+    std::fill(w.begin(), w.end(), 0.0);
+    w[e] = 1.0;
+    for (int j = 0; j < q; j++) {
+      const double *cj = &a[(size_t)j * n];
+      double t = -qraux[j] * w[j];
+      for (int i = j + 1; i < n; i++) t -= cj[i] * w[i];
+      t /= qraux[j];
+      w[j] += t * qraux[j];
+      for (int i = j + 1; i < n; i++) w[i] += t * cj[i];
+    }
+    for (int j = 0; j < q; j++) b[j] = w[j];
+    for (int j = q - 1; j >= 0; j--) {
+      b[j] /= a[(size_t)j * n + j];
+      for (int i = 0; i < j; i++) b[i] -= b[j] * a[(size_t)j * n + i];
+    }
+    for (int j = 0; j < q; j++) H[(size_t)j * n + e] = b[j];
+  }
+  return true;
+}
+
+static int n_response_of(fgs_ctx *c, int score_kind) {
+  if (score_kind == FGS_SCORE_S2N) return c->s2n_R;
+  if (score_kind == FGS_SCORE_LM) return c->lm_R;
+  return 0;
+}
+
+static int check_problem(fgs_ctx *c, bool need_sets) {
+  if (c->G <= 0 || c->n <= 0) { set_error("fgs_set_x has not been called"); return FGS_ERR_STATE; }
+  if (need_sets) {
+    if (c->S <= 0) { set_error("fgs_set_gene_sets has not been called"); return FGS_ERR_STATE; }
+    if (c->max_set > c->G) { set_error("gene set index %d exceeds the %d genes of x", c->max_set, c->G); return FGS_ERR_ARG; }
+  }
+  return FGS_OK;
+}
+
+// flags buffer: [0, P) per-permutation bits, [n-1] global bits
+static int flags_reset(fgs_ctx *c, long long P) {
+  FGS_TRY(c->flags.ensure((size_t)P + 1));
+  FGS_CUDA(cudaMemsetAsync(c->flags.p, 0, c->flags.n * sizeof(int), c->stream));
+  return FGS_OK;
+}
+static int flags_check(fgs_ctx *c, long long P) {
+  std::vector<int> h(c->flags.n);
+  FGS_CUDA(cudaMemcpyAsync(h.data(), c->flags.p, c->flags.n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  FGS_TRY(sync(c));
+  if (h[c->flags.n - 1] & 8) { set_error("permutation matrix holds an index outside [1, n_sample]"); return FGS_ERR_ARG; }
+  for (long long p = 0; p < P; p++)
+    if (h[p]) {
+      set_error("Gene scoring function returned NA or Inf.");  // R/flexgsea.R:400-402
+      return FGS_ERR_NONFINITE;
+    }
+  return FGS_OK;
+}
+
+struct StageTimer {
+  fgs_ctx *c;
+  std::vector<cudaEvent_t> evs;  // 4 per block: start, scored, ranked, es
+  explicit StageTimer(fgs_ctx *ctx) : c(ctx) {}
+  void mark() {
+    if (!c->profiling) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, c->stream);
+    evs.push_back(e);
+  }
+  void finish(float prologue_ms) {
+    for (int i = 0; i < 5; i++) c->last_ms[i] = 0;
+    if (!c->profiling) return;
+    c->last_ms[0] = prologue_ms;
+    for (size_t b = 0; b + 3 < evs.size(); b += 4) {
+      float t;
+      cudaEventElapsedTime(&t, evs[b], evs[b + 1]); c->last_ms[1] += t;
+      cudaEventElapsedTime(&t, evs[b + 1], evs[b + 2]); c->last_ms[2] += t;
+      cudaEventElapsedTime(&t, evs[b + 2], evs[b + 3]); c->last_ms[3] += t;
+    }
+    for (auto e : evs) cudaEventDestroy(e);
+    evs.clear();
+    c->last_ms[4] = c->last_ms[0] + c->last_ms[1] + c->last_ms[2] + c->last_ms[3];
+  }
+};
+
+// columns (score vectors) processed per block: bounded so the scratch
+// (scores 8G + rank 2G + weights 8G bytes per column) stays ~<= 1.5 GB
+static long long block_columns(fgs_ctx *c, long long C_total) {
+  long long cb = c->opt_perm_block > 0 ? c->opt_perm_block : 2048;
+  long long cap = (long long)(1.5e9 / (18.0 * (double)c->G + 64));
+  if (cap < 1) cap = 1;
+  if (cb > cap) cb = cap;
+  if (cb > C_total) cb = C_total;
+  return cb < 1 ? 1 : cb;
+}
+
+// rank + ES of the score columns currently in c->scores
+static int rank_and_es(fgs_ctx *c, int es_kind, double p_exp, int abs_flag, long long Cb,
+                       double *d_es, StageTimer &tm) {
+  const int G = c->G;
+  if (es_kind == FGS_ES_WEIGHTED_KS) {
+    const size_t Gp = pitch_of(G);
+    FGS_TRY(c->rank16.ensure(Gp * Cb));
+    FGS_TRY(c->sabs.ensure(Gp * Cb));
+    long long l0 = c->launches;
+    FGS_TRY(launch_sort(c, c->scores.p, G, Cb, abs_flag, p_exp, c->rank16.p, c->sabs.p));
+    c->last_launches[2] += c->launches - l0;
+    tm.mark();
+    l0 = c->launches;
+    FGS_TRY(launch_es_wks(c, c->rank16.p, c->sabs.p, G, Cb, d_es));
+    c->last_launches[3] += c->launches - l0;
+    tm.mark();
+  } else if (es_kind == FGS_ES_MAXMEAN || es_kind == FGS_ES_MEAN) {
+    tm.mark();
+    long long l0 = c->launches;
+    FGS_TRY(launch_es_mean(c, c->scores.p, G, Cb, es_kind, abs_flag, d_es));
+    c->last_launches[3] += c->launches - l0;
+    tm.mark();
+  } else {
+    set_error("unknown es_kind %d", es_kind);
+    return FGS_ERR_ARG;
+  }
+  c->last_cols = Cb;
+  c->last_G = G;
+  return FGS_OK;
+}
+
+}  // namespace fgs
+
+using namespace fgs;
+
+extern "C" {
+
+int fgs_abi_version(void) { return FGS_ABI_VERSION; }
+const char *fgs_last_error(void) { return g_err; }
+
+int fgs_device_count(int *count) {
+  if (!count) return FGS_ERR_ARG;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *count = 0;
+    set_error("no CUDA device: %s", cudaGetErrorString(e));
+    return FGS_ERR_CUDA;
+  }
+  *count = n;
+  return FGS_OK;
+}
+
+int fgs_create(int device, fgs_ctx **out) {
+  if (!out) return FGS_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  FGS_TRY(fgs_device_count(&n));
+  if (device < 0 || device >= n) { set_error("device %d out of range (%d visible)", device, n); return FGS_ERR_ARG; }
+  FGS_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FGS_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return FGS_ERR_UNSUPPORTED;
+  }
+  fgs_ctx *c = new fgs_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  FGS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = c;
+  return FGS_OK;
+}
+
+int fgs_destroy(fgs_ctx *c) {
+  if (!c) return FGS_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->x.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release();
+  c->set_order.release(); c->set_slow.release(); c->slow_ids.release(); c->ybin.release();
+  c->n1n2.release(); c->lm_H.release(); c->perm.release(); c->labels.release(); c->lm_B.release();
+  c->scores.release(); c->rank16.release(); c->sabs.release(); c->sort_keys.release();
+  c->sort_idx.release(); c->flags.release(); c->counters.release(); c->es_null.release();
+  c->sig_d.release(); c->sig_i.release();
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return FGS_OK;
+}
+
+int fgs_launch_count(fgs_ctx *c, long long *count) {
+  if (!c || !count) return FGS_ERR_ARG;
+  *count = c->launches;
+  return FGS_OK;
+}
+int fgs_set_profiling(fgs_ctx *c, int enabled) {
+  if (!c) return FGS_ERR_ARG;
+  c->profiling = enabled != 0;
+  return FGS_OK;
+}
+int fgs_last_timings(fgs_ctx *c, float *ms, long long *launches) {
+  if (!c) return FGS_ERR_ARG;
+  if (ms) for (int i = 0; i < 5; i++) ms[i] = c->last_ms[i];
+  if (launches) for (int i = 0; i < 5; i++) launches[i] = c->last_launches[i];
+  return FGS_OK;
+}
+int fgs_set_option(fgs_ctx *c, const char *name, long long value) {
+  if (!c || !name) return FGS_ERR_ARG;
+  if (!strcmp(name, "perm_block")) c->opt_perm_block = (int)value;
+  else if (!strcmp(name, "force_generic_es")) c->opt_force_generic = (int)value;
+  else { set_error("unknown option '%s'", name); return FGS_ERR_ARG; }
+  return FGS_OK;
+}
+
+// ---------------------------------------------------------------------------
+int fgs_set_x(fgs_ctx *c, const double *x, int n_sample, int n_gene) {
+  if (!c || !x || n_sample <= 0 || n_gene <= 0) { set_error("fgs_set_x: bad argument"); return FGS_ERR_ARG; }
+  FGS_TRY(use_device(c));
+  FGS_TRY(c->x.ensure((size_t)n_sample * n_gene));
+  FGS_TRY(h2d(c, c->x.p, x, (size_t)n_sample * n_gene));
+  c->n = n_sample; c->G = n_gene;
+  c->gene_sd_valid = false;
+  FGS_TRY(sync(c));
+  return FGS_OK;
+}
+
+int fgs_set_gene_sets(fgs_ctx *c, const int *offsets, const int *index, int n_sets) {
+  if (!c || !offsets || n_sets <= 0) { set_error("fgs_set_gene_sets: bad argument"); return FGS_ERR_ARG; }
+  FGS_TRY(use_device(c));
+  if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return FGS_ERR_ARG; }
+  const long long nnz = offsets[n_sets];
+  if (nnz > 0 && !index) { set_error("fgs_set_gene_sets: index is NULL"); return FGS_ERR_ARG; }
+  std::vector<int> idx0((size_t)nnz), order(n_sets);
+  std::vector<unsigned char> slow(n_sets, 0);
+  std::vector<int> slow_ids, tmp;
+  int max_idx = 0;
+  for (int s = 0; s < n_sets; s++) {
+    const int a = offsets[s], b = offsets[s + 1];
+    if (b < a) { set_error("offsets not monotone at set %d", s); return FGS_ERR_ARG; }
+    for (int j = a; j < b; j++) {
+      if (index[j] < 1) { set_error("gene index %d < 1 in set %d (NA from match()?)", index[j], s); return FGS_ERR_ARG; }
+      idx0[j] = index[j] - 1;
+      max_idx = std::max(max_idx, index[j]);
+    }
+    tmp.assign(idx0.begin() + a, idx0.begin() + b);
+    std::sort(tmp.begin(), tmp.end());
+    bool dup = std::adjacent_find(tmp.begin(), tmp.end()) != tmp.end();
+    if (dup || (b - a) > 512) { slow[s] = 1; slow_ids.push_back(s); }
+    order[s] = s;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int p, int q) {
+    return (offsets[p + 1] - offsets[p]) > (offsets[q + 1] - offsets[q]);
+  });
+  FGS_TRY(c->set_off.ensure((size_t)n_sets + 1));
+  FGS_TRY(c->set_idx.ensure((size_t)std::max<long long>(nnz, 1)));
+  FGS_TRY(c->set_order.ensure(n_sets));
+  FGS_TRY(c->set_slow.ensure(n_sets));
+  FGS_TRY(c->slow_ids.ensure(std::max<size_t>(slow_ids.size(), 1)));
+  FGS_TRY(h2d(c, c->set_off.p, offsets, (size_t)n_sets + 1));
+  FGS_TRY(h2d(c, c->set_idx.p, idx0.data(), (size_t)nnz));
+  FGS_TRY(h2d(c, c->set_order.p, order.data(), (size_t)n_sets));
+  FGS_TRY(h2d(c, c->set_slow.p, slow.data(), (size_t)n_sets));
+  FGS_TRY(h2d(c, c->slow_ids.p, slow_ids.data(), slow_ids.size()));
+  FGS_TRY(sync(c));
+  c->S = n_sets; c->nnz = nnz; c->max_set = max_idx; c->n_slow = (int)slow_ids.size();
+  c->h_set_off.assign(offsets, offsets + n_sets + 1);
+  return FGS_OK;
+}
+
+int fgs_set_response_s2n(fgs_ctx *c, const int *y_bin, int n_sample, int n_response) {
+  if (!c || !y_bin || n_sample <= 0 || n_response <= 0) { set_error("fgs_set_response_s2n: bad argument"); return FGS_ERR_ARG; }
+  FGS_TRY(use_device(c));
+  std::vector<int> nn(2 * (size_t)n_response, 0);
+  for (int r = 0; r < n_response; r++)
+    for (int i = 0; i < n_sample; i++) {
+      int v = y_bin[(size_t)r * n_sample + i];
+      if (v == INT_MIN) continue;
+      nn[2 * r + (v ? 0 : 1)]++;
+    }
+  FGS_TRY(c->ybin.ensure((size_t)n_sample * n_response));
+  FGS_TRY(c->n1n2.ensure(2 * (size_t)n_response));
+  FGS_TRY(h2d(c, c->ybin.p, y_bin, (size_t)n_sample * n_response));
+  FGS_TRY(h2d(c, c->n1n2.p, nn.data(), nn.size()));
+  FGS_TRY(sync(c));
+  c->s2n_R = n_response;
+  if (c->n && c->n != n_sample) { /* checked again at run time */ }
+  return FGS_OK;
+}
+
+int fgs_set_response_lm(fgs_ctx *c, const double *design, int n_sample, int n_col, int has_intercept) {
+  if (!c || !design || n_sample <= 0 || n_col <= 0) { set_error("fgs_set_response_lm: bad argument"); return FGS_ERR_ARG; }
+  FGS_TRY(use_device(c));
+  const int R = n_col - (has_intercept ? 1 : 0);
+  if (R <= 0) { set_error("design has no non-intercept column"); return FGS_ERR_ARG; }
+  std::vector<double> D(design, design + (size_t)n_sample * n_col), H;
+  if (!design_pinv(D, n_sample, n_col, H)) {
+    set_error("Gene scoring function returned NA or Inf. (rank-deficient design)");
+    return FGS_ERR_NONFINITE;
+  }
+  FGS_TRY(c->lm_H.ensure((size_t)R * n_sample));
+  FGS_TRY(h2d(c, c->lm_H.p, H.data() + (has_intercept ? n_sample : 0), (size_t)R * n_sample));
+  FGS_TRY(sync(c));
+  c->lm_q = n_col; c->lm_R = R; c->lm_icpt = has_intercept ? 1 : 0;
+  c->h_design.swap(D);
+  return FGS_OK;
+}
+
+int fgs_n_response(fgs_ctx *c, int score_kind, int *n_response) {
+  if (!c || !n_response) return FGS_ERR_ARG;
+  *n_response = n_response_of(c, score_kind);
+  return FGS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// gene scores of `P` permutations starting at device perm column p0 (d_perm may
+// be NULL = identity) into c->scores [P*R][G]; flags at c->flags + flag0
+static int score_block(fgs_ctx *c, int score_kind, const int *d_perm, const uint32_t *d_labels,
+                       int P, long long flag0) {
+  const int n = c->n, G = c->G;
+  const int R = n_response_of(c, score_kind);
+  const long long Cb = (long long)P * R;
+  FGS_TRY(c->scores.ensure((size_t)G * Cb));
+  if (score_kind == FGS_SCORE_S2N) {
+    FGS_TRY(launch_s2n(c, c->x.p, n, G, d_labels, c->n1n2.p, R, Cb, c->scores.p, c->flags.p + flag0));
+    FGS_TRY(launch_s2n_patch(c, c->scores.p, G, R, P, c->flags.p + flag0));
+  } else {
+    if (!c->gene_sd_valid) {
+      FGS_TRY(c->gene_sd.ensure(G));
+      FGS_TRY(launch_gene_sd(c, c->x.p, n, G, c->gene_sd.p));
+      c->gene_sd_valid = true;
+    }
+    FGS_TRY(c->lm_B.ensure((size_t)n * Cb));
+    FGS_TRY(launch_lm_build_B(c, c->lm_H.p, d_perm, n, R, P, c->lm_B.p));
+    FGS_TRY(launch_lm_gemm(c, c->x.p, n, G, c->lm_B.p, Cb, c->gene_sd.p, c->scores.p,
+                           c->flags.p + flag0, R));
+  }
+  return FGS_OK;
+}
+
+static int check_response(fgs_ctx *c, int score_kind) {
+  if (score_kind == FGS_SCORE_S2N) {
+    if (c->s2n_R <= 0) { set_error("fgs_set_response_s2n has not been called"); return FGS_ERR_STATE; }
+  } else if (score_kind == FGS_SCORE_LM) {
+    if (c->lm_R <= 0) { set_error("fgs_set_response_lm has not been called"); return FGS_ERR_STATE; }
+  } else { set_error("unknown score_kind %d", score_kind); return FGS_ERR_ARG; }
+  return FGS_OK;
+}
+
+int fgs_s2n(fgs_ctx *c, const double *x, int n_sample_x, int n_gene, const int *y, int n_sample_y,
+            int n_response, double *coef) {
+  if (!c || !x || !y || !coef || n_gene <= 0 || n_response <= 0) { set_error("fgs_s2n: bad argument"); return FGS_ERR_ARG; }
+  if (n_sample_x != n_sample_y) {  // src/ggsea.cpp:15-17
+    std::memset(coef, 0, sizeof(double) * (size_t)n_gene * n_response);
+    return FGS_OK;
+  }
+  FGS_TRY(use_device(c));
+  // independent of the resident problem: temporary buffers
+  DevBuf<double> dx, dsc; DevBuf<int> dy, dnn, dfl; DevBuf<uint32_t> dlab;
+  const int n = n_sample_x, W = (n + 31) / 32;
+  int rc = FGS_OK;
+  std::vector<int> nn(2 * (size_t)n_response, 0);
+  for (int r = 0; r < n_response; r++)
+    for (int i = 0; i < n; i++) { int v = y[(size_t)r * n + i]; if (v != INT_MIN) nn[2 * r + (v ? 0 : 1)]++; }
+  auto body = [&]() -> int {
+    FGS_TRY(dx.ensure((size_t)n * n_gene)); FGS_TRY(dsc.ensure((size_t)n_gene * n_response));
+    FGS_TRY(dy.ensure((size_t)n * n_response)); FGS_TRY(dnn.ensure(nn.size()));
+    FGS_TRY(dfl.ensure(2)); FGS_TRY(dlab.ensure((size_t)n_response * 2 * W));
+    FGS_TRY(h2d(c, dx.p, x, (size_t)n * n_gene)); FGS_TRY(h2d(c, dy.p, y, (size_t)n * n_response));
+    FGS_TRY(h2d(c, dnn.p, nn.data(), nn.size()));
+    FGS_CUDA(cudaMemsetAsync(dfl.p, 0, 2 * sizeof(int), c->stream));
+    FGS_TRY(flags_reset(c, 1));
+    FGS_TRY(launch_labels(c, nullptr, dy.p, n, n_response, 1, dlab.p));
+    FGS_TRY(launch_s2n(c, dx.p, n, n_gene, dlab.p, dnn.p, n_response, n_response, dsc.p, dfl.p));
+    FGS_TRY(d2h(c, coef, dsc.p, (size_t)n_gene * n_response));
+    FGS_TRY(sync(c));
+    return FGS_OK;
+  };
+  rc = body();
+  dx.release(); dsc.release(); dy.release(); dnn.release(); dfl.release(); dlab.release();
+  return rc;
+}
+
+int fgs_score_observed(fgs_ctx *c, int score_kind, int abs_flag, double *scores) {
+  if (!c || !scores) return FGS_ERR_ARG;
+  FGS_TRY(use_device(c));
+  FGS_TRY(check_problem(c, false));
+  FGS_TRY(check_response(c, score_kind));
+  const int R = n_response_of(c, score_kind), n = c->n, G = c->G;
+  FGS_TRY(flags_reset(c, 1));
+  if (score_kind == FGS_SCORE_S2N) {
+    const int W = (n + 31) / 32;
+    FGS_TRY(c->labels.ensure((size_t)R * 2 * W));
+    FGS_TRY(launch_labels(c, nullptr, c->ybin.p, n, R, 1, c->labels.p));
+  }
+  FGS_TRY(score_block(c, score_kind, nullptr, c->labels.p, 1, 0));
+  if (abs_flag) FGS_TRY(launch_abs_inplace(c, c->scores.p, (long long)G * R));
+  FGS_TRY(d2h(c, scores, c->scores.p, (size_t)G * R));
+  FGS_TRY(flags_check(c, 1));
+  return FGS_OK;
+}
+
+int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs_flag,
+                  const int *perm, unsigned long long seed, long long perm_id0, int n_perm,
+                  double *es_null_out) {
+  if (!c || n_perm < 0) { set_error("fgs_perm_null: bad argument"); return FGS_ERR_ARG; }
+  FGS_TRY(use_device(c));
+  FGS_TRY(check_problem(c, true));
+  FGS_TRY(check_response(c, score_kind));
+  const int n = c->n, G = c->G, S = c->S, P = n_perm;
+  const int R = n_response_of(c, score_kind);
+  for (int i = 0; i < 5; i++) c->last_launches[i] = 0;
+  FGS_TRY(c->es_null.ensure(std::max<size_t>((size_t)S * R * P, 1)));
+  c->null_S = S; c->null_R = R; c->null_P = P;
+  if (P == 0) return FGS_OK;
+  FGS_TRY(flags_reset(c, P));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (c->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream); }
+  long long l0 = c->launches;
+  // K1: permutations (uploaded or drawn) and, for s2n, permuted class masks
+  FGS_TRY(c->perm.ensure((size_t)n * P));
+  if (perm) FGS_TRY(h2d(c, c->perm.p, perm, (size_t)n * P));
+  else FGS_TRY(launch_philox_perm(c, seed, perm_id0, n, P, c->perm.p));
+  const int W = (n + 31) / 32;
+  if (score_kind == FGS_SCORE_S2N) {
+    FGS_TRY(c->labels.ensure((size_t)P * R * 2 * W));
+    FGS_TRY(launch_labels(c, c->perm.p, c->ybin.p, n, R, P, c->labels.p));
+  }
+  c->last_launches[0] = c->launches - l0;
+  float pro_ms = 0;
+  if (c->profiling) { cudaEventRecord(e1, c->stream); }
+  StageTimer tm(c);
+  const long long Cb_max = block_columns(c, (long long)P * R);
+  const int Pb_max = (int)std::max<long long>(1, Cb_max / R);
+  for (int p0 = 0; p0 < P; p0 += Pb_max) {
+    const int Pb = std::min(Pb_max, P - p0);
+    tm.mark();
+    l0 = c->launches;
+    FGS_TRY(score_block(c, score_kind, c->perm.p + (size_t)p0 * n,
+                        c->labels.p + (size_t)p0 * R * 2 * W, Pb, p0));
+    c->last_launches[1] += c->launches - l0;
+    tm.mark();
+    FGS_TRY(rank_and_es(c, es_kind, p_exp, abs_flag, (long long)Pb * R,
+                        c->es_null.p + (size_t)p0 * R * S, tm));
+  }
+  int rc = flags_check(c, P);
+  if (c->profiling) {
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&pro_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+  tm.finish(pro_ms);
+  c->last_launches[4] = c->last_launches[0] + c->last_launches[1] + c->last_launches[2] + c->last_launches[3];
+  if (rc != FGS_OK) return rc;
+  if (es_null_out) {
+    FGS_TRY(d2h(c, es_null_out, c->es_null.p, (size_t)S * R * P));
+    FGS_TRY(sync(c));
+  }
+  return FGS_OK;
+}
+
+int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scores, int n_gene,
+                       int n_response, int n_perm, double *es_out) {
+  if (!c || !scores || n_gene <= 0 || n_response <= 0 || n_perm < 0) { set_error("fgs_es_from_scores: bad argument"); return FGS_ERR_ARG; }
+  FGS_TRY(use_device(c));
+  if (c->S <= 0) { set_error("fgs_set_gene_sets has not been called"); return FGS_ERR_STATE; }
+  if (c->G != 0 && c->G != n_gene && c->x.p) { /* x not needed on this path; sets decide */ }
+  if (c->max_set > n_gene) { set_error("gene set index %d exceeds %d genes", c->max_set, n_gene); return FGS_ERR_ARG; }
+  const int saveG = c->G;
+  c->G = n_gene;
+  const int S = c->S, R = n_response, P = n_perm;
+  const long long C = (long long)R * P;
+  for (int i = 0; i < 5; i++) c->last_launches[i] = 0;
+  int rc = FGS_OK;
+  auto body = [&]() -> int {
+    FGS_TRY(c->es_null.ensure(std::max<size_t>((size_t)S * C, 1)));
+    c->null_S = S; c->null_R = R; c->null_P = P;
+    if (C == 0) return FGS_OK;
+    FGS_TRY(flags_reset(c, C));
+    StageTimer tm(c);
+    const long long Cb_max = block_columns(c, C);
+    for (long long c0 = 0; c0 < C; c0 += Cb_max) {
+      const long long Cb = std::min(Cb_max, C - c0);
+      FGS_TRY(c->scores.ensure((size_t)n_gene * Cb));
+      tm.mark();
+      FGS_TRY(h2d(c, c->scores.p, scores + (size_t)c0 * n_gene, (size_t)n_gene * Cb));
+      FGS_TRY(launch_check_finite(c, c->scores.p, (long long)n_gene * Cb, n_gene, c->flags.p + c0));
+      tm.mark();
+      FGS_TRY(rank_and_es(c, es_kind, p_exp, 0, Cb, c->es_null.p + (size_t)c0 * S, tm));
+    }
+    int r2 = flags_check(c, C);
+    tm.finish(0.f);
+    if (r2 != FGS_OK) return r2;
+    if (es_out) { FGS_TRY(d2h(c, es_out, c->es_null.p, (size_t)S * C)); FGS_TRY(sync(c)); }
+    return FGS_OK;
+  };
+  rc = body();
+  c->G = saveG;
+  return rc;
+}
+
+int fgs_debug_last_scores(fgs_ctx *c, double *scores, int *rank, long long n_col) {
+  if (!c) return FGS_ERR_ARG;
+  FGS_TRY(use_device(c));
+  if (n_col > c->last_cols || c->last_G <= 0) { set_error("debug tap: only %lld columns resident", c->last_cols); return FGS_ERR_STATE; }
+  const int G = c->last_G;
+  if (scores) FGS_TRY(d2h(c, scores, c->scores.p, (size_t)G * n_col));
+  if (rank) {
+    const size_t Gp = pitch_of(G);
+    std::vector<uint16_t> h(Gp * n_col);
+    FGS_TRY(d2h(c, h.data(), c->rank16.p, Gp * n_col));
+    FGS_TRY(sync(c));
+    for (long long col = 0; col < n_col; col++)
+      for (int g = 0; g < G; g++) rank[(size_t)col * G + g] = h[(size_t)col * Gp + g];
+  }
+  FGS_TRY(sync(c));
+  return FGS_OK;
+}
+
+int fgs_null_device_ptr(fgs_ctx *c, void **dptr, int *n_sets, int *n_response, int *n_perm) {
+  if (!c) return FGS_ERR_ARG;
+  if (dptr) *dptr = c->es_null.p;
+  if (n_sets) *n_sets = c->null_S;
+  if (n_response) *n_response = c->null_R;
+  if (n_perm) *n_perm = c->null_P;
+  return FGS_OK;
+}
+
+int fgs_set_null(fgs_ctx *c, const double *es_null, int n_sets, int n_response, int n_perm) {
+  if (!c || (!es_null && n_perm > 0) || n_sets <= 0 || n_response <= 0 || n_perm < 0) { set_error("fgs_set_null: bad argument"); return FGS_ERR_ARG; }
+  FGS_TRY(use_device(c));
+  size_t len = (size_t)n_sets * n_response * n_perm;
+  FGS_TRY(c->es_null.ensure(std::max<size_t>(len, 1)));
+  FGS_TRY(h2d(c, c->es_null.p, es_null, len));
+  FGS_TRY(sync(c));
+  c->null_S = n_sets; c->null_R = n_response; c->null_P = n_perm;
+  return FGS_OK;
+}
+
+// ---------------------------------------------------------------------------
+int fgs_observed_es(fgs_ctx *c, int es_kind, double p_exp, const double *scores, int n_gene,
+                    int n_response, double *es, double *max_es_at, double *le_prop, int *running_es_at,
+                    double *running_es_pos, double *running_es_neg, int *le_first, int *le_count) {
+  if (!c || !scores || n_response <= 0 || n_gene <= 0) { set_error("fgs_observed_es: bad argument"); return FGS_ERR_ARG; }
+  FGS_TRY(use_device(c));
+  if (c->S <= 0) { set_error("fgs_set_gene_sets has not been called"); return FGS_ERR_STATE; }
+  if (c->max_set > n_gene) { set_error("gene set index %d exceeds %d genes", c->max_set, n_gene); return FGS_ERR_ARG; }
+  const int G = n_gene, S = c->S, R = n_response;
+  const size_t SR = (size_t)S * R, NR = (size_t)std::max<long long>(c->nnz, 1) * R;
+  FGS_TRY(c->scores.ensure((size_t)G * R));
+  FGS_TRY(flags_reset(c, R));
+  FGS_TRY(h2d(c, c->scores.p, scores, (size_t)G * R));
+  FGS_TRY(launch_check_finite(c, c->scores.p, (long long)G * R, G, c->flags.p));
+  DevBuf<double> d_es, d_mea, d_lep, d_pos, d_neg; DevBuf<int> d_at, d_lf, d_lc;
+  auto body = [&]() -> int {
+    FGS_TRY(d_es.ensure(SR));
+    if (es_kind == FGS_ES_WEIGHTED_KS) {
+      const size_t Gp = pitch_of(G);
+      FGS_TRY(c->rank16.ensure(Gp * R)); FGS_TRY(c->sabs.ensure(Gp * R));
+      FGS_TRY(d_mea.ensure(SR)); FGS_TRY(d_lep.ensure(SR)); FGS_TRY(d_lf.ensure(SR)); FGS_TRY(d_lc.ensure(SR));
+      FGS_TRY(d_pos.ensure(NR)); FGS_TRY(d_neg.ensure(NR)); FGS_TRY(d_at.ensure(NR));
+      FGS_TRY(launch_sort(c, c->scores.p, G, R, 0, p_exp, c->rank16.p, c->sabs.p));
+      FGS_TRY(launch_observed_wks(c, c->rank16.p, c->sabs.p, G, R, d_es.p, d_mea.p, d_lep.p, d_at.p,
+                                  d_pos.p, d_neg.p, d_lf.p, d_lc.p));
+      c->last_cols = R; c->last_G = G;
+      FGS_TRY(d2h(c, max_es_at, d_mea.p, SR)); FGS_TRY(d2h(c, le_prop, d_lep.p, SR));
+      FGS_TRY(d2h(c, le_first, d_lf.p, SR)); FGS_TRY(d2h(c, le_count, d_lc.p, SR));
+      FGS_TRY(d2h(c, running_es_at, d_at.p, (size_t)c->nnz * R));
+      FGS_TRY(d2h(c, running_es_pos, d_pos.p, (size_t)c->nnz * R));
+      FGS_TRY(d2h(c, running_es_neg, d_neg.p, (size_t)c->nnz * R));
+    } else if (es_kind == FGS_ES_MAXMEAN || es_kind == FGS_ES_MEAN) {
+      FGS_TRY(launch_es_mean(c, c->scores.p, G, R, es_kind, 0, d_es.p));
+    } else { set_error("unknown es_kind %d", es_kind); return FGS_ERR_ARG; }
+    FGS_TRY(d2h(c, es, d_es.p, SR));
+    return flags_check(c, R);
+  };
+  int rc = body();
+  cudaStreamSynchronize(c->stream);
+  d_es.release(); d_mea.release(); d_lep.release(); d_pos.release(); d_neg.release();
+  d_at.release(); d_lf.release(); d_lc.release();
+  return rc;
+}
+
+// ---------------------------------------------------------------------------
+// significance
+static int sig_check(fgs_ctx *c, int response) {
+  if (c->null_S <= 0 || c->null_R <= 0) { set_error("no resident null: run fgs_perm_null / fgs_es_from_scores / fgs_set_null first"); return FGS_ERR_STATE; }
+  if (response < 0 || response >= c->null_R) { set_error("response %d out of range (%d)", response, c->null_R); return FGS_ERR_ARG; }
+  return FGS_OK;
+}
+
+int fgs_sig_stage1(fgs_ctx *c, const double *es, int response, int split_p, int abs_flag,
+                   double *sums, long long *counts) {
+  if (!c || !es) return FGS_ERR_ARG;
+  FGS_TRY(use_device(c));
+  FGS_TRY(sig_check(c, response));
+  const int S = c->null_S;
+  DevBuf<double> d_es, d_sums; DevBuf<long long> d_counts;
+  auto body = [&]() -> int {
+    FGS_TRY(d_es.ensure(S)); FGS_TRY(d_sums.ensure((size_t)S * 4)); FGS_TRY(d_counts.ensure((size_t)S * 6));
+    FGS_TRY(h2d(c, d_es.p, es, S));
+    FGS_TRY(launch_sig_stage1(c, c->es_null.p, S, c->null_R, c->null_P, response, d_es.p, split_p,
+                              abs_flag, d_sums.p, d_counts.p));
+    FGS_TRY(d2h(c, sums, d_sums.p, (size_t)S * 4)); FGS_TRY(d2h(c, counts, d_counts.p, (size_t)S * 6));
+    return sync(c);
+  };
+  int rc = body();
+  d_es.release(); d_sums.release(); d_counts.release();
+  return rc;
+}
+
+int fgs_sig_stage2(fgs_ctx *c, const double *es, int response, int split_p, int calc_nes,
+                   int abs_flag, const double *sums_parts, int n_parts, const long long *counts_total,
+                   long long n_perm_total, double *p, double *p_high, double *p_low, double *nes,
+                   double *fwer, double *fdr_bh, long long *null_counts, long long *glob) {
+  if (!c || !es || !sums_parts || !counts_total || n_parts <= 0) return FGS_ERR_ARG;
+  FGS_TRY(use_device(c));
+  FGS_TRY(sig_check(c, response));
+  const int S = c->null_S;
+  DevBuf<double> d; DevBuf<long long> di;
+  auto body = [&]() -> int {
+    // doubles: es[S] parts[n_parts*S*4] p ph pl mpos mneg nes fwer fdr [8S]
+    FGS_TRY(d.ensure((size_t)S * (9 + 4 * (size_t)n_parts)));
+    FGS_TRY(di.ensure((size_t)S * 7 + 4));
+    double *d_es = d.p, *d_parts = d_es + S, *d_p = d_parts + (size_t)n_parts * S * 4, *d_ph = d_p + S,
+           *d_pl = d_ph + S, *d_mp = d_pl + S, *d_mn = d_mp + S, *d_nes = d_mn + S, *d_fw = d_nes + S,
+           *d_bh = d_fw + S;
+    long long *d_cnt = di.p, *d_nc = d_cnt + (size_t)S * 6, *d_gl = d_nc + S;
+    FGS_TRY(h2d(c, d_es, es, S));
+    FGS_TRY(h2d(c, d_parts, sums_parts, (size_t)n_parts * S * 4));
+    FGS_TRY(h2d(c, d_cnt, counts_total, (size_t)S * 6));
+    FGS_TRY(launch_sig_means(c, d_parts, n_parts, d_cnt, d_es, S, n_perm_total, split_p, calc_nes,
+                             abs_flag, d_p, d_ph, d_pl, d_mp, d_mn, d_nes, d_fw));
+    if (calc_nes)
+      FGS_TRY(launch_sig_stage2(c, c->es_null.p, S, c->null_R, c->null_P, response, d_es, abs_flag,
+                                d_mp, d_mn, d_nes, d_nc, d_gl));
+    FGS_TRY(d2h(c, p, d_p, S)); FGS_TRY(d2h(c, p_high, d_ph, S)); FGS_TRY(d2h(c, p_low, d_pl, S));
+    FGS_TRY(d2h(c, nes, d_nes, S)); FGS_TRY(d2h(c, fwer, d_fw, S));
+    if (calc_nes) { FGS_TRY(d2h(c, null_counts, d_nc, S)); FGS_TRY(d2h(c, glob, d_gl, 2)); }
+    else { FGS_TRY(launch_bh(c, d_p, S, d_bh)); FGS_TRY(d2h(c, fdr_bh, d_bh, S)); }
+    return sync(c);
+  };
+  int rc = body();
+  d.release(); di.release();
+  return rc;
+}
+
+int fgs_sig_finish(fgs_ctx *c, const double *nes, const long long *null_counts,
+                   const long long *glob, int n_sets, int abs_flag, double *fdr,
+                   long long *fdr_counts, long long *glob_counts) {
+  if (!c || !nes || !null_counts || !glob || n_sets <= 0) return FGS_ERR_ARG;
+  FGS_TRY(use_device(c));
+  const int S = n_sets;
+  DevBuf<double> d; DevBuf<long long> di;
+  auto body = [&]() -> int {
+    FGS_TRY(d.ensure((size_t)S * 2)); FGS_TRY(di.ensure((size_t)S * 3 + 8));
+    double *d_nes = d.p, *d_fdr = d_nes + S;
+    long long *d_nc = di.p, *d_gl = d_nc + S, *d_fc = d_gl + 2, *d_gc = d_fc + (size_t)S * 2;
+    FGS_TRY(h2d(c, d_nes, nes, S)); FGS_TRY(h2d(c, d_nc, null_counts, S)); FGS_TRY(h2d(c, d_gl, glob, 2));
+    FGS_TRY(launch_sig_finish(c, d_nes, d_nc, d_gl, S, abs_flag, d_fdr, d_fc, d_gc));
+    FGS_TRY(d2h(c, fdr, d_fdr, S)); FGS_TRY(d2h(c, fdr_counts, d_fc, (size_t)S * 2));
+    FGS_TRY(d2h(c, glob_counts, d_gc, 4));
+    return sync(c);
+  };
+  int rc = body();
+  d.release(); di.release();
+  return rc;
+}
+
+int fgs_calc_sig(fgs_ctx *c, const double *es, int response, int split_p, int calc_nes, int abs_flag,
+                 double *p, double *p_high, double *p_low, double *nes, double *fdr, double *fwer,
+                 long long *p_counts, long long *fdr_counts, long long *glob_counts) {
+  if (!c || !es) return FGS_ERR_ARG;
+  FGS_TRY(use_device(c));
+  FGS_TRY(sig_check(c, response));
+  const int S = c->null_S, P = c->null_P;
+  if (P == 0) return FGS_OK;  // R/flexgsea.R:575-577
+  DevBuf<double> d; DevBuf<long long> di;
+  auto body = [&]() -> int {
+    // doubles: es sums[4S] p ph pl mpos mneg nes fwer fdr
+    FGS_TRY(d.ensure((size_t)S * 13)); FGS_TRY(di.ensure((size_t)S * 9 + 8));
+    double *d_es = d.p, *d_sums = d_es + S, *d_p = d_sums + (size_t)S * 4, *d_ph = d_p + S, *d_pl = d_ph + S,
+           *d_mp = d_pl + S, *d_mn = d_mp + S, *d_nes = d_mn + S, *d_fw = d_nes + S, *d_fdr = d_fw + S;
+    long long *d_cnt = di.p, *d_nc = d_cnt + (size_t)S * 6, *d_gl = d_nc + S, *d_fc = d_gl + 2, *d_gc = d_fc + (size_t)S * 2;
+    FGS_TRY(h2d(c, d_es, es, S));
+    FGS_TRY(launch_sig_stage1(c, c->es_null.p, S, c->null_R, P, response, d_es, split_p, abs_flag, d_sums, d_cnt));
+    FGS_TRY(launch_sig_means(c, d_sums, 1, d_cnt, d_es, S, P, split_p, calc_nes, abs_flag, d_p, d_ph,
+                             d_pl, d_mp, d_mn, d_nes, d_fw));
+    if (calc_nes) {
+      FGS_TRY(launch_sig_stage2(c, c->es_null.p, S, c->null_R, P, response, d_es, abs_flag, d_mp, d_mn,
+                                d_nes, d_nc, d_gl));
+      FGS_TRY(launch_sig_finish(c, d_nes, d_nc, d_gl, S, abs_flag, d_fdr, d_fc, d_gc));
+    } else {
+      FGS_TRY(launch_bh(c, d_p, S, d_fdr));
+    }
+    FGS_TRY(d2h(c, p, d_p, S)); FGS_TRY(d2h(c, p_high, d_ph, S)); FGS_TRY(d2h(c, p_low, d_pl, S));
+    FGS_TRY(d2h(c, nes, d_nes, S)); FGS_TRY(d2h(c, fdr, d_fdr, S)); FGS_TRY(d2h(c, fwer, d_fw, S));
+    if (p_counts) {  // (numerator-1, denominator-1) of p, or (high, low) counts
+      std::vector<long long> h((size_t)S * 6);
+      FGS_TRY(d2h(c, h.data(), d_cnt, (size_t)S * 6));
+      FGS_TRY(sync(c));
+      for (int s = 0; s < S; s++) {
+        if (split_p) {
+          bool pos_side = (es[s] >= 0.0) || abs_flag;
+          p_counts[2 * s] = pos_side ? h[(size_t)s * 6 + 3] : h[(size_t)s * 6 + 4];
+          p_counts[2 * s + 1] = pos_side ? h[(size_t)s * 6 + 0] : h[(size_t)s * 6 + 2];
+        } else { p_counts[2 * s] = h[(size_t)s * 6 + 3]; p_counts[2 * s + 1] = h[(size_t)s * 6 + 4]; }
+      }
+    }
+    if (calc_nes) { FGS_TRY(d2h(c, fdr_counts, d_fc, (size_t)S * 2)); FGS_TRY(d2h(c, glob_counts, d_gc, 4)); }
+    return sync(c);
+  };
+  int rc = body();
+  d.release(); di.release();
+  return rc;
+}
+
+}  // extern "C"

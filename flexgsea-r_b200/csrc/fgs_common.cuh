@@ -1,0 +1,173 @@
+// Shared declarations of the flexgsea sm_100a library (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "flexgsea_b200.h"
+
+namespace fgs {
+
+void set_error(const char *fmt, ...);
+
+#define FGS_CUDA(call)                                                         \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      fgs::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,      \
+                     cudaGetErrorString(e__));                                 \
+      return e__ == cudaErrorMemoryAllocation ? FGS_ERR_OOM : FGS_ERR_CUDA;    \
+    }                                                                          \
+  } while (0)
+
+#define FGS_TRY(call)                  \
+  do {                                 \
+    int rc__ = (call);                 \
+    if (rc__ != FGS_OK) return rc__;   \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;  // capacity in elements
+  int ensure(size_t want) {
+    if (want <= n) return FGS_OK;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc of %zu bytes failed: %s", want * sizeof(T), cudaGetErrorString(e));
+      cudaGetLastError();
+      return FGS_ERR_OOM;
+    }
+    n = want;
+    return FGS_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+// error bits accumulated on the device during a run
+enum : int { FLAG_POS_INF = 1, FLAG_NEG_INF = 2, FLAG_NAN = 4 };
+
+}  // namespace fgs
+
+struct fgs_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 0;
+  int smem_optin = 0;  // max dynamic shared memory per block
+  long long launches = 0;
+  bool profiling = false;
+  float last_ms[5] = {0, 0, 0, 0, 0};
+  long long last_launches[5] = {0, 0, 0, 0, 0};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+  // options
+  int opt_perm_block = 0;      // 0 = auto
+  int opt_force_generic = 0;
+  int opt_score_ppt = 0;
+
+  // expression matrix x [n x G] (gene's samples contiguous)
+  int n = 0, G = 0;
+  fgs::DevBuf<double> x;
+  fgs::DevBuf<double> gene_sd;  // sd(x[,g]) for lm
+  bool gene_sd_valid = false;
+
+  // gene sets
+  int S = 0;
+  long long nnz = 0;
+  int max_set = 0;
+  fgs::DevBuf<int> set_off;        // [S+1]
+  fgs::DevBuf<int> set_idx;        // [nnz] 0-based gene ids
+  fgs::DevBuf<int> set_order;      // [S] set ids by descending size
+  fgs::DevBuf<unsigned char> set_slow;  // [S] 1 = duplicates or too large for the bitmap kernel
+  std::vector<int> h_set_off;
+  int n_slow = 0;
+  fgs::DevBuf<int> slow_ids;       // [n_slow]
+
+  // s2n response: y_bin [n x R]
+  int s2n_R = 0;
+  fgs::DevBuf<int> ybin;
+  fgs::DevBuf<int> n1n2;  // [R][2]
+  // lm response
+  int lm_q = 0, lm_R = 0, lm_icpt = 0;
+  fgs::DevBuf<double> lm_H;  // [R x n] rows of R^-1 Q^T for the scored columns
+  std::vector<double> h_design;
+
+  // permutation machinery
+  fgs::DevBuf<int> perm;          // [n x Pb] 1-based
+  fgs::DevBuf<uint32_t> labels;   // [Pb*R][2][W]
+  fgs::DevBuf<double> lm_B;       // [n x Cb] permuted design block
+
+  // per-block scratch
+  fgs::DevBuf<double> scores;     // [Cb][G]
+  fgs::DevBuf<uint16_t> rank16;   // [Cb][G] 1-based descending rank
+  fgs::DevBuf<double> sabs;       // [Cb][G] |score|^p in rank order
+  fgs::DevBuf<unsigned long long> sort_keys;  // ping-pong scratch
+  fgs::DevBuf<uint32_t> sort_idx;
+  fgs::DevBuf<int> flags;         // per-perm non-finite flags + [last] global
+  fgs::DevBuf<int> counters;      // work counters
+  long long last_cols = 0;        // columns held by scores/rank16 (debug taps)
+  int last_G = 0;
+
+  // resident null distribution es_null [S, R, P]
+  fgs::DevBuf<double> es_null;
+  int null_S = 0, null_R = 0, null_P = 0;
+
+  // significance scratch
+  fgs::DevBuf<double> sig_d;
+  fgs::DevBuf<long long> sig_i;
+};
+
+namespace fgs {
+
+// ---- kernel launch wrappers (each returns FGS_OK / error) ------------------
+// K1
+int launch_philox_perm(fgs_ctx *c, unsigned long long seed, long long perm_id0, int n, int P,
+                       int *d_perm);
+int launch_labels(fgs_ctx *c, const int *d_perm, const int *d_ybin, int n, int R, int P,
+                  uint32_t *d_labels);
+// K2'
+int launch_s2n(fgs_ctx *c, const double *d_x, int n, int G, const uint32_t *d_labels,
+               const int *d_n1n2, int R, long long C, double *d_scores, int *d_flags);
+int launch_s2n_patch(fgs_ctx *c, double *d_scores, int G, int R, int P, int *d_flags);
+// K2 (lm)
+int launch_lm_build_B(fgs_ctx *c, const double *d_H, const int *d_perm, int n, int R, int P,
+                      double *d_B);
+int launch_lm_gemm(fgs_ctx *c, const double *d_x, int n, int G, const double *d_B, long long C,
+                   const double *d_gene_sd, double *d_scores, int *d_flags, int R);
+int launch_gene_sd(fgs_ctx *c, const double *d_x, int n, int G, double *d_sd);
+// generic helpers
+int launch_check_finite(fgs_ctx *c, const double *d_v, long long len, long long per_flag,
+                        int *d_flags);
+int launch_abs_inplace(fgs_ctx *c, double *d_v, long long len);
+// K3
+int launch_sort(fgs_ctx *c, const double *d_scores, int G, long long C, int abs_flag, double p_exp,
+                uint16_t *d_rank16, double *d_sabs);
+// K4 / K5
+int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
+                  double *d_es /* [C][S] */);
+int launch_es_wks_generic(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G,
+                          long long C, const int *d_set_ids, int n_ids, double *d_es);
+int launch_es_mean(fgs_ctx *c, const double *d_scores, int G, long long C, int es_kind,
+                   int abs_flag, double *d_es);
+int launch_observed_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, int R,
+                        double *d_es, double *d_max_es_at, double *d_le_prop, int *d_at,
+                        double *d_pos, double *d_neg, int *d_le_first, int *d_le_count);
+// K6 / K7
+int launch_sig_stage1(fgs_ctx *c, const double *d_null, int S, int R, int P, int response,
+                      const double *d_es, int split_p, int abs_flag, double *d_sums,
+                      long long *d_counts);
+int launch_sig_stage2(fgs_ctx *c, const double *d_null, int S, int R, int P, int response,
+                      const double *d_es, int abs_flag, const double *d_mpos, const double *d_mneg,
+                      double *d_nes, long long *d_null_counts, long long *d_glob);
+int launch_sig_finish(fgs_ctx *c, const double *d_nes, const long long *d_null_counts,
+                      const long long *d_glob, int S, int abs_flag, double *d_fdr,
+                      long long *d_fdr_counts, long long *d_glob_counts);
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+// row pitch (elements) of the per-column rank16 / sabs arrays: 16-byte aligned rows
+__host__ __device__ inline size_t pitch_of(int G) { return ((size_t)G + 7) & ~(size_t)7; }
+
+}  // namespace fgs

@@ -1,0 +1,99 @@
+// K1: permutation draw and permuted class labels.
+//
+// Replaces `y.perm <- y[sample.int(nrow(y)), , drop=F]` of the reference
+// (R/flexgsea.R:384, :443).  Either an R-made permutation matrix is used as is
+// (same RNG stream as the reference), or each permutation is drawn on the
+// device: Fisher-Yates driven by Philox4x32-10 keyed by (seed, global
+// permutation id), so results do not depend on how permutations are sharded.
+#include "fgs_common.cuh"
+
+namespace fgs {
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+// one thread per permutation; the permutation lives in its column of d_perm
+__global__ void philox_perm_kernel(unsigned long long seed, long long perm_id0, int n, int P,
+                                   int *__restrict__ perm) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  int *a = perm + (size_t)p * n;
+  for (int i = 0; i < n; i++) a[i] = i + 1;
+  unsigned long long id = (unsigned long long)(perm_id0 + p);
+  uint32_t buf[4];
+  int have = 0;
+  uint32_t chunk = 0;
+  for (int i = n - 1; i >= 1; i--) {
+    if (!have) {
+      buf[0] = chunk++; buf[1] = 0; buf[2] = (uint32_t)id; buf[3] = (uint32_t)(id >> 32);
+      philox4x32_10(buf, (uint32_t)seed, (uint32_t)(seed >> 32));
+      have = 4;
+    }
+    uint32_t u = buf[4 - have];
+    have--;
+    uint32_t j = __umulhi(u, (uint32_t)(i + 1));
+    int t = a[i]; a[i] = a[j]; a[j] = t;
+  }
+}
+
+int launch_philox_perm(fgs_ctx *c, unsigned long long seed, long long perm_id0, int n, int P,
+                       int *d_perm) {
+  if (P <= 0) return FGS_OK;
+  philox_perm_kernel<<<ceil_div(P, 128), 128, 0, c->stream>>>(seed, perm_id0, n, P, d_perm);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
+}
+
+// labels[col][0][w] = class-1 mask, labels[col][1][w] = class-2 mask of the
+// permuted y_bin column; col = p * R + r.  NA_LOGICAL samples are in neither
+// mask (src/ggsea.cpp:29).  One warp per column.  A permutation entry outside
+// [1, n] raises flag bit 8 in *bad.
+__global__ void labels_kernel(const int *__restrict__ perm, const int *__restrict__ ybin, int n,
+                              int R, long long C, int W, uint32_t *__restrict__ labels,
+                              int *__restrict__ bad) {
+  long long col = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (col >= C) return;
+  long long p = col / R;
+  int r = (int)(col % R);
+  const int *pi = perm ? perm + (size_t)p * n : nullptr;
+  const int *yc = ybin + (size_t)r * n;
+  for (int wb = 0; wb < W; wb++) {
+    int i = wb * 32 + lane;
+    int v = INT_MIN;
+    if (i < n) {
+      int src = pi ? pi[i] - 1 : i;
+      if (src < 0 || src >= n) { atomicOr(bad, 8); src = 0; }
+      v = yc[src];
+    }
+    uint32_t m1 = __ballot_sync(0xffffffffu, v != INT_MIN && v != 0);
+    uint32_t m2 = __ballot_sync(0xffffffffu, v != INT_MIN && v == 0);
+    if (lane == 0) {
+      labels[(col * 2 + 0) * W + wb] = m1;
+      labels[(col * 2 + 1) * W + wb] = m2;
+    }
+  }
+}
+
+int launch_labels(fgs_ctx *c, const int *d_perm, const int *d_ybin, int n, int R, int P,
+                  uint32_t *d_labels) {
+  long long C = (long long)P * R;
+  if (C <= 0) return FGS_OK;
+  int W = (n + 31) / 32;
+  labels_kernel<<<ceil_div(C, 8), 256, 0, c->stream>>>(d_perm, d_ybin, n, R, C, W, d_labels,
+                                                       c->flags.p + (c->flags.n - 1));
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
+}
+
+}  // namespace fgs

@@ -1,0 +1,469 @@
+// K6 / K7: significance of the observed ES against the resident null.
+//
+// Replaces flexgsea_calc_sig (R/flexgsea.R:564-629), calc_fdr_nes (:500-533),
+// adj_fdr_nes (:474-498) and flexgsea_calc_sig_simple (:544-547).
+//
+// The reference's pooled FDR is O(S^2 P): every set rescans the whole S x P
+// null-NES matrix (:512-528).  Here the null is streamed ONCE: each null value
+// is normalised on the fly (:619-621) and binary-searched into the sorted
+// observed NES; exact integer histogram counts + a suffix/prefix sum give every
+// set's exceedance count.  All counts are integers, so the result is
+// independent of thread order.  Per-set sums of the null (for the NES means,
+// :602-616) are accumulated in double-double and combined in a fixed order, so
+// the means round like R's long-double mean() and are reproducible across any
+// split of the permutations over chunks or GPUs.
+#include "fgs_common.cuh"
+
+namespace fgs {
+
+struct dd { double hi, lo; };
+__device__ __forceinline__ dd dd_add_d(dd a, double b) {
+  double s = __dadd_rn(a.hi, b);
+  double bb = __dsub_rn(s, a.hi);
+  double e = __dadd_rn(__dsub_rn(a.hi, __dsub_rn(s, bb)), __dsub_rn(b, bb));
+  e = __dadd_rn(e, a.lo);
+  double hi = __dadd_rn(s, e);
+  double lo = __dsub_rn(e, __dsub_rn(hi, s));
+  return {hi, lo};
+}
+__device__ __forceinline__ dd dd_add_dd(dd a, dd b) {
+  dd r = dd_add_d(a, b.hi);
+  return dd_add_d(r, b.lo);
+}
+// (hi + lo) / n rounded to double
+__device__ __forceinline__ double dd_div_n(dd a, double n) {
+  double q = a.hi / n;
+  double r = fma(-q, n, a.hi) + a.lo;
+  return q + r / n;
+}
+
+constexpr int SIG_NF = 4;  // sums per set: pos hi, pos lo, neg hi, neg lo
+constexpr int SIG_NC = 6;  // counts per set
+
+// ---- stage 1: per-set partials over a chunk of permutations -----------------
+__global__ void __launch_bounds__(128)
+sig_partial_kernel(const double *__restrict__ null, int S, int R, int P, int resp,
+                   const double *__restrict__ es, int split_p, int abs_flag, int chunk_len,
+                   double *__restrict__ psums /* [nchunk][S][4] */,
+                   long long *__restrict__ pcounts /* [nchunk][S][6] */) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int chunk = blockIdx.y;
+  const int p0 = chunk * chunk_len, p1 = min(P, p0 + chunk_len);
+  const double e = es[s];
+  const bool pos_side = (e >= 0.0) || abs_flag;
+  dd sp = {0.0, 0.0}, sn = {0.0, 0.0};
+  long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+  const double *base = null + (size_t)s + (size_t)S * resp;
+  const size_t stride = (size_t)S * R;
+  for (int p = p0; p < p1; p++) {
+    const double v = base[stride * p];
+    if (v >= 0.0) { c0++; sp = dd_add_d(sp, v); }
+    if (v < 0.0) { c1++; sn = dd_add_d(sn, v); }
+    if (v <= 0.0) c2++;
+    if (split_p) {  // :579-587
+      if (pos_side) { if (v >= 0.0 && e <= v) c3++; }
+      else { if (v <= 0.0 && e >= v) c4++; }
+    } else {        // :589-597
+      if (e <= v) c3++;
+      if (e >= v) c4++;
+    }
+  }
+  double *ps = psums + ((size_t)chunk * S + s) * SIG_NF;
+  ps[0] = sp.hi; ps[1] = sp.lo; ps[2] = sn.hi; ps[3] = sn.lo;
+  long long *pc = pcounts + ((size_t)chunk * S + s) * SIG_NC;
+  pc[0] = c0; pc[1] = c1; pc[2] = c2; pc[3] = c3; pc[4] = c4; pc[5] = 0;
+}
+
+__global__ void sig_combine_kernel(const double *__restrict__ psums,
+                                   const long long *__restrict__ pcounts, int S, int nchunk,
+                                   double *__restrict__ sums, long long *__restrict__ counts) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  dd sp = {0.0, 0.0}, sn = {0.0, 0.0};
+  long long c[SIG_NC] = {0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < nchunk; k++) {  // fixed order
+    const double *ps = psums + ((size_t)k * S + s) * SIG_NF;
+    sp = dd_add_dd(sp, {ps[0], ps[1]});
+    sn = dd_add_dd(sn, {ps[2], ps[3]});
+    const long long *pc = pcounts + ((size_t)k * S + s) * SIG_NC;
+    for (int i = 0; i < SIG_NC; i++) c[i] += pc[i];
+  }
+  if (sums) { double *o = sums + (size_t)s * SIG_NF; o[0] = sp.hi; o[1] = sp.lo; o[2] = sn.hi; o[3] = sn.lo; }
+  if (counts) for (int i = 0; i < SIG_NC; i++) counts[(size_t)s * SIG_NC + i] = c[i];
+}
+
+int launch_sig_stage1(fgs_ctx *c, const double *d_null, int S, int R, int P, int response,
+                      const double *d_es, int split_p, int abs_flag, double *d_sums,
+                      long long *d_counts) {
+  int nchunk = P / 64;
+  int want = (c->num_sms * 16 * 128) / (S > 0 ? S : 1) + 1;
+  if (nchunk > want) nchunk = want;
+  if (nchunk < 1) nchunk = 1;
+  if (nchunk > 1024) nchunk = 1024;
+  int chunk_len = (P + nchunk - 1) / nchunk;
+  if (chunk_len < 1) chunk_len = 1;
+  nchunk = P > 0 ? (P + chunk_len - 1) / chunk_len : 1;
+  FGS_TRY(c->sig_d.ensure((size_t)nchunk * S * SIG_NF));
+  FGS_TRY(c->sig_i.ensure((size_t)nchunk * S * SIG_NC));
+  dim3 grid(ceil_div(S, 128), nchunk);
+  sig_partial_kernel<<<grid, 128, 0, c->stream>>>(d_null, S, R, P, response, d_es, split_p,
+                                                  abs_flag, chunk_len, c->sig_d.p, c->sig_i.p);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  sig_combine_kernel<<<ceil_div(S, 128), 128, 0, c->stream>>>(c->sig_d.p, c->sig_i.p, S, nchunk,
+                                                              d_sums, d_counts);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
+}
+
+// ---- means, p-values, NES, FWER from combined sums / counts ----------------
+// sums_parts [nparts][S][4] (one part per GPU, combined here in part order),
+// counts [S][6] (already summed).  Outputs [S].
+__global__ void sig_means_kernel(const double *__restrict__ sums_parts, int nparts,
+                                 const long long *__restrict__ counts,
+                                 const double *__restrict__ es, int S, long long P_total,
+                                 int split_p, int calc_nes, int abs_flag, double *__restrict__ p_out,
+                                 double *__restrict__ p_high, double *__restrict__ p_low,
+                                 double *__restrict__ mpos_out, double *__restrict__ mneg_out,
+                                 double *__restrict__ nes_out, double *__restrict__ fwer_out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const double e = es[s];
+  const long long *c = counts + (size_t)s * SIG_NC;
+  double p;
+  if (split_p) {
+    if ((e >= 0.0) || abs_flag) p = (double)(c[3] + 1) / (double)(c[0] + 1);  // :580-582
+    else p = (double)(c[4] + 1) / (double)(c[2] + 1);                         // :584-585
+    p_high[s] = nan(""); p_low[s] = nan("");
+  } else {
+    const double ph = (double)(c[3] + 1) / (double)(P_total + 1);             // :590
+    const double pl = (double)(c[4] + 1) / (double)(P_total + 1);             // :596
+    p_high[s] = ph;
+    if (abs_flag) { p = ph; p_low[s] = nan(""); }
+    else { p_low[s] = pl; p = fmin(fmin(pl, ph) * 2, 1.0); }                  // :598
+  }
+  p_out[s] = p;
+  fwer_out[s] = fmin(p * (double)S, 1.0);                                     // :627
+  if (calc_nes) {
+    dd sp = {0.0, 0.0}, sn = {0.0, 0.0};
+    for (int k = 0; k < nparts; k++) {
+      const double *ps = sums_parts + ((size_t)k * S + s) * SIG_NF;
+      sp = dd_add_dd(sp, {ps[0], ps[1]});
+      sn = dd_add_dd(sn, {ps[2], ps[3]});
+    }
+    double mp = c[0] > 0 ? dd_div_n(sp, (double)c[0]) : nan("");              // :602
+    if (isnan(mp) && e >= 0.0) mp = e;                                        // :603-604
+    double mg = c[1] > 0 ? dd_div_n(sn, (double)c[1]) : nan("");              // :612-614
+    if (isnan(mg) && e < 0.0) mg = e;                                         // :615-616
+    mpos_out[s] = mp; mneg_out[s] = mg;
+    nes_out[s] = abs_flag ? e / mp : e / (e >= 0.0 ? mp : -mg);               // :607, :617-618
+  } else {
+    mpos_out[s] = nan(""); mneg_out[s] = nan(""); nes_out[s] = nan("");
+  }
+}
+
+// ---- ordering helper: stable position of every element within its group ----
+// group(i) in {0 = none, 1, 2}; position among same-group elements by
+// (key ascending, index ascending).  O(S^2) compares, one thread per element.
+__global__ void group_rank_kernel(const double *__restrict__ key, const int *__restrict__ group,
+                                  int n, int *__restrict__ pos, int *__restrict__ group_n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int gi = group[i];
+  const double ki = key[i];
+  int r = 0, tot = 0;
+  for (int j = 0; j < n; j++) {
+    if (group[j] != gi) continue;
+    tot++;
+    const double kj = key[j];
+    r += (kj < ki) || (kj == ki && j < i);
+  }
+  pos[i] = r;
+  if (gi > 0) group_n[gi] = tot;  // same value from every thread of the group
+}
+
+// thresholds for the pooled-FDR count: group 1 = sets compared with '>'
+// (nes >= 0, or abs; :518), group 2 = sets compared with '<'; NaN -> none
+__global__ void fdr_groups_kernel(const double *__restrict__ nes, int S, int abs_flag,
+                                  int *__restrict__ group) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S) return;
+  const double v = nes[i];
+  group[i] = isnan(v) ? 0 : (((v >= 0.0) || abs_flag) ? 1 : 2);
+}
+__global__ void scatter_sorted_kernel(const double *__restrict__ key, const int *__restrict__ group,
+                                      const int *__restrict__ pos, int n,
+                                      double *__restrict__ sorted1, int *__restrict__ id1,
+                                      double *__restrict__ sorted2, int *__restrict__ id2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (group[i] == 1) { sorted1[pos[i]] = key[i]; id1[pos[i]] = i; }
+  else if (group[i] == 2) { sorted2[pos[i]] = key[i]; id2[pos[i]] = i; }
+}
+
+// ---- stage 2: one streaming pass over the local null -------------------------
+// hist1[b] += 1 where b = #{thresholds1 <  v'};  set at sorted position j gets
+//   #{v' > t_j} = sum_{b > j} hist1[b]
+// hist2[b] += 1 where b = #{thresholds2 <= v'}; set at sorted position j gets
+//   #{v' < t_j} = sum_{b <= j} hist2[b]
+template <bool T_SMEM>
+__global__ void __launch_bounds__(256)
+fdr_count_kernel(const double *__restrict__ null, int S, int R, int P, int resp, int abs_flag,
+                 const double *__restrict__ mpos, const double *__restrict__ mneg,
+                 const double *__restrict__ t1, int n1, const double *__restrict__ t2, int n2,
+                 int chunk_len, unsigned long long *__restrict__ hist1,
+                 unsigned long long *__restrict__ hist2, unsigned long long *__restrict__ glob) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double *st1 = (double *)smem;
+  double *st2 = st1 + (T_SMEM ? n1 : 0);
+  unsigned int *h1 = (unsigned int *)(st2 + (T_SMEM ? n2 : 0));
+  unsigned int *h2 = h1 + (n1 + 1);
+  for (int i = threadIdx.x; i < n1 + n2 + 2; i += blockDim.x) h1[i] = 0;
+  if (T_SMEM) {
+    for (int i = threadIdx.x; i < n1; i += blockDim.x) st1[i] = t1[i];
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) st2[i] = t2[i];
+  }
+  __syncthreads();
+  const double *a1 = T_SMEM ? st1 : t1, *a2 = T_SMEM ? st2 : t2;
+  const int p0 = blockIdx.y * chunk_len, p1 = min(P, p0 + chunk_len);
+  unsigned long long gpos = 0, gneg = 0;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+    const double mp = mpos[s], mg = mneg[s];
+    const double *base = null + (size_t)s + (size_t)S * resp;
+    const size_t stride = (size_t)S * R;
+    for (int p = p0; p < p1; p++) {
+      const double v = base[stride * p];
+      const double nv = abs_flag ? v / mp : v / (v >= 0.0 ? mp : -mg);  // :608-610, :619-621
+      if (nv > 0.0) gpos++;                                             // :503
+      if (nv < 0.0) gneg++;                                             // :504
+      if (isnan(nv)) continue;
+      if (n1 > 0 && nv > a1[0]) {  // #{t1 < nv}: lower bound
+        int lo = 0, hi = n1;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (a1[mid] < nv) lo = mid + 1; else hi = mid; }
+        atomicAdd(&h1[lo], 1u);
+      }
+      if (n2 > 0 && nv < a2[n2 - 1]) {  // #{t2 <= nv}: upper bound
+        int lo = 0, hi = n2;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (a2[mid] <= nv) lo = mid + 1; else hi = mid; }
+        atomicAdd(&h2[lo], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= n1; i += blockDim.x) if (h1[i]) atomicAdd(&hist1[i], (unsigned long long)h1[i]);
+  for (int i = threadIdx.x; i <= n2; i += blockDim.x) if (h2[i]) atomicAdd(&hist2[i], (unsigned long long)h2[i]);
+  for (int o = 16; o; o >>= 1) {
+    gpos += __shfl_xor_sync(0xffffffffu, gpos, o);
+    gneg += __shfl_xor_sync(0xffffffffu, gneg, o);
+  }
+  if ((threadIdx.x & 31) == 0) { if (gpos) atomicAdd(&glob[0], gpos); if (gneg) atomicAdd(&glob[1], gneg); }
+}
+
+// histogram -> per-set exceedance counts (single CTA; n <= a few 10^4)
+__global__ void hist_to_counts_kernel(const unsigned long long *__restrict__ hist1, const int *id1,
+                                      int n1, const unsigned long long *__restrict__ hist2,
+                                      const int *id2, int n2, int S,
+                                      long long *__restrict__ null_counts) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int j = n1 - 1; j >= 0; j--) { run += hist1[j + 1]; null_counts[id1[j]] = (long long)run; }
+  }
+  if (threadIdx.x == 32 && blockIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int j = 0; j < n2; j++) { run += hist2[j]; null_counts[id2[j]] = (long long)run; }
+  }
+}
+
+// ---- finish: raw FDR + monotone adjustment ----------------------------------
+__global__ void fdr_raw_kernel(const double *__restrict__ nes, const long long *__restrict__ null_counts,
+                               const long long *__restrict__ glob, int S, int abs_flag,
+                               double *__restrict__ fdr, long long *__restrict__ fdr_counts,
+                               long long *__restrict__ glob_counts, int *__restrict__ adj_group) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S) return;
+  const double v = nes[i];
+  long long cp = 0, cn = 0, a = 0;
+  const bool pos_side = (v >= 0.0) || abs_flag;
+  for (int j = 0; j < S; j++) {
+    const double w = nes[j];
+    cp += w > 0.0; cn += w < 0.0;                     // :501-502
+    a += pos_side ? (w > v) : (w < v);                // :519, :523
+  }
+  const long long b = null_counts[i];
+  double rel, rel_null;
+  if (pos_side) { rel = (double)(a + 1) / (double)cp; rel_null = (double)(b + 1) / (double)glob[0]; }
+  else { rel = (double)(a + 1) / (double)cn; rel_null = (double)(b + 1) / (double)glob[1]; }
+  if (isnan(v)) rel = nan("");
+  fdr[i] = rel_null / rel;                            // :527
+  if (fdr_counts) { fdr_counts[2 * i] = a; fdr_counts[2 * i + 1] = b; }
+  if (i == 0 && glob_counts) { glob_counts[0] = cp; glob_counts[1] = cn; glob_counts[2] = glob[0]; glob_counts[3] = glob[1]; }
+  adj_group[i] = isnan(v) ? 0 : (v >= 0.0 ? 1 : 2);   // adj_fdr_nes splits on nes >= 0 only (:477, :488)
+}
+__global__ void negate_group2_kernel(const double *__restrict__ nes, const int *__restrict__ group,
+                                     int S, double *__restrict__ key) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S) return;
+  // group 1: increasing NES (:478); group 2: decreasing NES (:489) == increasing -NES
+  key[i] = group[i] == 2 ? -nes[i] : nes[i];
+}
+// inclusive prefix-min in the given order, start value `init`; single CTA.
+// vals[id[k]] is visited for k = 0..n-1 and overwritten with the running min.
+__global__ void __launch_bounds__(1024)
+ordered_prefix_min_kernel(double *__restrict__ vals, const int *__restrict__ group,
+                          const int *__restrict__ pos, int S, int which, int n, double init,
+                          int *__restrict__ order_scratch) {
+  __shared__ double cmin[1024];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < S; i += blockDim.x) if (group[i] == which) order_scratch[pos[i]] = i;
+  __syncthreads();
+  const int per = (n + blockDim.x - 1) / blockDim.x;
+  const int k0 = tid * per, k1 = min(n, k0 + per);
+  double m = INFINITY;
+  for (int k = k0; k < k1; k++) m = fmin(m, vals[order_scratch[k]]);
+  cmin[tid] = m;
+  __syncthreads();
+  double run = init;
+  for (int t = 0; t < tid; t++) run = fmin(run, cmin[t]);
+  for (int k = k0; k < k1; k++) {
+    const int i = order_scratch[k];
+    const double v = vals[i];
+    if (v <= run) run = v; else vals[i] = run;  // :479-483 (NaN never passes '<=')
+  }
+}
+
+// BH (p.adjust(p, 'BH'), R/flexgsea.R:625): o = order(p, decreasing=TRUE);
+// pmin(1, cummin(n / (n:1) * p[o]))[order(o)]
+__global__ void bh_prepare_kernel(const double *__restrict__ p, int n, double *__restrict__ key,
+                                  int *__restrict__ group) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  key[i] = -p[i];  // decreasing p == increasing -p, ties by index
+  group[i] = 1;
+}
+__global__ void bh_scale_kernel(const double *__restrict__ p, const int *__restrict__ pos, int n,
+                                double *__restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  vals[i] = ((double)n / (double)(n - pos[i])) * p[i];
+}
+__global__ void clamp1_kernel(double *__restrict__ v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = fmin(v[i], 1.0);
+}
+
+int launch_sig_means(fgs_ctx *c, const double *d_sums_parts, int nparts, const long long *d_counts,
+                     const double *d_es, int S, long long P_total, int split_p, int calc_nes,
+                     int abs_flag, double *d_p, double *d_ph, double *d_pl, double *d_mpos,
+                     double *d_mneg, double *d_nes, double *d_fwer) {
+  sig_means_kernel<<<ceil_div(S, 128), 128, 0, c->stream>>>(d_sums_parts, nparts, d_counts, d_es, S,
+                                                            P_total, split_p, calc_nes, abs_flag,
+                                                            d_p, d_ph, d_pl, d_mpos, d_mneg, d_nes,
+                                                            d_fwer);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
+}
+
+// work layout (ints / doubles / u64) carved by the caller
+int launch_sig_stage2(fgs_ctx *c, const double *d_null, int S, int R, int P, int response,
+                      const double *d_es, int abs_flag, const double *d_mpos, const double *d_mneg,
+                      double *d_nes, long long *d_null_counts, long long *d_glob) {
+  (void)d_es;
+  // scratch: group[S], pos[S], gn[4], id1[S], id2[S] (ints); t1[S], t2[S] (doubles);
+  // hist1[S+1], hist2[S+1] (u64)
+  FGS_TRY(c->counters.ensure((size_t)4 * S + 8));
+  int *group = c->counters.p, *pos = group + S, *id1 = pos + S, *id2 = id1 + S, *gn = id2 + S;
+  FGS_TRY(c->sig_d.ensure((size_t)2 * S + 2));
+  double *t1 = c->sig_d.p, *t2 = t1 + S;
+  FGS_TRY(c->sig_i.ensure((size_t)2 * S + 4));
+  unsigned long long *h1 = (unsigned long long *)c->sig_i.p, *h2 = h1 + S + 1;
+  FGS_CUDA(cudaMemsetAsync(gn, 0, 4 * sizeof(int), c->stream));
+  FGS_CUDA(cudaMemsetAsync(h1, 0, (size_t)(2 * S + 2) * sizeof(unsigned long long), c->stream));
+  FGS_CUDA(cudaMemsetAsync(d_glob, 0, 2 * sizeof(long long), c->stream));
+  FGS_CUDA(cudaMemsetAsync(d_null_counts, 0, (size_t)S * sizeof(long long), c->stream));
+  const int nb = ceil_div(S, 128);
+  fdr_groups_kernel<<<nb, 128, 0, c->stream>>>(d_nes, S, abs_flag, group);
+  group_rank_kernel<<<nb, 128, 0, c->stream>>>(d_nes, group, S, pos, gn);
+  scatter_sorted_kernel<<<nb, 128, 0, c->stream>>>(d_nes, group, pos, S, t1, id1, t2, id2);
+  c->launches += 3;
+  FGS_CUDA(cudaGetLastError());
+  int h_gn[4];
+  FGS_CUDA(cudaMemcpyAsync(h_gn, gn, sizeof(h_gn), cudaMemcpyDeviceToHost, c->stream));
+  FGS_CUDA(cudaStreamSynchronize(c->stream));
+  const int n1 = h_gn[1], n2 = h_gn[2];
+  if (P > 0) {
+    int gx = ceil_div(S, 256);
+    int gy = (c->num_sms * 8) / gx + 1;
+    if (gy > P) gy = P;
+    int chunk_len = (P + gy - 1) / gy;
+    gy = (P + chunk_len - 1) / chunk_len;
+    size_t smem_t = (size_t)(n1 + n2) * 8 + (size_t)(n1 + n2 + 2) * 4;
+    size_t smem_h = (size_t)(n1 + n2 + 2) * 4;
+    dim3 grid(gx, gy);
+    if (smem_t <= (size_t)c->smem_optin / 2) {
+      auto k = fdr_count_kernel<true>;
+      FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      k<<<grid, 256, smem_t, c->stream>>>(d_null, S, R, P, response, abs_flag, d_mpos, d_mneg, t1, n1,
+                                          t2, n2, chunk_len, h1, h2, (unsigned long long *)d_glob);
+    } else {
+      auto k = fdr_count_kernel<false>;
+      FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+      k<<<grid, 256, smem_h, c->stream>>>(d_null, S, R, P, response, abs_flag, d_mpos, d_mneg, t1, n1,
+                                          t2, n2, chunk_len, h1, h2, (unsigned long long *)d_glob);
+    }
+    c->launches++;
+    FGS_CUDA(cudaGetLastError());
+  }
+  hist_to_counts_kernel<<<1, 64, 0, c->stream>>>(h1, id1, n1, h2, id2, n2, S, d_null_counts);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
+}
+
+int launch_sig_finish(fgs_ctx *c, const double *d_nes, const long long *d_null_counts,
+                      const long long *d_glob, int S, int abs_flag, double *d_fdr,
+                      long long *d_fdr_counts, long long *d_glob_counts) {
+  FGS_TRY(c->counters.ensure((size_t)4 * S + 8));
+  int *group = c->counters.p, *pos = group + S, *order = pos + S, *gn = order + S + S;
+  FGS_TRY(c->sig_d.ensure((size_t)2 * S + 2));
+  double *key = c->sig_d.p;
+  const int nb = ceil_div(S, 128);
+  FGS_CUDA(cudaMemsetAsync(gn, 0, 4 * sizeof(int), c->stream));
+  fdr_raw_kernel<<<nb, 128, 0, c->stream>>>(d_nes, d_null_counts, d_glob, S, abs_flag, d_fdr,
+                                            d_fdr_counts, d_glob_counts, group);
+  negate_group2_kernel<<<nb, 128, 0, c->stream>>>(d_nes, group, S, key);
+  group_rank_kernel<<<nb, 128, 0, c->stream>>>(key, group, S, pos, gn);
+  c->launches += 3;
+  FGS_CUDA(cudaGetLastError());
+  int h_gn[4];
+  FGS_CUDA(cudaMemcpyAsync(h_gn, gn, sizeof(h_gn), cudaMemcpyDeviceToHost, c->stream));
+  FGS_CUDA(cudaStreamSynchronize(c->stream));
+  for (int which = 1; which <= 2; which++) {
+    if (h_gn[which] <= 0) continue;
+    ordered_prefix_min_kernel<<<1, 1024, 0, c->stream>>>(d_fdr, group, pos, S, which, h_gn[which],
+                                                         1.0, order);
+    c->launches++;
+  }
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
+}
+
+int launch_bh(fgs_ctx *c, const double *d_p, int S, double *d_fdr) {
+  FGS_TRY(c->counters.ensure((size_t)4 * S + 8));
+  int *group = c->counters.p, *pos = group + S, *order = pos + S, *gn = order + S + S;
+  FGS_TRY(c->sig_d.ensure((size_t)2 * S + 2));
+  double *key = c->sig_d.p;
+  const int nb = ceil_div(S, 128);
+  bh_prepare_kernel<<<nb, 128, 0, c->stream>>>(d_p, S, key, group);
+  group_rank_kernel<<<nb, 128, 0, c->stream>>>(key, group, S, pos, gn);
+  bh_scale_kernel<<<nb, 128, 0, c->stream>>>(d_p, pos, S, d_fdr);
+  ordered_prefix_min_kernel<<<1, 1024, 0, c->stream>>>(d_fdr, group, pos, S, 1, S, INFINITY, order);
+  clamp1_kernel<<<nb, 128, 0, c->stream>>>(d_fdr, S);
+  c->launches += 5;
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
+}
+
+}  // namespace fgs

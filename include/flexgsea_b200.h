@@ -1,0 +1,178 @@
+/*
+ * flexgsea_b200.h -- C ABI of the sm_100a library that replaces flexgsea's
+ * sample-permutation enrichment loop.
+ *
+ * Drop-in boundary: the reference package reaches native
+ * code through R's .Call into its DLL -- one registered routine,
+ * `_flexgsea_s2n_C(SEXP x, SEXP y)` (reference src/RcppExports.cpp:10-24),
+ * called from R/RcppExports.R:4-6.  Everything else on the hot path is
+ * interpreted R (R/flexgsea.R:356-472, :474-629, :725-937).  The entry points
+ * below are what an Rcpp shim (r-package/src/flexgsea_native.cpp, see
+ * INTEGRATION.md) binds: plain pointers and sizes, no R, torch or CUDA types.
+ *
+ * Conventions
+ *  - every matrix is column-major, exactly as R holds it; inputs are read-only
+ *    host memory unless a parameter says "device";
+ *  - gene-set members are 1-based gene indices as produced by
+ *    match(set, gene.names) (R/flexgsea.R:279, :412), duplicates kept;
+ *  - every function returns FGS_OK or an error code; fgs_last_error() gives the
+ *    message (thread-local).  Nothing here longjmps or throws across the ABI.
+ *  - there is no CPU fallback: without a CUDA device fgs_create fails.
+ */
+#ifndef FLEXGSEA_B200_H
+#define FLEXGSEA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGS_ABI_VERSION 1
+
+#define FGS_OK 0
+#define FGS_ERR_ARG 1
+#define FGS_ERR_CUDA 2
+/* "Gene scoring function returned NA or Inf." R/flexgsea.R:251-253, :400-402 */
+#define FGS_ERR_NONFINITE 3
+#define FGS_ERR_OOM 4
+#define FGS_ERR_STATE 5
+#define FGS_ERR_UNSUPPORTED 6
+
+/* gene.score.fn built-ins: flexgsea_s2n (R/flexgsea.R:689-723),
+ * flexgsea_lm (:647-676) */
+#define FGS_SCORE_S2N 0
+#define FGS_SCORE_LM 1
+/* es.fn built-ins: flexgsea_weighted_ks (:925-937), flexgsea_maxmean
+ * (:749-753), flexgsea_mean (:775-779) */
+#define FGS_ES_WEIGHTED_KS 0
+#define FGS_ES_MAXMEAN 1
+#define FGS_ES_MEAN 2
+
+typedef struct fgs_ctx fgs_ctx;
+
+int fgs_abi_version(void);
+const char *fgs_last_error(void);
+int fgs_device_count(int *count);
+
+/* One context per GPU (device ordinal); owns the stream and all device state.
+ * The R side keeps it in an external pointer with a finalizer. */
+int fgs_create(int device, fgs_ctx **ctx);
+int fgs_destroy(fgs_ctx *ctx);
+
+/* ---- s2n_C: reference src/ggsea.cpp:6-76, .Call entry
+ * src/RcppExports.cpp:10-19.  x [n_sample_x x n_gene] double, y
+ * [n_sample_y x n_response] int logical (NA_LOGICAL = INT_MIN is skipped),
+ * coef [n_gene x n_response].  Bit-identical to the reference: sequential
+ * sample order, its three passes, population variance, no FMA.  Row mismatch
+ * returns an all-zero matrix like src/ggsea.cpp:15-17. */
+int fgs_s2n(fgs_ctx *ctx, const double *x, int n_sample_x, int n_gene, const int *y,
+            int n_sample_y, int n_response, double *coef);
+
+/* ---- problem upload (once per flexgsea() call) ------------------------- */
+/* x [n_sample x n_gene] (R/flexgsea.R:159-173, t.x == FALSE layout) */
+int fgs_set_x(fgs_ctx *ctx, const double *x, int n_sample, int n_gene);
+/* filtered gene sets as CSR (replaces the per-set match() of :279 and :412) */
+int fgs_set_gene_sets(fgs_ctx *ctx, const int *offsets, const int *index, int n_sets);
+/* flexgsea_s2n's y_bin (:704-710): [n_sample x n_response] int logical */
+int fgs_set_response_s2n(fgs_ctx *ctx, const int *y_bin, int n_sample, int n_response);
+/* flexgsea_lm's model matrix (:648-663): [n_sample x n_col] double;
+ * has_intercept != 0 drops the first column from the scores (:667-669).
+ * FGS_ERR_NONFINITE when the design is rank deficient (lm.fit gives NA). */
+int fgs_set_response_lm(fgs_ctx *ctx, const double *design, int n_sample, int n_col,
+                        int has_intercept);
+/* number of score columns R the current response yields for score_kind */
+int fgs_n_response(fgs_ctx *ctx, int score_kind, int *n_response);
+
+/* ---- observed pass (R/flexgsea.R:246-292) ------------------------------ */
+/* gene.score.fn(x, y, abs): scores [n_gene x R], +-Inf patch of :715-716 and
+ * abs applied.  FGS_ERR_NONFINITE mirrors the stop() of :251-253. */
+int fgs_score_observed(fgs_ctx *ctx, int score_kind, int abs_flag, double *scores);
+/* es.fn$run on the observed scores with all extras
+ * (flexgsea_weighted_ks_ :841-908).  scores [n_gene x R] host.  Outputs, each
+ * optional (NULL): es [S x R]; max_es_at, le_prop [S x R] (weighted KS only);
+ * ragged arrays sharing the CSR offsets, [nnz x R]: running_es_at (1-based gene
+ * ids in rank order), running_es_pos, running_es_neg; le_first/le_count
+ * [S x R]: the leading edge of set s is running_es_at[offsets[s] + le_first ..
+ * + le_count). */
+int fgs_observed_es(fgs_ctx *ctx, int es_kind, double p_exponent, const double *scores,
+                    int n_gene, int n_response, double *es, double *max_es_at, double *le_prop,
+                    int *running_es_at, double *running_es_pos, double *running_es_neg,
+                    int *le_first, int *le_count);
+
+/* ---- null loop: flexgsea_perm_sequential / _parallel (:356-472) -------- */
+/* Computes es_null [S, R, n_perm] for permutations perm_id0 .. perm_id0 +
+ * n_perm - 1.  perm != NULL: [n_sample x n_perm] int, 1-based,
+ * y.perm[i,] = y[perm[i,p],] (:384) -- an R-made matrix reproduces R's RNG
+ * stream.  perm == NULL: permutations are drawn on the device, Philox4x32-10
+ * keyed by (seed, global permutation id), so the result does not depend on how
+ * permutations are sharded over GPUs.  The null stays resident on the device
+ * for fgs_calc_sig; es_null_out (host, optional) receives a copy. */
+int fgs_perm_null(fgs_ctx *ctx, int score_kind, int es_kind, double p_exponent,
+                  int abs_flag, const int *perm, unsigned long long seed,
+                  long long perm_id0, int n_perm, double *es_null_out);
+/* Same, for a user-defined gene.score.fn: the R closure made
+ * scores [n_gene, n_response, n_perm] (:393-394); ranking onward runs here. */
+int fgs_es_from_scores(fgs_ctx *ctx, int es_kind, double p_exponent, const double *scores,
+                       int n_gene, int n_response, int n_perm, double *es_out);
+/* debug / parity taps for the block most recently processed by fgs_perm_null
+ * or fgs_es_from_scores when n_perm * R <= the internal block (tests only):
+ * scores [G x C], rank (1-based descending, R/flexgsea.R:929-931) [G x C] */
+int fgs_debug_last_scores(fgs_ctx *ctx, double *scores, int *rank, long long n_col);
+/* device pointer + shape of the resident null [S, R, P_local] (for NCCL
+ * all-gather by the host when es_null is a requested return value) */
+int fgs_null_device_ptr(fgs_ctx *ctx, void **dptr, int *n_sets, int *n_response, int *n_perm);
+/* load a null made elsewhere (user es.fn, or tests): es_null [S, R, P] host */
+int fgs_set_null(fgs_ctx *ctx, const double *es_null, int n_sets, int n_response, int n_perm);
+
+/* ---- significance: flexgsea_calc_sig (:564-629), _simple (:544-547) ---- */
+/* One response at a time, on the resident null.  Single-GPU convenience:
+ * outputs [S] each (NULL to skip): p, p_high, p_low (simple variant), nes, fdr,
+ * fwer; counts for parity checks: p_counts [S x 2] (numerator-1, denominator-1;
+ * or the high/low counts), fdr_counts [S x 2] (#{nes cmp nes_i},
+ * #{nes_null cmp nes_i}), glob_counts [4] (:501-504). */
+int fgs_calc_sig(fgs_ctx *ctx, const double *es, int response, int split_p, int calc_nes,
+                 int abs_flag, double *p, double *p_high, double *p_low, double *nes,
+                 double *fdr, double *fwer, long long *p_counts, long long *fdr_counts,
+                 long long *glob_counts);
+/* Staged form for permutations sharded over GPUs (one context per rank).
+ * stage1: local per-set partials over this rank's shard: sums [S x 4] =
+ * (sum of null >= 0 as hi,lo double-double; sum of null < 0 as hi,lo),
+ * counts [S x 6] = (n(null>=0), n(null<0), n(null<=0), #{es<=null & null>=0},
+ * #{es>=null & null<=0}, spare) or, simple variant, (#{es<=null}, #{es>=null}).
+ * The host all-gathers sums (combined in rank order) and all-reduces counts.
+ * stage2: given the combined means, local pooled-FDR counts: null_counts [S]
+ * (#{nes_null cmp nes_i} over the shard) and glob [2] (#{nes_null>0},
+ * #{nes_null<0}); all-reduced by the host.  finish: S-length epilogue on the
+ * device from combined counts. */
+int fgs_sig_stage1(fgs_ctx *ctx, const double *es, int response, int split_p, int abs_flag,
+                   double *sums, long long *counts);
+/* sums_parts [n_parts x S x 4]: every rank's stage-1 sums, in rank order;
+ * counts_total [S x 6]: the all-reduced counts; n_perm_total: P over all ranks.
+ * Outputs [S]: p, p_high, p_low, nes, fwer; null_counts [S], glob [2] are this
+ * rank's pooled-FDR counts (only when calc_nes); fdr_bh [S] is p.adjust(p, 'BH')
+ * (:625, only when !calc_nes -- then there is no stage 3). */
+int fgs_sig_stage2(fgs_ctx *ctx, const double *es, int response, int split_p, int calc_nes,
+                   int abs_flag, const double *sums_parts, int n_parts,
+                   const long long *counts_total, long long n_perm_total, double *p,
+                   double *p_high, double *p_low, double *nes, double *fwer,
+                   double *fdr_bh, long long *null_counts, long long *glob);
+int fgs_sig_finish(fgs_ctx *ctx, const double *nes, const long long *null_counts,
+                   const long long *glob, int n_sets, int abs_flag, double *fdr,
+                   long long *fdr_counts, long long *glob_counts);
+
+/* ---- instrumentation --------------------------------------------------- */
+/* number of kernels this library launched on ctx since creation */
+int fgs_launch_count(fgs_ctx *ctx, long long *count);
+/* device time (ms, CUDA events on the context's stream) of the stages of the
+ * most recent fgs_perm_null / fgs_es_from_scores: [0] labels+perm, [1] score,
+ * [2] rank/sort, [3] ES, [4] total; kernel launches per stage in launches[5] */
+int fgs_last_timings(fgs_ctx *ctx, float *ms, long long *launches);
+/* enable per-stage event timing (adds stream synchronisation points) */
+int fgs_set_profiling(fgs_ctx *ctx, int enabled);
+/* tuning / test hooks: "perm_block" (permutations per block), "force_generic_es"
+ * (route every set through the duplicate-safe O(m^2) kernel) */
+int fgs_set_option(fgs_ctx *ctx, const char *name, long long value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

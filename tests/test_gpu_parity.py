@@ -1,0 +1,407 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI, against the CPU
+oracle on the same seeded inputs and the same permutation matrix, and against
+the reference's golden vectors.  Bars (BASELINE.json north_star): gene scores
+and ranks bit-exact, leading-edge indices exact, ES/NES within 1e-10 absolute,
+p-value / FDR counts identical."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import flexgsea_r_b200 as fg
+from flexgsea_r_b200 import _native as nat, synth
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "weighted_ks.json")))
+ES_TOL = 1e-10  # absolute, north_star
+NA = np.iinfo(np.int32).min
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = fg.Context(0)
+    yield c
+    c.close()
+
+
+def _case(G=1000, n=20, S=50, P=96, sizes=(10, 50), dist="uniform", seed=0):
+    off, idx = synth.gene_sets_csr(G, S, sizes, dist, seed=seed + 1)
+    x, y = synth.two_class(G, n, off, idx, seed=seed + 2)
+    perm = synth.perm_matrix(n, P, seed=seed + 4)
+    return x, y, perm, off, idx
+
+
+def _ranks(oracle, scores):  # scores [G, C]
+    return np.stack([oracle.rank_desc(scores[:, c]) for c in range(scores.shape[1])], axis=1)
+
+
+# ---------------------------------------------------------------- a4: s2n_C
+def test_s2n_bit_exact(ctx, oracle):
+    from test_oracle_golden import X_TOY
+    y = np.array([[1, 0, 0, 1], [0, 0, 1, 1]], dtype=np.int32).T
+    assert np.array_equal(ctx.s2n(X_TOY, y), oracle.s2n_C(X_TOY, y))
+    rng = np.random.default_rng(5)
+    for n, G, R in ((37, 211, 3), (200, 1000, 1), (1, 5, 1), (33, 64, 2), (901, 70, 1)):
+        x = rng.normal(6, 2, size=(n, G))
+        yb = (rng.random((n, R)) < 0.4).astype(np.int32)
+        if n > 3:
+            yb[3, R - 1] = NA
+        got = ctx.s2n(x, yb)
+        want = oracle.s2n_C(x, yb)
+        assert np.array_equal(got, want, equal_nan=True), (n, G, R)
+        if oracle.ref_lib() is not None:
+            assert np.array_equal(got, oracle.s2n_C(x, yb, use_ref=True), equal_nan=True)
+    # row mismatch -> zeros (src/ggsea.cpp:15-17)
+    assert not ctx.s2n(rng.normal(size=(10, 4)), np.ones((9, 1), dtype=np.int32)).any()
+
+
+# ------------------------------------------------- a1/a2/a3/a6/a7: null loop
+@pytest.mark.parametrize("R", [1, 2])
+@pytest.mark.parametrize("abs_flag", [False, True])
+def test_perm_null_s2n_wks(ctx, oracle, R, abs_flag):
+    x, y, perm, off, idx = _case()
+    if R == 2:
+        rng = np.random.default_rng(9)
+        y = np.column_stack([y[:, 0], rng.permutation(y[:, 0])])
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    P = perm.shape[1]
+    got = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm, abs_flag=abs_flag)
+    rc, want, sc = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, oracle.ES_WKS,
+                                    abs_flag=abs_flag, return_scores=True)
+    assert rc == 0
+    gsc, grk = ctx.debug_last(P * R)
+    want_sc = sc.reshape(sc.shape[0], -1, order="F")
+    if abs_flag:  # the device keeps signed scores and applies abs when ranking
+        assert np.array_equal(np.abs(gsc), want_sc)
+    else:
+        assert np.array_equal(gsc, want_sc)                     # bit-exact scores
+    assert np.array_equal(grk, _ranks(oracle, want_sc))         # bit-exact ranks
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= ES_TOL
+
+
+def test_perm_null_blocks_and_generic_kernel(ctx, oracle):
+    """permutation blocking must not change results; the order-free kernel
+    (used for duplicate / oversized sets) agrees with the bitmap kernel."""
+    x, y, perm, off, idx = _case(P=70)
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    a = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, 70, perm=perm)
+    ctx.set_option("perm_block", 16)
+    b = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, 70, perm=perm)
+    ctx.set_option("perm_block", 0)
+    assert np.array_equal(a, b)
+    ctx.set_option("force_generic_es", 1)
+    g = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, 70, perm=perm)
+    ctx.set_option("force_generic_es", 0)
+    assert np.abs(a - g).max() <= 1e-13
+
+
+def test_duplicates_large_and_edge_sets(ctx, oracle):
+    """sets with duplicated members (R keeps them, m counts them), a set above
+    the bitmap capacity, a single-gene set and the all-genes set (ES = NaN)."""
+    G, n, P = 700, 16, 24
+    rng = np.random.default_rng(3)
+    sets = [rng.choice(G, 30, replace=False) + 1,
+            np.array([5, 9, 5, 77, 9, 200]),              # duplicates
+            rng.choice(G, 600, replace=False) + 1,        # > 512 members
+            np.array([42]),
+            np.arange(1, G + 1),                          # G - m == 0 -> NaN
+            rng.choice(G, 512, replace=False) + 1]        # exactly the capacity
+    off, idx = oracle.csr(sets)
+    x, y = synth.two_class(G, n, seed=8)
+    perm = synth.perm_matrix(n, P, seed=1)
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    got = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm)
+    rc, want = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, oracle.ES_WKS)
+    assert np.isnan(want[4]).all() and np.isnan(got[4]).all()
+    keep = [0, 1, 2, 3, 5]
+    assert np.abs(got[keep] - want[keep]).max() <= ES_TOL
+
+
+@pytest.mark.parametrize("es_kind", ["maxmean", "mean"])
+def test_perm_null_mean_maxmean(ctx, oracle, es_kind):
+    x, y, perm, off, idx = _case(P=40)
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    k = nat.ES_MAXMEAN if es_kind == "maxmean" else nat.ES_MEAN
+    ok = oracle.ES_MAXMEAN if es_kind == "maxmean" else oracle.ES_MEAN
+    got = ctx.perm_null(nat.SCORE_S2N, k, 40, perm=perm)
+    rc, want = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, ok)
+    assert rc == 0 and np.abs(got - want).max() <= ES_TOL
+    assert np.array_equal(np.sign(got), np.sign(want))
+
+
+def test_philox_permutations_match_definition(ctx, oracle):
+    """device-drawn permutations: same Philox4x32-10 Fisher-Yates as the oracle's
+    definition, keyed by the GLOBAL permutation id (shard independent)."""
+    x, y, _, off, idx = _case(P=1)
+    n = x.shape[0]
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    seed, P = 1234567, 48
+    a = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, seed=seed, perm_id0=0)
+    perm = np.stack([oracle.philox_perm(seed, p, n) for p in range(P)], axis=1)
+    b = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm)
+    assert np.array_equal(a, b)
+    lo = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, 20, seed=seed, perm_id0=0)
+    hi = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P - 20, seed=seed, perm_id0=20)
+    assert np.array_equal(np.concatenate([lo, hi], axis=2), a)
+
+
+def test_nonfinite_scores_raise_like_reference(ctx):
+    """a gene with zero variance in both classes and equal means gives 0/0:
+    the reference stops with "Gene scoring function returned NA or Inf."
+    (R/flexgsea.R:251-253, :400-402)."""
+    x, y, perm, off, idx = _case(P=8)
+    x = x.copy(); x[:, 7] = 3.0
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    with pytest.raises(fg.NonFiniteScoreError):
+        ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, 8, perm=perm)
+    with pytest.raises(fg.NonFiniteScoreError):
+        ctx.score_observed(nat.SCORE_S2N)
+
+
+def test_inf_patch(ctx, oracle):
+    """zero variance in both classes but different means -> +-Inf, patched to
+    1.1 * max/min finite over the permutation's score matrix (:715-716)."""
+    G, n = 300, 12
+    x, y = synth.two_class(G, n, seed=5)
+    x = x.copy()
+    x[:, 3] = np.where(y[:, 0] == 1, 2.0, 1.0)   # +Inf
+    x[:, 11] = np.where(y[:, 0] == 1, 1.0, 2.0)  # -Inf
+    off, idx = synth.gene_sets_csr(G, 10, (10, 30), "uniform", seed=2)
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    got = ctx.score_observed(nat.SCORE_S2N)
+    want = oracle.s2n_post(oracle.s2n_C(x, y))
+    assert np.isfinite(want).all() and np.array_equal(got, want)
+    perm = np.arange(1, n + 1, dtype=np.int32).reshape(-1, 1)
+    null = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, 1, perm=perm)
+    rc, ref = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, oracle.ES_WKS)
+    assert rc == 0 and np.abs(null - ref).max() <= ES_TOL
+
+
+# ------------------------------------------------ a6: ranking (ties, -0.0)
+def test_rank_ties_and_user_scores(ctx, oracle):
+    rng = np.random.default_rng(2)
+    G, R, P = 517, 2, 9
+    sc = rng.normal(size=(G, R, P))
+    sc[rng.integers(0, G, 60), 0, :] = 0.25        # exact ties
+    sc[10, :, :] = 0.0; sc[20, :, :] = -0.0        # -0.0 ties with 0.0
+    sc[:, 1, 3] = np.round(sc[:, 1, 3], 1)         # heavy ties
+    off, idx = synth.gene_sets_csr(G, 20, (5, 80), "uniform", seed=6)
+    ctx.set_gene_sets(off, idx)
+    got = ctx.es_from_scores(nat.ES_WEIGHTED_KS, sc)
+    _, rk = ctx.debug_last(R * P, G=G)
+    flat = sc.reshape(G, -1, order="F")
+    assert np.array_equal(rk, _ranks(oracle, flat))
+    rc, want = oracle.es_from_scores(oracle.ES_WKS, sc, off, idx)
+    assert rc == 0 and np.abs(got - want).max() <= ES_TOL
+    for kind, ok in ((nat.ES_MEAN, oracle.ES_MEAN), (nat.ES_MAXMEAN, oracle.ES_MAXMEAN)):
+        g2 = ctx.es_from_scores(kind, sc)
+        _, w2 = oracle.es_from_scores(ok, sc, off, idx)
+        assert np.abs(g2 - w2).max() <= ES_TOL
+    bad = sc.copy(); bad[3, 0, 0] = np.inf
+    with pytest.raises(fg.NonFiniteScoreError):
+        ctx.es_from_scores(nat.ES_WEIGHTED_KS, bad)
+
+
+# --------------------------------------- a8: observed extras + the goldens
+def test_weighted_ks_golden_on_device(ctx, oracle):
+    """tests/testthat/test_weighted_ks.R through the device path."""
+    rng = fg.RRNG(GOLD["seed"], "Rounding")
+    scores = rng.rnorm(3000).reshape(3, 1000).T
+    gs = rng.sample_int(1000, 20)
+    ctx.set_gene_sets(np.array([0, 20], dtype=np.int32), gs)
+    o = ctx.observed_es(nat.ES_WEIGHTED_KS, scores)
+    assert np.abs(o["es"][0] - np.array(GOLD["es"]["values"])).max() <= 1e-12
+    assert list(o["max_es_at"][0].astype(int)) == GOLD["max_es_at"]["values"]
+    assert list(o["le_prop"][0]) == GOLD["le_prop"]["values"]
+    null = ctx.es_from_scores(nat.ES_WEIGHTED_KS, scores[:, :, None])
+    assert np.abs(null[0, :, 0] - np.array(GOLD["es"]["values"])).max() <= 1e-12
+    res = fg.flexgsea_weighted_ks.run(scores[:, :, None], gs, None, return_stats=("le_prop", "max_es_at"))
+    assert np.abs(res["es"][:, 0] - np.array(GOLD["es"]["values"])).max() <= 1e-12
+    assert list(res["max_es_at"][:, 0].astype(int)) == GOLD["max_es_at"]["values"]
+
+
+def test_observed_extras_exact(ctx, oracle):
+    x, y, _, off, idx = _case(S=40)
+    dup = np.array([5, 9, 5, 77, 9, 200], dtype=np.int32)
+    off = np.concatenate([off, [off[-1] + dup.size]]).astype(np.int32)
+    idx = np.concatenate([idx, dup]).astype(np.int32)
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    sc = ctx.score_observed(nat.SCORE_S2N)
+    o = ctx.observed_es(nat.ES_WEIGHTED_KS, sc)
+    rank = oracle.rank_desc(sc[:, 0])
+    for s in range(off.size - 1):
+        w = oracle.wks_column(sc[:, 0], rank, idx[off[s]:off[s + 1]], extras=True)
+        sl = slice(off[s], off[s + 1])
+        assert abs(o["es"][s, 0] - w["es"]) <= 1e-15
+        assert o["max_es_at"][s, 0] == w["max_es_at"] and o["le_prop"][s, 0] == w["le_prop"]
+        assert np.array_equal(o["running_es_at"][sl, 0], w["running_es_at"])
+        assert np.abs(o["running_es_pos"][sl, 0] - w["running_es_pos"]).max() <= 1e-15
+        assert np.abs(o["running_es_neg"][sl, 0] - w["running_es_neg"]).max() <= 1e-15
+        le = o["running_es_at"][off[s] + o["le_first"][s, 0]: off[s] + o["le_first"][s, 0] + o["le_count"][s, 0], 0]
+        assert np.array_equal(le, w["leading_edge"])           # leading-edge indices exact
+
+
+# ------------------------------------------------------- a5: flexgsea_lm
+def test_lm_scores_and_null(ctx, oracle):
+    G, n, P = 600, 40, 30
+    off, idx = synth.gene_sets_csr(G, 25, (10, 60), "uniform", seed=3)
+    x, _ = synth.two_class(G, n, seed=4)
+    design = synth.continuous_response(n, k=2, seed=5)
+    perm = synth.perm_matrix(n, P, seed=6)
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_lm(design, True)
+    got = ctx.score_observed(nat.SCORE_LM)
+    rc, want = oracle.lm_scores(x, design, True)
+    assert rc == 0 and got.shape == want.shape == (G, 3)
+    assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+    null = ctx.perm_null(nat.SCORE_LM, nat.ES_WEIGHTED_KS, P, perm=perm)
+    rc, ref, sc = oracle.perm_null(x, oracle.SCORE_LM, design, True, perm, off, idx, oracle.ES_WKS,
+                                   return_scores=True)
+    assert rc == 0
+    gsc, grk = ctx.debug_last(P * 3)
+    flat = sc.reshape(G, -1, order="F")
+    assert np.abs(gsc - flat).max() <= 1e-12
+    # lm parity is tolerance-based (QR vs contraction round differently): ranks
+    # may only differ where the oracle's scores are within that tolerance
+    rr = _ranks(oracle, flat)
+    bad = np.argwhere(grk != rr)
+    for g, c in bad:
+        other = np.where(rr[:, c] == grk[g, c])[0][0]
+        assert abs(flat[g, c] - flat[other, c]) <= 1e-12
+    if len(bad) == 0:
+        assert np.abs(null - ref).max() <= ES_TOL
+    with pytest.raises(fg.NonFiniteScoreError):
+        ctx.set_response_lm(np.column_stack([design, design[:, 1]]), True)
+
+
+# ------------------------------------------------- a10-a12: significance
+@pytest.mark.parametrize("abs_flag", [False, True])
+@pytest.mark.parametrize("simple", [False, True])
+def test_calc_sig_counts_identical(ctx, oracle, simple, abs_flag):
+    rng = np.random.default_rng(21)
+    S, P = 300, 700
+    es = rng.normal(size=S); en = rng.normal(size=(S, P))
+    if abs_flag:
+        es, en = np.abs(es), np.abs(en)
+    es[4] = en[4].max() + 1; es[7] = 0.0; en[7, :5] = 0.0
+    en[9, :] = np.abs(en[9, :]); es[9] = -0.3          # no negative null: NaN mean fix-up (:615-616)
+    ctx.set_null(en)
+    got = ctx.calc_sig(es, 0, not simple, not simple, abs_flag)
+    want = oracle.calc_sig(es, en, not simple, not simple, abs_flag)
+    assert np.array_equal(got["p_counts"], want["p_counts"])
+    assert np.array_equal(got["p"], want["p"])
+    assert np.array_equal(got["fwer"], want["fwer"])
+    if simple:
+        assert np.array_equal(got["p_high"], want["p_high"])
+        if not abs_flag:
+            assert np.array_equal(got["p_low"], want["p_low"])
+        assert np.allclose(got["fdr"], want["fdr"], rtol=1e-14, atol=0)
+    else:
+        assert np.abs(got["nes"] - want["nes"]).max() <= ES_TOL
+        assert np.array_equal(got["fdr_counts"], want["fdr_counts"])
+        assert np.array_equal(got["glob_counts"], want["glob_counts"])
+        assert np.allclose(got["fdr"], want["fdr"], rtol=1e-12, atol=0)
+
+
+def test_fdr_reference_properties_on_device(ctx):
+    """tests/testthat/test_fdr.R:20-54 through the device path."""
+    from test_oracle_golden import _fdr_inputs
+    es, en = _fdr_inputs()
+    for fn in (fg.flexgsea_calc_sig, fg.flexgsea_calc_sig_simple):
+        sig = fn(es, en)
+        for k in ("p", "fdr", "fwer"):
+            assert sig[k].min() > 0 and sig[k].max() <= 1
+        assert sig["p"][3] <= .1 and sig["p"][4] <= .1 and sig["fdr"][3] <= .1 and sig["fdr"][4] <= .1
+        assert all(sig["fdr"][i] > .1 for i in (0, 1, 2, 5, 6, 7, 8, 9))
+
+
+def test_staged_sig_equals_single(ctx):
+    """the multi-GPU staged significance (two shards emulated on one GPU)
+    reproduces the single-pass result exactly."""
+    rng = np.random.default_rng(33)
+    S, P = 120, 500
+    es = rng.normal(size=S); en = rng.normal(size=(S, 1, P))
+    ctx.set_null(en)
+    one = ctx.calc_sig(es)
+    parts, counts, ncs, gls = [], [], [], []
+    shards = [en[:, :, :230], en[:, :, 230:]]
+    for sh in shards:
+        ctx.set_null(sh)
+        s, c = ctx.sig_stage1(es)
+        parts.append(s); counts.append(c)
+    total = counts[0] + counts[1]
+    for sh in shards:
+        ctx.set_null(sh)
+        r = ctx.sig_stage2(es, np.stack(parts), total, P)
+        ncs.append(r["null_counts"]); gls.append(r["glob"])
+    fin = ctx.sig_finish(r["nes"], ncs[0] + ncs[1], gls[0] + gls[1])
+    assert np.array_equal(r["p"], one["p"]) and np.array_equal(r["nes"], one["nes"])
+    assert np.array_equal(fin["fdr_counts"], one["fdr_counts"])
+    assert np.array_equal(fin["fdr"], one["fdr"])
+
+
+# ----------------------------------------------------- the R-API mirror
+def test_flexgsea_end_to_end(ctx, oracle):
+    """flexgsea() with flexgsea_s2n + flexgsea_weighted_ks (BASELINE configs[0]
+    shape) against the oracle pipeline on the same permutation matrix."""
+    import pandas as pd
+    G, n, S, P = 1000, 20, 50, 200
+    off, idx = synth.gene_sets_csr(G, S, (10, 50), "uniform", seed=1)
+    x, y = synth.two_class(G, n, off, idx, seed=2)
+    genes = ["g%d" % (i + 1) for i in range(G)]
+    sets = {"set%d" % s: [genes[i - 1] for i in idx[off[s]:off[s + 1]]] for s in range(S)}
+    perm = synth.perm_matrix(n, P, seed=4)
+    res = fg.flexgsea(pd.DataFrame(x, columns=genes), np.where(y[:, 0] == 1, "a", "b"), sets, nperm=P,
+                      verbose=False, perm=perm, return_values=["es_null", "leading_edge", "running_es_at"])
+    assert list(res["table"].keys()) == ["Response 1"]
+    tab = res["table"]["Response 1"]
+    assert list(tab.columns) == ["es", "p", "nes", "fdr", "fwer", "max_es_at", "le_prop", "GeneSet"]
+    assert list(tab["GeneSet"]) == list(sets.keys())
+    rc, null = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, oracle.ES_WKS)
+    assert np.abs(res["es_null"] - null).max() <= ES_TOL
+    sc = oracle.s2n_post(oracle.s2n_C(x, y))
+    rank = oracle.rank_desc(sc[:, 0])
+    es = np.array([oracle.wks_column(sc[:, 0], rank, idx[off[s]:off[s + 1]]) for s in range(S)])
+    assert np.abs(tab["es"].to_numpy() - es).max() <= 1e-12
+    sig = oracle.calc_sig(tab["es"].to_numpy(), res["es_null"][:, 0, :])
+    assert np.array_equal(tab["p"].to_numpy(), sig["p"])
+    assert np.abs(tab["nes"].to_numpy() - sig["nes"]).max() <= ES_TOL
+    assert np.allclose(tab["fdr"].to_numpy(), sig["fdr"], rtol=1e-12)
+    assert ((tab["p"] >= 0) & (tab["p"] <= 1)).all()
+    le = res["leading_edge"]["Response 1"]["set0"]
+    w = oracle.wks_column(sc[:, 0], rank, idx[off[0]:off[1]], extras=True)
+    assert np.array_equal(le, w["leading_edge"])
+
+
+def test_flexgsea_lm_structure(ctx):
+    """tests/testthat/test_main.R: matrix / data.frame / model.matrix y with
+    flexgsea_lm, maxmean and weighted KS, single gene set, extras."""
+    import pandas as pd
+    x = pd.DataFrame({
+        "x1": [-0.91036224, -0.23633198, 0.07675882, -0.14270400],
+        "x2": [-0.0005694878, -0.9734813268, -2.0230448058, 0.3552175208],
+        "x2.big": [-0.005694878, -9.734813268, -20.230448058, 3.552175208],
+        "x3": [0.1979443, -1.0453220, -0.1528467, 0.0897873],
+        "x4": [-0.1979443, 1.0453220, 0.1528467, -0.0897873],
+        "x5": [0.1979672, -1.0453921, -0.1528823, 0.0897534]})
+    y = pd.DataFrame({"y1": [0.19801108, -1.05384953, -0.15942901, 0.09702427],
+                      "y2": [1.793303, 1.589571, -1.412860, 2.192915]})
+    gs = {"pw1": ["x1", "x2", "x3"], "pw2": ["x2", "x2.big"], "pw3": ["x3", "x5"]}
+    mm = fg.ModelMatrix(np.column_stack([np.ones(4), y.to_numpy()]), ["(Intercept)", "y1", "y2"])
+    for yy in (y.to_numpy(), y, mm):
+        for esf in (fg.flexgsea_maxmean, fg.flexgsea_weighted_ks):
+            res = fg.flexgsea(x, yy, gs, es_fn=esf, nperm=100, verbose=False, gs_size_min=1, block_size=11,
+                              gene_score_fn=fg.flexgsea_lm, return_values=["es_null"], seed=1)
+            names = ["Response1", "Response2"] if isinstance(yy, np.ndarray) else ["y1", "y2"]
+            assert list(res["table"].keys()) == names
+            for t in res["table"].values():
+                assert list(t["GeneSet"]) == list(gs.keys())
+                assert ((t["p"] >= 0) & (t["p"] <= 1)).all()
+            assert res["es_null"].shape == (3, 2, 100)
+    res = fg.flexgsea(x, y, {"pw1": gs["pw1"]}, nperm=100, verbose=False, gs_size_min=1,
+                      gene_score_fn=fg.flexgsea_lm, return_values=["es_null", "running_es_pos"], seed=2)
+    assert res["es_null"].shape == (1, 2, 100)
+    assert isinstance(res["running_es_pos"], dict)

@@ -1,0 +1,133 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol
+include/flexgsea_b200.h declares (no compute without a GPU), and the host logic
+that mirrors the reference's R API (GMT ingest, gene-set filtering, CSR packing,
+response encoding, R's RNG stream, permutation sharding)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import flexgsea_r_b200 as fg
+from flexgsea_r_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "flexgsea_b200.h")).read()
+    declared = set(re.findall(r"\b(fgs_[a-z0-9_]+)\s*\(", hdr)) - {"fgs_ctx"}
+    lib = fg._native.load()
+    assert declared == set(fg._native.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.fgs_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    if fg._native.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(fg.FlexgseaError):
+        fg.Context(0)
+
+
+def test_product_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "flexgsea-r_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in txt and "liboracle" not in txt and "oracle/" not in txt, f
+
+
+def test_read_gmt_and_filter(tmp_path):
+    p = tmp_path / "a.gmt"
+    p.write_text("S1\thttp://x\tg1\tg2\tg3\nS2\tna\tg2\tzz\nS3\tna\tg9\n")
+    gs = fg.read_gmt(str(p))
+    assert list(gs) == ["S1", "S2", "S3"] and gs["S1"] == ["g1", "g2", "g3"] and gs["S2"] == ["g2", "zz"]
+    names = ["g1", "g2", "g3", "g4"]
+    f = fg.filter_gene_sets(gs, names, gs_size_min=1, gs_size_max=2, verbose=False)
+    assert list(f) == ["S2"] and f["S2"] == ["g2"]        # R/flexgsea.R:941-952
+    f = fg.filter_gene_sets(gs, names, gs_size_min=1, gs_size_max=300, verbose=False)
+    off, idx = fg.gene_sets_to_csr(f, names)
+    assert list(off) == [0, 3, 4] and list(idx) == [1, 2, 3, 2]
+    # duplicated gene names: match() takes the first (:279)
+    off, idx = fg.gene_sets_to_csr({"a": ["g2", "g2"]}, ["g1", "g2", "g2"])
+    assert list(idx) == [2, 2]
+
+
+def test_binarise_like_flexgsea_s2n():
+    yb, names = api._binarise(np.array(["b", "a", "a", "b"]))
+    assert list(yb[:, 0]) == [0, 1, 1, 0] and names is None          # classes[1] = 'a'
+    yb, _ = api._binarise(np.array([[1, 1, 0, 0]]).T)
+    assert list(yb[:, 0]) == [0, 0, 1, 1]                            # class 1 = sort(unique)[1] = 0
+    yb, _ = api._binarise(np.array([True, False, True]))
+    assert list(yb[:, 0]) == [1, 0, 1]
+    yb, _ = api._binarise(np.array([1.0, np.nan, 2.0]))
+    assert yb[1, 0] == api.NA_LOGICAL
+    with pytest.raises(ValueError):
+        api._binarise(np.array([1, 2, 3]))
+
+
+def test_design_like_flexgsea_lm():
+    d, names = api._design(np.array([[1.0, 2.0], [3.0, 4.0], [5.0, 7.0]]))
+    assert names == ["(Intercept)", "Response1", "Response2"] and d.shape == (3, 3) and (d[:, 0] == 1).all()
+    d, names = api._design(np.array([1.0, 2.0, 4.0]))
+    assert names == ["(Intercept)", "Response"]
+
+
+def test_rrng_sample_kinds():
+    r = fg.RRNG(1, "Rejection")
+    assert sorted(r.sample_int(10)) == list(range(1, 11))
+    # R >= 3.6: set.seed(1); sample.int(10) -> 9 4 7 1 2 5 3 10 6 8
+    assert list(fg.RRNG(1, "Rejection").sample_int(10)) == [9, 4, 7, 1, 2, 5, 3, 10, 6, 8]
+    # R 3.x (Rounding): set.seed(1); sample.int(10) -> 3 4 5 7 2 8 9 6 10 1
+    assert list(fg.RRNG(1, "Rounding").sample_int(10)) == [3, 4, 5, 7, 2, 8, 9, 6, 10, 1]
+    pm = fg.RRNG(3).perm_matrix(7, 5)
+    assert pm.shape == (5, 7) and all(sorted(row) == list(range(1, 8)) for row in pm)
+
+
+def test_shard_spans_cover_all_permutations():
+    for world in (1, 2, 3, 8):
+        spans = []
+        for rank in range(world):
+            s = api._Shard(False); s.rank, s.world = rank, world
+            spans.append(s.span(1001))
+        assert spans[0][0] == 0 and spans[-1][1] == 1001
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+
+
+_GLOO = r'''
+import os, sys, numpy as np
+sys.path.insert(0, %r)
+import torch.distributed as dist
+import flexgsea_r_b200 as fg
+from flexgsea_r_b200 import api
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%d" %% int(sys.argv[2]), rank=int(sys.argv[1]), world_size=2)
+sh = api._Shard(None)
+assert (sh.rank, sh.world) == (int(sys.argv[1]), 2)
+lo, hi = sh.span(101)
+g = sh.all_gather(np.full((3, 4), float(sh.rank)))
+assert g.shape == (2, 3, 4) and (g[0] == 0).all() and (g[1] == 1).all()   # rank order
+r = sh.all_reduce_sum(np.arange(5, dtype=np.int64) * (sh.rank + 1))
+assert list(r) == [0, 3, 6, 9, 12]
+tot = sh.all_reduce_sum(np.array([hi - lo], dtype=np.int64))
+assert tot[0] == 101
+dist.destroy_process_group()
+print("ok")
+'''
+
+
+def test_sharding_collectives_gloo_world2(tmp_path):
+    """N>1 host path on CPU: two gloo ranks, all-gather in rank order and
+    int64 all-reduce as sharded_sig uses them."""
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO % ROOT)
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(port)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
