@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- the headline metric of BASELINE.json on synthetic data.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config C2]
+
+metric: gene-set x permutation ES/sec of the sample-permutation null loop
+(permute -> gene score -> rank -> ES), config C2 by default: flexgsea_s2n +
+flexgsea_weighted_ks (p=1), 20,000 genes x 200 samples two-class, 8,000 gene
+sets of 15-500 genes, nperm=10,000.  One "step" = the whole null loop over the
+10,000 permutations.
+
+  value : S*R*P*N / device time (CUDA events on the library's stream, inputs
+          resident in HBM, permutations drawn on the device), max over ranks.
+  e2e   : the same metric through the public C-ABI calls a flexgsea() call
+          makes, host buffers in pinned memory, H2D/D2H inside the timed
+          region, wall clock.
+  roofline / cpu_baseline / clocks / stages: see DESIGN.md "Measurement".
+
+N > 1 (torchrun): permutations are independent units, every rank runs its own
+10,000 (weak scaling, no data-path collective); the significance step's small
+NCCL exchanges are exercised once after the timed loop.
+--impl reference: the reference's CPU path.  R is not installable here (no R,
+no network), so this arm times the oracle restatement of the reference's loop
+(oracle/oracle.c, OpenMP over permutations, all host cores) on a bounded
+sample of the same workload; rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD_TEXT = {
+    "C1": "C1: s2n + weighted KS (p=1), 1,000 genes x 20 samples two-class, 50 gene sets (10-50), nperm=1,000",
+    "C2": "C2: s2n + weighted KS (p=1), 20,000 genes x 200 samples two-class, 8,000 gene sets (15-500), nperm=10,000",
+    "C4": "C4: s2n + maxmean ES, 20,000 genes x 200 samples two-class, 20,000 gene sets (15-300), nperm=50,000",
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(name, seed=1):
+    from flexgsea_r_b200 import synth
+    c = dict(synth.CONFIGS[name])
+    off, idx = synth.gene_sets_csr(c["G"], c["S"], c["sizes"], c["size_dist"], seed=seed)
+    x, y = synth.two_class(c["G"], c["n"], off, idx, seed=seed + 1)
+    return c, x, y, off, idx
+
+
+def pinned(a):
+    """copy of `a` in page-locked host memory (column-major kept)"""
+    import torch
+    flat = np.asfortranarray(a).reshape(-1, order="F")
+    t = torch.from_numpy(flat.copy()).pin_memory()
+    return t.numpy().reshape(a.shape, order="F"), t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as orc
+    from flexgsea_r_b200 import synth
+    orc.build()
+    c, x, y, off, idx = workload(args.config)
+    es_kind = orc.ES_MAXMEAN if args.config == "C4" else orc.ES_WKS
+    cores = orc.num_threads()
+    P_s = args.ref_perms if args.ref_perms else max(cores * 8, 64)
+    perm = synth.perm_matrix(c["n"], P_s, seed=4)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        rc, _ = orc.perm_null(x, orc.SCORE_S2N, y, False, perm, off, idx, es_kind)
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = c["S"] * P_s / (ms / 1e3)
+    sample = ("%d of the %d permutations per step, all gene sets; C restatement of the reference loop "
+              "(oracle/oracle.c), OpenMP over permutations" % (P_s, c["P"]))
+    print(json.dumps({
+        "impl": "reference", "metric": "gene-set x permutation ES/sec (null loop)", "value": val, "unit": "ES/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_TEXT[args.config], "step": "bounded sample: " + sample},
+        "cpu_baseline": {"value": val, "unit": "ES/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "ES/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "R is absent from this image (no R/Rscript/libR, no network): the reference package cannot run; "
+                "this is the restated-reference CPU baseline (no R interpreter overhead, so a stronger baseline)",
+    }))
+
+
+def run_gpu(args):
+    import torch
+    import flexgsea_r_b200 as fg
+    from flexgsea_r_b200 import _native as nat, synth, api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    c, x, y, off, idx = workload(args.config)
+    G, n, S, P = c["G"], c["n"], c["S"], c["P"]
+    if args.perms:
+        P = args.perms
+    R = 1
+    es_kind = nat.ES_MAXMEAN if args.config == "C4" else nat.ES_WEIGHTED_KS
+    nnz = int(off[-1])
+    ctx = fg.Context(local)
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    ctx.set_profiling(True)
+    seed = 20261019
+
+    def step():
+        ctx.perm_null(nat.SCORE_S2N, es_kind, P, perm=None, seed=seed, perm_id0=rank * P, want_host=False)
+        return ctx.last_timings()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    dev_ms, stage_ms, stage_launch = 0.0, {"perm": 0.0, "score": 0.0, "rank": 0.0, "es": 0.0}, None
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        ms, ln = step()
+        dev_ms += ms["total"]
+        for k in stage_ms:
+            stage_ms[k] += ms[k]
+        stage_launch = ln
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - w0)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = float(t[0]), float(t[1])
+    units = float(S) * R * P * world * args.steps
+    value = units / (dev_ms / 1e3)
+
+    # ---- end to end through the public C-ABI calls of one flexgsea() run --------
+    perm_h = synth.perm_matrix(n, P, seed=4 + rank)
+    xp, _k1 = pinned(x); yp, _k2 = pinned(y.astype(np.int32)); pp, _k3 = pinned(perm_h)
+    offp, _k4 = pinned(off); idxp, _k5 = pinned(idx)
+
+    def e2e_step():
+        ctx.set_x(xp); ctx.set_gene_sets(offp, idxp); ctx.set_response_s2n(yp)
+        sc = ctx.score_observed(nat.SCORE_S2N)
+        obs = ctx.observed_es(es_kind, sc)
+        ctx.perm_null(nat.SCORE_S2N, es_kind, P, perm=pp, want_host=False)
+        sig = ctx.calc_sig(obs["es"][:, 0], 0, True, True, False)
+        return sig
+
+    e2e_step()
+    barrier()
+    e0 = time.perf_counter()
+    e_steps = max(1, min(args.steps, 3))
+    for _ in range(e_steps):
+        sig = e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - e0) / e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te[0])
+    h2d = x.nbytes + 4 * n + perm_h.nbytes + 4 * (S + 1 + nnz) + 8 * G * R + 8 * S
+    d2h = 8 * G * R + S * R * (8 * 3 + 4 * 2) + (nnz * R * 20 if es_kind == nat.ES_WEIGHTED_KS else 0) + S * (6 * 8 + 4 * 8) + 32
+
+    # ---- multi-GPU: the significance exchange (all-gather sums, all-reduce counts)
+    if dist is not None:
+        sc = ctx.score_observed(nat.SCORE_S2N)
+        es_obs = ctx.observed_es(es_kind, sc)["es"][:, 0]
+        shard = api._Shard(None)
+        r = api.sharded_sig(ctx, shard, fg.flexgsea_calc_sig, es_obs, 0, False, P * world)
+        assert np.isfinite(r["fdr"]).all()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------
+    peak, peak_src = peaks()
+    Gp = (G + 7) & ~7
+    dom = max(("score", "rank", "es"), key=lambda k: stage_ms[k])
+    alg_bytes_col = {  # algorithmic HBM bytes per score column (DESIGN.md "Kernels")
+        "score": 8 * G,                 # score write (x is L2 resident, 8*n*G once)
+        "rank": 8 * G + 10 * Gp,        # score read + rank (u16) and rank-ordered weight (f64) write
+        "es": (10 * Gp if es_kind == nat.ES_WEIGHTED_KS else 8 * G) + 8 * S,
+    }
+    cols = P * R
+    roof = {}
+    for k in ("score", "rank", "es"):
+        nl = max(1, stage_launch[k])
+        t_ms = stage_ms[k] / args.steps
+        once = 4 * (nnz + S + 1) if k == "es" else (8 * n * G if k == "score" else 0)
+        b = cols * alg_bytes_col[k] + once * nl
+        roof[k] = {"ms_per_step": t_ms, "launches_per_step": nl, "alg_bytes_per_step": b,
+                   "achieved_gbs": b / (t_ms / 1e3) / 1e9 if t_ms > 0 else None}
+    dl = roof[dom]
+    per_launch_bytes = dl["alg_bytes_per_step"] / dl["launches_per_step"]
+    per_launch_ms = dl["ms_per_step"] / dl["launches_per_step"]
+    roofline = {"bound": "hbm", "kernel": {"score": "s2n_kernel", "rank": "sort_rank_kernel",
+                                            "es": "es_wks_kernel" if es_kind == nat.ES_WEIGHTED_KS else "es_mean_kernel"}[dom],
+                "achieved": dl["achieved_gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": dl["achieved_gbs"] / peak, "traffic": None,
+                "alg_bytes_per_launch": per_launch_bytes, "launch_ms": per_launch_ms,
+                "note": "stage time from CUDA events on the library's stream inside the timed region"}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get(roofline["kernel"])
+        except Exception:
+            pass
+
+    # ---- CPU baseline beside it (rank 0, N == 1 only) ---------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyoracle as orc
+        cores = orc.num_threads()
+        P_s = max(cores * 8, 64)
+        ps = synth.perm_matrix(n, P_s, seed=4)
+        ok = orc.ES_MAXMEAN if args.config == "C4" else orc.ES_WKS
+        orc.perm_null(x, orc.SCORE_S2N, y, False, ps[:, :cores], off, idx, ok)
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 10.0 or reps < 1:
+            rc, _ = orc.perm_null(x, orc.SCORE_S2N, y, False, ps, off, idx, ok)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        cpu = {"value": S * R * P_s / dt, "unit": "ES/s", "cores": cores, "kind": "port",
+               "sample": "%d of the %d permutations, all %d gene sets, C restatement (oracle/oracle.c) with "
+                         "OpenMP over permutations" % (P_s, P, S)}
+
+    out = {
+        "metric": "gene-set x permutation ES/sec (null loop)", "value": value, "unit": "ES/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_TEXT[args.config], "nperm_per_gpu": P, "genes": G, "samples": n,
+                   "gene_sets": S, "nnz": nnz, "responses": R, "seeds": {"sets": 1, "x": 2, "philox": seed},
+                   "permutations": "device Philox4x32-10 (value); host int32 matrix uploaded (e2e)",
+                   "l2": "inputs larger than L2: each block streams %d MB of scores/ranks/weights (L2 is 126 MB)"
+                         % int(min(P, 2048) * (18 * G) / 1e6),
+                   "score_mode": "bit-faithful s2n (reference operation order, no FMA)"},
+        "wall_ms_per_step": wall_ms / args.steps,
+        "e2e": {"value": float(S) * R * P * world / e2e_s, "unit": "ES/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
+                "what": "set_x + set_gene_sets + set_response + observed scores/ES(+extras) + null loop "
+                        "(host permutation matrix) + calc_sig; pinned host buffers; result table read back"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "stages": roof,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="C2", choices=list(WORKLOAD_TEXT))
+    ap.add_argument("--perms", type=int, default=0, help="override nperm per GPU (debug)")
+    ap.add_argument("--ref-perms", type=int, default=0, help="permutations per reference step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

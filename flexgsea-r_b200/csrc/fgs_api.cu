@@ -159,7 +159,6 @@ struct StageTimer {
     }
     for (auto e : evs) cudaEventDestroy(e);
     evs.clear();
-    c->last_ms[4] = c->last_ms[0] + c->last_ms[1] + c->last_ms[2] + c->last_ms[3];
   }
 };
 
@@ -246,6 +245,7 @@ int fgs_create(int device, fgs_ctx **out) {
   c->num_sms = prop.multiProcessorCount;
   c->smem_optin = (int)prop.sharedMemPerBlockOptin;
   FGS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) FGS_CUDA(cudaEventCreate(&c->ev[i]));
   *out = c;
   return FGS_OK;
 }
@@ -260,6 +260,7 @@ int fgs_destroy(fgs_ctx *c) {
   c->scores.release(); c->rank16.release(); c->sabs.release(); c->sort_keys.release();
   c->sort_idx.release(); c->flags.release(); c->counters.release(); c->es_null.release();
   c->sig_d.release(); c->sig_i.release();
+  for (int i = 0; i < 2; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream);
   delete c;
   return FGS_OK;
@@ -319,9 +320,14 @@ int fgs_set_gene_sets(fgs_ctx *c, const int *offsets, const int *index, int n_se
       idx0[j] = index[j] - 1;
       max_idx = std::max(max_idx, index[j]);
     }
-    tmp.assign(idx0.begin() + a, idx0.begin() + b);
-    std::sort(tmp.begin(), tmp.end());
-    bool dup = std::adjacent_find(tmp.begin(), tmp.end()) != tmp.end();
+    // duplicate detection in O(m): stamp[gene] = last set that held it
+    bool dup = false;
+    for (int j = a; j < b; j++) {
+      const size_t g = (size_t)idx0[j];
+      if (g >= tmp.size()) tmp.resize(std::max(g + 1, tmp.size() * 2), -1);
+      if (tmp[g] == s) dup = true;
+      tmp[g] = s;
+    }
     if (dup || (b - a) > 512) { slow[s] = 1; slow_ids.push_back(s); }
     order[s] = s;
   }
@@ -491,6 +497,7 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
   if (P == 0) return FGS_OK;
   FGS_TRY(flags_reset(c, P));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
+  FGS_CUDA(cudaEventRecord(c->ev[0], c->stream));  // always-on device time of the whole null loop
   if (c->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream); }
   long long l0 = c->launches;
   // K1: permutations (uploaded or drawn) and, for s2n, permuted class masks
@@ -519,6 +526,7 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
     FGS_TRY(rank_and_es(c, es_kind, p_exp, abs_flag, (long long)Pb * R,
                         c->es_null.p + (size_t)p0 * R * S, tm));
   }
+  FGS_CUDA(cudaEventRecord(c->ev[1], c->stream));
   int rc = flags_check(c, P);
   if (c->profiling) {
     cudaEventSynchronize(e1);
@@ -526,6 +534,7 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
     cudaEventDestroy(e0); cudaEventDestroy(e1);
   }
   tm.finish(pro_ms);
+  if (cudaEventSynchronize(c->ev[1]) == cudaSuccess) cudaEventElapsedTime(&c->last_ms[4], c->ev[0], c->ev[1]);
   c->last_launches[4] = c->last_launches[0] + c->last_launches[1] + c->last_launches[2] + c->last_launches[3];
   if (rc != FGS_OK) return rc;
   if (es_null_out) {
@@ -553,6 +562,7 @@ int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scor
     c->null_S = S; c->null_R = R; c->null_P = P;
     if (C == 0) return FGS_OK;
     FGS_TRY(flags_reset(c, C));
+    FGS_CUDA(cudaEventRecord(c->ev[0], c->stream));
     StageTimer tm(c);
     const long long Cb_max = block_columns(c, C);
     for (long long c0 = 0; c0 < C; c0 += Cb_max) {
@@ -564,8 +574,10 @@ int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scor
       tm.mark();
       FGS_TRY(rank_and_es(c, es_kind, p_exp, 0, Cb, c->es_null.p + (size_t)c0 * S, tm));
     }
+    FGS_CUDA(cudaEventRecord(c->ev[1], c->stream));
     int r2 = flags_check(c, C);
     tm.finish(0.f);
+    if (cudaEventSynchronize(c->ev[1]) == cudaSuccess) cudaEventElapsedTime(&c->last_ms[4], c->ev[0], c->ev[1]);
     if (r2 != FGS_OK) return r2;
     if (es_out) { FGS_TRY(d2h(c, es_out, c->es_null.p, (size_t)S * C)); FGS_TRY(sync(c)); }
     return FGS_OK;
