@@ -166,7 +166,7 @@ struct StageTimer {
 // (scores 8G + rank 2G + weights 8G bytes per column) stays ~<= 1.5 GB
 static long long block_columns(fgs_ctx *c, long long C_total) {
   long long cb = c->opt_perm_block > 0 ? c->opt_perm_block : 2048;
-  long long cap = (long long)(1.5e9 / (18.0 * (double)c->G + 64));
+  long long cap = (long long)(3.0e9 / (18.0 * (double)c->G + 2.0 * (double)c->list_pitch + 64));
   if (cap < 1) cap = 1;
   if (cb > cap) cb = cap;
   if (cb > C_total) cb = C_total;
@@ -255,7 +255,7 @@ int fgs_destroy(fgs_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->x.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release();
-  c->set_order.release(); c->set_slow.release(); c->slow_ids.release(); c->ybin.release();
+  c->set_info.release(); c->es_lists.release(); c->slow_ids.release(); c->ybin.release();
   c->n1n2.release(); c->lm_H.release(); c->perm.release(); c->labels.release(); c->lm_B.release();
   c->scores.release(); c->rank16.release(); c->sabs.release(); c->sort_keys.release();
   c->sort_idx.release(); c->flags.release(); c->counters.release(); c->es_null.release();
@@ -336,13 +336,20 @@ int fgs_set_gene_sets(fgs_ctx *c, const int *offsets, const int *index, int n_se
   });
   FGS_TRY(c->set_off.ensure((size_t)n_sets + 1));
   FGS_TRY(c->set_idx.ensure((size_t)std::max<long long>(nnz, 1)));
-  FGS_TRY(c->set_order.ensure(n_sets));
-  FGS_TRY(c->set_slow.ensure(n_sets));
+  std::vector<int4> info(n_sets);
+  long long lp = 0;
+  for (int k = 0; k < n_sets; k++) {
+    const int sid = order[k], m = offsets[sid + 1] - offsets[sid];
+    info[k] = make_int4(offsets[sid], slow[sid] ? (m | (int)0x80000000) : m, (int)lp, sid);
+    if (!slow[sid]) lp += (m + 7) & ~7;  // 16-byte aligned list starts
+  }
+  if (lp > 0x7fffffffLL) { set_error("gene sets too large"); return FGS_ERR_UNSUPPORTED; }
+  c->list_pitch = std::max<long long>(lp, 8);
+  FGS_TRY(c->set_info.ensure(n_sets));
   FGS_TRY(c->slow_ids.ensure(std::max<size_t>(slow_ids.size(), 1)));
   FGS_TRY(h2d(c, c->set_off.p, offsets, (size_t)n_sets + 1));
   FGS_TRY(h2d(c, c->set_idx.p, idx0.data(), (size_t)nnz));
-  FGS_TRY(h2d(c, c->set_order.p, order.data(), (size_t)n_sets));
-  FGS_TRY(h2d(c, c->set_slow.p, slow.data(), (size_t)n_sets));
+  FGS_TRY(h2d(c, c->set_info.p, info.data(), (size_t)n_sets));
   FGS_TRY(h2d(c, c->slow_ids.p, slow_ids.data(), slow_ids.size()));
   FGS_TRY(sync(c));
   c->S = n_sets; c->nnz = nnz; c->max_set = max_idx; c->n_slow = (int)slow_ids.size();

@@ -80,8 +80,11 @@ struct fgs_ctx {
   int max_set = 0;
   fgs::DevBuf<int> set_off;        // [S+1]
   fgs::DevBuf<int> set_idx;        // [nnz] 0-based gene ids
-  fgs::DevBuf<int> set_order;      // [S] set ids by descending size
-  fgs::DevBuf<unsigned char> set_slow;  // [S] 1 = duplicates or too large for the bitmap kernel
+  // [S] in processing order (descending size): {member offset, m | slow << 31,
+  // offset of the set's ordered-rank list inside a column's list row, set id}
+  fgs::DevBuf<int4> set_info;
+  long long list_pitch = 0;        // uint16 elements per column of ordered-rank lists
+  fgs::DevBuf<uint16_t> es_lists;  // [Cb][list_pitch]
   std::vector<int> h_set_off;
   int n_slow = 0;
   fgs::DevBuf<int> slow_ids;       // [n_slow]

@@ -6,16 +6,20 @@
 //   neg = pos - w[o];  es = max(pos) > -min(neg) ? max(pos) : min(neg)
 // K5 replaces flexgsea_maxmean_ (:725-741) and flexgsea_mean_ (:755-767).
 //
-// es_wks_kernel (one persistent CTA per SM, one column at a time, a warp per
-// gene set): the column's rank array (uint16) and rank-ordered hit weights
-// (fp64) are staged in shared memory.  A set's members are ordered by rank
-// WITHOUT a comparison sort: every member sets one bit of a per-warp bitmap
-// over rank space; lane l owns a contiguous (odd-strided, bank-conflict-free)
-// range of bitmap words, so a popcount prefix over lanes gives each hit its
-// ordinal and a walk over the set bits emits the ranks in order.  The running
-// sum is then a blocked warp scan in fp64.  Bitmap bits are set with plain byte
-// read-modify-writes; the rare same-byte collisions inside one warp instruction
-// are found by a read-back and repaired.
+// Weighted KS runs as two persistent kernels per block of columns (one CTA per
+// SM, a column at a time, a warp per gene set), split so that each phase keeps
+// only what it needs in shared memory and 32 warps fit beside it:
+//  A  es_order_kernel: the column's rank array (uint16) is staged on chip.  A
+//     set's members are ordered by rank WITHOUT a comparison sort: every member
+//     sets one bit of a per-warp bitmap over rank space; lane l owns a
+//     contiguous (odd-strided, bank-conflict-free) range of bitmap words, so a
+//     popcount prefix over lanes gives each hit its ordinal and a walk over the
+//     set bits emits the ranks in order (uint16 lists, 2 nnz bytes per column).
+//     Bits are set with plain byte read-modify-writes; the rare same-byte
+//     collisions inside one warp instruction are found by a read-back and
+//     repaired.
+//  B  es_scan_kernel: the column's rank-ordered hit weights (fp64) are staged on
+//     chip; the running sum over a set's ordered hits is a blocked warp scan.
 //
 // Sets with duplicated members (same rank twice cannot live in a bitmap) or
 // more than ES_LISTCAP members go through es_wks_generic_kernel, an
@@ -41,132 +45,151 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-template <bool W_SMEM>
-__global__ void __launch_bounds__(512, 1)
-es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sabs, int G,
-              long long C, const int *__restrict__ set_off, const int *__restrict__ set_idx,
-              const int *__restrict__ set_order, const unsigned char *__restrict__ set_slow, int S,
-              int wpl, double *__restrict__ es_out) {
+// ---- phase A: order every set's members by rank (no weights needed) ----------
+// Persistent CTA per column, up to 32 warps, a warp per set.  Shared memory:
+// the column's rank array (uint16) + one rank-space bitmap per warp.  Output:
+// the set's 0-based ranks in increasing order, uint16, at lists[col][loff ..).
+__global__ void __launch_bounds__(1024, 1)
+es_order_kernel(const uint16_t *__restrict__ rank16, int G, long long C,
+                const int4 *__restrict__ set_info, const int *__restrict__ set_idx, int S, int wpl,
+                uint16_t *__restrict__ lists, long long Lp) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const size_t Gp = pitch_of(G);
   uint16_t *s_rank = (uint16_t *)smem;
-  size_t o = Gp * 2;
-  double *s_abs = (double *)(smem + o);
-  if (W_SMEM) o += Gp * 8;
-  uint32_t *bm_all = (uint32_t *)(smem + o);
-  o += (size_t)nwarps * 32 * wpl * 4;
-  uint16_t *list_all = (uint16_t *)(smem + o);
-  o += (size_t)nwarps * ES_LISTCAP * 2;
-  int *s_next = (int *)(smem + o);
-
+  uint32_t *bm_all = (uint32_t *)(smem + Gp * 2);
   uint32_t *bm = bm_all + (size_t)warp * 32 * wpl;
   unsigned char *bm8 = (unsigned char *)bm;
-  uint16_t *list = list_all + (size_t)warp * ES_LISTCAP;
   uint32_t *myw = bm + lane * wpl;
 
   for (int i = tid; i < nwarps * 32 * wpl; i += blockDim.x) bm_all[i] = 0;
 
   for (long long col = blockIdx.x; col < C; col += gridDim.x) {
     __syncthreads();
-    {  // stage the column: 16-byte vector copies (rows are 16-byte aligned)
+    {
       const uint4 *src = (const uint4 *)(rank16 + (size_t)col * Gp);
       uint4 *dst = (uint4 *)s_rank;
       for (int i = tid; i < (int)(Gp / 8); i += blockDim.x) dst[i] = __ldg(src + i);
-      if (W_SMEM) {
-        const double2 *ws = (const double2 *)(sabs + (size_t)col * Gp);
-        double2 *wd = (double2 *)s_abs;
-        for (int i = tid; i < (int)(Gp / 2); i += blockDim.x) wd[i] = __ldg(ws + i);
-      }
-      if (tid == 0) *s_next = 0;
     }
     __syncthreads();
-    const double *wsrc = W_SMEM ? s_abs : sabs + (size_t)col * Gp;
-    double *es_col = es_out + (size_t)col * S;
+    uint16_t *lcol = lists + (size_t)col * Lp;
 
-    for (;;) {
-      int k = 0;
-      if (lane == 0) k = atomicAdd(s_next, 1);
-      k = __shfl_sync(0xffffffffu, k, 0);
-      if (k >= S) break;
-      const int s = set_order[k];
-      if (set_slow[s]) continue;  // es_wks_generic_kernel does these
-      const int off = set_off[s], m = set_off[s + 1] - off;
-      const int nb = (m + 31) >> 5;  // <= 16
-
-      // ---- mark members in rank space -------------------------------------
-      uint32_t r0v[16];
+    for (int k = warp; k < S; k += nwarps) {
+      const int4 info = __ldg(set_info + k);  // {member offset, m | slow << 31, list offset, set id}
+      if (info.y < 0) continue;               // es_wks_generic_kernel does these
+      const int off = info.x, m = info.y;
+      const int nb = (m + 31) >> 5;           // <= 16
+      // member ids first (independent loads in flight), then the dependent smem chain
+      uint32_t rv[16];
 #pragma unroll
-      for (int b = 0; b < 16; b++) {
+      for (int b = 0; b < 16; b++)
         if (b < nb) {
-          int j = b * 32 + lane;
+          const int j = b * 32 + lane;
+          rv[b] = (j < m) ? (uint32_t)__ldg(set_idx + off + j) : 0xffffffffu;
+        }
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        if (b < nb) {
           uint32_t r0 = 0xffffffffu;
-          if (j < m) {
-            r0 = (uint32_t)s_rank[set_idx[off + j]] - 1u;
-            unsigned char v = bm8[r0 >> 3];
+          if (rv[b] != 0xffffffffu) {
+            r0 = (uint32_t)s_rank[rv[b]] - 1u;
+            const unsigned char v = bm8[r0 >> 3];
             bm8[r0 >> 3] = v | (unsigned char)(1u << (r0 & 7));
           }
-          r0v[b] = r0;
+          rv[b] = r0;
           __syncwarp();
         }
-      }
       for (;;) {  // read back; repair bits lost to same-byte collisions
         bool miss = false;
 #pragma unroll
-        for (int b = 0; b < 16; b++) {
+        for (int b = 0; b < 16; b++)
           if (b < nb) {
-            uint32_t r0 = r0v[b];
+            const uint32_t r0 = rv[b];
             if (r0 != 0xffffffffu) {
-              unsigned char v = bm8[r0 >> 3], bit = (unsigned char)(1u << (r0 & 7));
+              const unsigned char v = bm8[r0 >> 3], bit = (unsigned char)(1u << (r0 & 7));
               if (!(v & bit)) { miss = true; bm8[r0 >> 3] = v | bit; }
             }
             __syncwarp();
           }
-        }
         if (!__any_sync(0xffffffffu, miss)) break;
       }
-
-      // ---- ordinal of every hit: popcount prefix over lane-owned words ------
+      // ordinal of every hit: popcount prefix over lane-owned word ranges
       int cnt = 0;
       for (int i = 0; i < wpl; i++) cnt += __popc(myw[i]);
       int inc = cnt;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, d);
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
         if (lane >= d) inc += t;
       }
-      int pos = inc - cnt;
+      uint16_t *out = lcol + info.z + (inc - cnt);
       for (int i = 0; i < wpl; i++) {
         uint32_t w = myw[i];
         if (w) {
           myw[i] = 0;
           const int rb = (lane * wpl + i) << 5;
           do {
-            int b = __ffs(w) - 1;
+            const int b = __ffs(w) - 1;
             w &= w - 1;
-            list[pos++] = (uint16_t)(rb + b);
+            *out++ = (uint16_t)(rb + b);
           } while (w);
         }
       }
       __syncwarp();
+    }
+  }
+}
 
-      // ---- running sum: lane takes hits [lane*c, lane*c + c) ----------------
-      const int c = nb, k0 = lane * c;
+// ---- phase B: running sum over the ordered hits ------------------------------
+// Persistent CTA per column, 32 warps, a warp per set.  Shared memory: the
+// column's rank-ordered hit weights (fp64).  Lane l takes hits [l*c, l*c + c):
+// local sums, one warp scan, then the running maxima / minima.
+constexpr int ES_SCAN_THREADS = 768;  // 24 warps: 85 registers each, no spills
+template <bool W_SMEM>
+__global__ void __launch_bounds__(ES_SCAN_THREADS, 1)
+es_scan_kernel(const double *__restrict__ sabs, int G, long long C,
+               const int4 *__restrict__ set_info, int S, const uint16_t *__restrict__ lists,
+               long long Lp, double *__restrict__ es_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const size_t Gp = pitch_of(G);
+  double *s_abs = (double *)smem;
+
+  for (long long col = blockIdx.x; col < C; col += gridDim.x) {
+    __syncthreads();
+    if (W_SMEM) {
+      const double2 *ws = (const double2 *)(sabs + (size_t)col * Gp);
+      double2 *wd = (double2 *)s_abs;
+      for (int i = tid; i < (int)(Gp / 2); i += blockDim.x) wd[i] = __ldg(ws + i);
+    }
+    __syncthreads();
+    const double *wsrc = W_SMEM ? s_abs : sabs + (size_t)col * Gp;
+    const uint16_t *lcol = lists + (size_t)col * Lp;
+    double *es_col = es_out + (size_t)col * S;
+
+    for (int k = warp; k < S; k += nwarps) {
+      const int4 info = __ldg(set_info + k);
+      if (info.y < 0) continue;
+      const int m = info.y;
+      const uint16_t *list = lcol + info.z;
+      const int c = (m + 31) >> 5, k0 = lane * c;
+      uint16_t rr[16];
+#pragma unroll
+      for (int t = 0; t < 16; t++)
+        if (t < c) rr[t] = (k0 + t < m) ? list[k0 + t] : (uint16_t)0;
       double wv[16];
       double lsum = 0.0;
 #pragma unroll
-      for (int t = 0; t < 16; t++) {
+      for (int t = 0; t < 16; t++)
         if (t < c) {
-          double w = 0.0;
-          if (k0 + t < m) w = wsrc[list[k0 + t]];
+          const double w = (k0 + t < m) ? wsrc[rr[t]] : 0.0;
           wv[t] = w;
           lsum += w;
         }
-      }
       double incw = lsum;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        double t = __shfl_up_sync(0xffffffffu, incw, d);
+        const double t = __shfl_up_sync(0xffffffffu, incw, d);
         if (lane >= d) incw += t;
       }
       const double W = __shfl_sync(0xffffffffu, incw, 31);
@@ -175,26 +198,24 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
       const double invW = 1.0 / W, invGm = 1.0 / (double)(G - m);
       double mx = -INFINITY, mn = INFINITY;
 #pragma unroll
-      for (int t = 0; t < 16; t++) {
+      for (int t = 0; t < 16; t++)
         if (t < c) {
           const int kk = k0 + t;
           if (kk < m) {
             cum += wv[t];
-            const int r = (int)list[kk] + 1;
+            const int r = (int)rr[t] + 1;
             const double ps = cum * invW - (double)(r - (kk + 1)) * invGm;
             const double ng = ps - wv[t] * invW;
             mx = fmax(mx, ps);
             mn = fmin(mn, ng);
           }
         }
-      }
       mx = warp_max(mx);
       mn = warp_min(mn);
-      __syncwarp();  // list reads done before the next set overwrites it
       if (lane == 0) {
-        double es = (mx > -mn) ? mx : mn;                       // strict, :833
+        double es = (mx > -mn) ? mx : mn;                      // strict, :833
         if (W == 0.0 || m == G || m == 0) es = nan("");        // 0/0 in the reference
-        es_col[s] = es;
+        es_col[info.w] = es;
       }
     }
   }
@@ -301,34 +322,38 @@ int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, in
   if (c->opt_force_generic)
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
   const size_t Gp = pitch_of(G);
-  int wpl = (int)((G + 1023) / 1024) | 1;  // odd stride: conflict-free lane-owned ranges
-  const size_t per_warp = (size_t)32 * wpl * 4 + (size_t)ES_LISTCAP * 2;
+  const int wpl = (int)((G + 1023) / 1024) | 1;  // odd stride: conflict-free lane-owned ranges
+  const size_t per_warp = (size_t)32 * wpl * 4;
   const size_t budget = (size_t)c->smem_optin;
-  size_t base_full = Gp * 2 + Gp * 8 + 16, base_rank = Gp * 2 + 16;
-  bool w_smem = base_full + 4 * per_warp <= budget;  // want >= 4 warps with weights on chip
-  size_t base = w_smem ? base_full : base_rank;
-  if (base + per_warp > budget) {
-    // not even one warp fits: everything through the order-free kernel
+  if (Gp * 2 + per_warp > budget)  // not even one warp fits: the order-free kernel does everything
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
-  }
-  int nwarps = (int)((budget - base) / per_warp);
-  if (nwarps > 16) nwarps = 16;
-  size_t smem = base + (size_t)nwarps * per_warp;
   int grid = c->num_sms;
   if (grid > C) grid = (int)C;
-  if (w_smem) {
-    auto k = es_wks_kernel<true>;
-    FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, nwarps * 32, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_off.p, c->set_idx.p,
-                                              c->set_order.p, c->set_slow.p, c->S, wpl, d_es);
-  } else {
-    auto k = es_wks_kernel<false>;
-    FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, nwarps * 32, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_off.p, c->set_idx.p,
-                                              c->set_order.p, c->set_slow.p, c->S, wpl, d_es);
+  {  // phase A
+    int nwarps = (int)((budget - Gp * 2) / per_warp);
+    if (nwarps > 32) nwarps = 32;
+    const size_t smem = Gp * 2 + (size_t)nwarps * per_warp;
+    FGS_TRY(c->es_lists.ensure((size_t)c->list_pitch * C));
+    FGS_CUDA(cudaFuncSetAttribute(es_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    es_order_kernel<<<grid, nwarps * 32, smem, c->stream>>>(d_rank16, G, C, c->set_info.p, c->set_idx.p,
+                                                            c->S, wpl, c->es_lists.p, c->list_pitch);
+    c->launches++;
+    FGS_CUDA(cudaGetLastError());
   }
-  c->launches++;
-  FGS_CUDA(cudaGetLastError());
+  {  // phase B
+    const bool w_smem = Gp * 8 <= budget;
+    const size_t smem = w_smem ? Gp * 8 : 0;
+    if (w_smem) {
+      auto k = es_scan_kernel<true>;
+      FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, ES_SCAN_THREADS, smem, c->stream>>>(d_sabs, G, C, c->set_info.p, c->S, c->es_lists.p, c->list_pitch, d_es);
+    } else {
+      es_scan_kernel<false><<<grid * 2, ES_SCAN_THREADS, 0, c->stream>>>(d_sabs, G, C, c->set_info.p, c->S,
+                                                              c->es_lists.p, c->list_pitch, d_es);
+    }
+    c->launches++;
+    FGS_CUDA(cudaGetLastError());
+  }
   if (c->n_slow > 0)
     FGS_TRY(launch_es_wks_generic(c, d_rank16, d_sabs, G, C, c->slow_ids.p, c->n_slow, d_es));
   return FGS_OK;
