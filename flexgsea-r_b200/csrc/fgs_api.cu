@@ -341,7 +341,7 @@ int fgs_set_gene_sets(fgs_ctx *c, const int *offsets, const int *index, int n_se
   for (int k = 0; k < n_sets; k++) {
     const int sid = order[k], m = offsets[sid + 1] - offsets[sid];
     info[k] = make_int4(offsets[sid], slow[sid] ? (m | (int)0x80000000) : m, (int)lp, sid);
-    if (!slow[sid]) lp += (m + 7) & ~7;  // 16-byte aligned list starts
+    if (!slow[sid]) lp += (m + 15) & ~15;  // 32-byte aligned list starts (16 ranks per lane max)
   }
   if (lp > 0x7fffffffLL) { set_error("gene sets too large"); return FGS_ERR_UNSUPPORTED; }
   c->list_pitch = std::max<long long>(lp, 8);

@@ -47,8 +47,96 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // ---- phase A: order every set's members by rank (no weights needed) ----------
 // Persistent CTA per column, up to 32 warps, a warp per set.  Shared memory:
-// the column's rank array (uint16) + one rank-space bitmap per warp.  Output:
-// the set's 0-based ranks in increasing order, uint16, at lists[col][loff ..).
+// the column's rank array (uint16), and per warp a rank-space bitmap plus a
+// per-word exclusive popcount prefix.  Output: the set's 0-based ranks in
+// increasing order, uint16, at lists[col][loff ..).
+//
+// Per set, with NB = batches of 32 members (compile-time class 1/2/4/8/16):
+//  1. every member sets its bit (byte read-modify-write; bits lost to same-byte
+//     collisions inside one warp instruction are found by a read-back and
+//     repaired),
+//  2. lane l popcounts its own contiguous word range (uint4 loads; the range
+//     stride is 4*odd words, so those are bank-conflict free), a warp scan turns
+//     the lane totals into bases, and the exclusive prefix of every word is
+//     stored,
+//  3. every member reads its word's prefix, adds the popcount of the lower bits
+//     of its word -- that is its ordinal -- and stores its rank at that slot.
+// No comparison sort, no divergent bit walk.
+template <int NB>
+__device__ __forceinline__ void order_one_set(const uint16_t *__restrict__ s_rank, uint32_t *bm,
+                                              uint16_t *wpre, int lane, int wpl,
+                                              const int *__restrict__ set_idx, int off, int m,
+                                              uint16_t *__restrict__ out) {
+  unsigned char *bm8 = (unsigned char *)bm;
+  uint32_t rv[NB];
+#pragma unroll
+  for (int b = 0; b < NB; b++) {  // member ids first: independent loads in flight
+    const int j = b * 32 + lane;
+    rv[b] = (j < m) ? (uint32_t)__ldg(set_idx + off + j) : 0xffffffffu;
+  }
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    if (rv[b] != 0xffffffffu) {
+      const uint32_t r0 = (uint32_t)s_rank[rv[b]] - 1u;
+      const unsigned char v = bm8[r0 >> 3];
+      bm8[r0 >> 3] = v | (unsigned char)(1u << (r0 & 7));
+      rv[b] = r0;
+    }
+  }
+  __syncwarp();
+  for (;;) {
+    bool miss = false;
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+      const uint32_t r0 = rv[b];
+      if (r0 != 0xffffffffu) {
+        const unsigned char v = bm8[r0 >> 3], bit = (unsigned char)(1u << (r0 & 7));
+        if (!(v & bit)) { miss = true; bm8[r0 >> 3] = v | bit; }
+      }
+    }
+    __syncwarp();
+    if (!__any_sync(0xffffffffu, miss)) break;
+  }
+  // per-word exclusive prefix over the lane's range, then the lane bases
+  const int wpl4 = wpl >> 2;
+  uint4 *my4 = (uint4 *)(bm + lane * wpl);
+  uint2 *pre2 = (uint2 *)(wpre + lane * wpl);
+  int cnt = 0;
+  for (int i = 0; i < wpl4; i++) {
+    const uint4 v = my4[i];
+    const int c0 = cnt, c1 = c0 + __popc(v.x), c2 = c1 + __popc(v.y), c3 = c2 + __popc(v.z);
+    cnt = c3 + __popc(v.w);
+    pre2[i] = make_uint2((uint32_t)c0 | ((uint32_t)c1 << 16), (uint32_t)c2 | ((uint32_t)c3 << 16));
+  }
+  int inc = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  const int base = inc - cnt;  // hits owned by lower lanes
+  // every lane needs every owner's base: broadcast through the prefix table
+  const uint32_t base2 = (uint32_t)base * 0x00010001u;
+  for (int i = 0; i < wpl4; i++) {
+    uint2 v = pre2[i];
+    v.x += base2; v.y += base2;  // no carry between halves: totals < 65536
+    pre2[i] = v;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    const uint32_t r0 = rv[b];
+    if (r0 != 0xffffffffu) {
+      const uint32_t wd = r0 >> 5;
+      const int ord = (int)wpre[wd] + __popc(bm[wd] & ((1u << (r0 & 31)) - 1u));
+      out[ord] = (uint16_t)r0;
+    }
+  }
+  __syncwarp();
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (int i = 0; i < wpl4; i++) my4[i] = z;
+}
+
 __global__ void __launch_bounds__(1024, 1)
 es_order_kernel(const uint16_t *__restrict__ rank16, int G, long long C,
                 const int4 *__restrict__ set_info, const int *__restrict__ set_idx, int S, int wpl,
@@ -58,9 +146,9 @@ es_order_kernel(const uint16_t *__restrict__ rank16, int G, long long C,
   const size_t Gp = pitch_of(G);
   uint16_t *s_rank = (uint16_t *)smem;
   uint32_t *bm_all = (uint32_t *)(smem + Gp * 2);
+  uint16_t *pre_all = (uint16_t *)(bm_all + (size_t)nwarps * 32 * wpl);
   uint32_t *bm = bm_all + (size_t)warp * 32 * wpl;
-  unsigned char *bm8 = (unsigned char *)bm;
-  uint32_t *myw = bm + lane * wpl;
+  uint16_t *wpre = pre_all + (size_t)warp * 32 * wpl;
 
   for (int i = tid; i < nwarps * 32 * wpl; i += blockDim.x) bm_all[i] = 0;
 
@@ -73,78 +161,94 @@ es_order_kernel(const uint16_t *__restrict__ rank16, int G, long long C,
     }
     __syncthreads();
     uint16_t *lcol = lists + (size_t)col * Lp;
-
     for (int k = warp; k < S; k += nwarps) {
       const int4 info = __ldg(set_info + k);  // {member offset, m | slow << 31, list offset, set id}
       if (info.y < 0) continue;               // es_wks_generic_kernel does these
       const int off = info.x, m = info.y;
-      const int nb = (m + 31) >> 5;           // <= 16
-      // member ids first (independent loads in flight), then the dependent smem chain
-      uint32_t rv[16];
-#pragma unroll
-      for (int b = 0; b < 16; b++)
-        if (b < nb) {
-          const int j = b * 32 + lane;
-          rv[b] = (j < m) ? (uint32_t)__ldg(set_idx + off + j) : 0xffffffffu;
-        }
-#pragma unroll
-      for (int b = 0; b < 16; b++)
-        if (b < nb) {
-          uint32_t r0 = 0xffffffffu;
-          if (rv[b] != 0xffffffffu) {
-            r0 = (uint32_t)s_rank[rv[b]] - 1u;
-            const unsigned char v = bm8[r0 >> 3];
-            bm8[r0 >> 3] = v | (unsigned char)(1u << (r0 & 7));
-          }
-          rv[b] = r0;
-          __syncwarp();
-        }
-      for (;;) {  // read back; repair bits lost to same-byte collisions
-        bool miss = false;
-#pragma unroll
-        for (int b = 0; b < 16; b++)
-          if (b < nb) {
-            const uint32_t r0 = rv[b];
-            if (r0 != 0xffffffffu) {
-              const unsigned char v = bm8[r0 >> 3], bit = (unsigned char)(1u << (r0 & 7));
-              if (!(v & bit)) { miss = true; bm8[r0 >> 3] = v | bit; }
-            }
-            __syncwarp();
-          }
-        if (!__any_sync(0xffffffffu, miss)) break;
-      }
-      // ordinal of every hit: popcount prefix over lane-owned word ranges
-      int cnt = 0;
-      for (int i = 0; i < wpl; i++) cnt += __popc(myw[i]);
-      int inc = cnt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
-      }
-      uint16_t *out = lcol + info.z + (inc - cnt);
-      for (int i = 0; i < wpl; i++) {
-        uint32_t w = myw[i];
-        if (w) {
-          myw[i] = 0;
-          const int rb = (lane * wpl + i) << 5;
-          do {
-            const int b = __ffs(w) - 1;
-            w &= w - 1;
-            *out++ = (uint16_t)(rb + b);
-          } while (w);
-        }
-      }
-      __syncwarp();
+      uint16_t *out = lcol + info.z;
+      if (m <= 32) order_one_set<1>(s_rank, bm, wpre, lane, wpl, set_idx, off, m, out);
+      else if (m <= 64) order_one_set<2>(s_rank, bm, wpre, lane, wpl, set_idx, off, m, out);
+      else if (m <= 128) order_one_set<4>(s_rank, bm, wpre, lane, wpl, set_idx, off, m, out);
+      else if (m <= 256) order_one_set<8>(s_rank, bm, wpre, lane, wpl, set_idx, off, m, out);
+      else order_one_set<16>(s_rank, bm, wpre, lane, wpl, set_idx, off, m, out);
     }
   }
 }
 
 // ---- phase B: running sum over the ordered hits ------------------------------
-// Persistent CTA per column, 32 warps, a warp per set.  Shared memory: the
-// column's rank-ordered hit weights (fp64).  Lane l takes hits [l*c, l*c + c):
-// local sums, one warp scan, then the running maxima / minima.
-constexpr int ES_SCAN_THREADS = 768;  // 24 warps: 85 registers each, no spills
+// Persistent CTA per column, a warp per set.  Shared memory: the column's
+// rank-ordered hit weights (fp64).  Lane l takes hits [l*NB, l*NB + NB) (one
+// vector load of its uint16 ranks): local sums, one warp scan, then the running
+// maxima / minima.
+template <int NB>
+__device__ __forceinline__ void load_ranks(const uint16_t *__restrict__ p, uint32_t (&rr)[NB]) {
+  if constexpr (NB == 1) {
+    rr[0] = *p;
+  } else if constexpr (NB == 2) {
+    const uint32_t v = *(const uint32_t *)p;
+    rr[0] = v & 0xffffu; rr[1] = v >> 16;
+  } else if constexpr (NB == 4) {
+    const uint2 v = *(const uint2 *)p;
+    rr[0] = v.x & 0xffffu; rr[1] = v.x >> 16; rr[2] = v.y & 0xffffu; rr[3] = v.y >> 16;
+  } else {
+#pragma unroll
+    for (int q = 0; q < NB / 8; q++) {
+      const uint4 v = *(const uint4 *)(p + 8 * q);
+      rr[8 * q + 0] = v.x & 0xffffu; rr[8 * q + 1] = v.x >> 16;
+      rr[8 * q + 2] = v.y & 0xffffu; rr[8 * q + 3] = v.y >> 16;
+      rr[8 * q + 4] = v.z & 0xffffu; rr[8 * q + 5] = v.z >> 16;
+      rr[8 * q + 6] = v.w & 0xffffu; rr[8 * q + 7] = v.w >> 16;
+    }
+  }
+}
+
+template <int NB>
+__device__ __forceinline__ double scan_one_set(const double *__restrict__ wsrc,
+                                               const uint16_t *__restrict__ list, int lane, int m,
+                                               int G) {
+  const int k0 = lane * NB;
+  uint32_t rr[NB];
+  load_ranks<NB>(list + k0, rr);
+  double wv[NB];
+  double lsum = 0.0;
+#pragma unroll
+  for (int t = 0; t < NB; t++) {
+    const double w = (k0 + t < m) ? wsrc[rr[t]] : 0.0;
+    wv[t] = w;
+    lsum += w;
+  }
+  double incw = lsum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, incw, d);
+    if (lane >= d) incw += t;
+  }
+  const double W = __shfl_sync(0xffffffffu, incw, 31);
+  double cum = incw - lsum;  // exclusive prefix of the lane (exact: incw = prefix + lsum)
+  const double invW = 1.0 / W, invGm = 1.0 / (double)(G - m);
+  double mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+  for (int t = 0; t < NB; t++) {
+    const int kk = k0 + t;
+    if (kk < m) {
+      cum += wv[t];
+      const double ps = cum * invW - (double)((int)rr[t] - kk) * invGm;  // r - k with r = rr+1, k = kk+1
+      const double ng = ps - wv[t] * invW;
+      mx = fmax(mx, ps);
+      mn = fmin(mn, ng);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  double es = (mx > -mn) ? mx : mn;                      // strict, :833
+  if (W == 0.0 || m == G || m == 0) es = nan("");        // 0/0 in the reference
+  return es;
+}
+
+constexpr int ES_SCAN_THREADS = 640;  // 20 warps: up to 102 registers each, no spills
 template <bool W_SMEM>
 __global__ void __launch_bounds__(ES_SCAN_THREADS, 1)
 es_scan_kernel(const double *__restrict__ sabs, int G, long long C,
@@ -172,51 +276,13 @@ es_scan_kernel(const double *__restrict__ sabs, int G, long long C,
       if (info.y < 0) continue;
       const int m = info.y;
       const uint16_t *list = lcol + info.z;
-      const int c = (m + 31) >> 5, k0 = lane * c;
-      uint16_t rr[16];
-#pragma unroll
-      for (int t = 0; t < 16; t++)
-        if (t < c) rr[t] = (k0 + t < m) ? list[k0 + t] : (uint16_t)0;
-      double wv[16];
-      double lsum = 0.0;
-#pragma unroll
-      for (int t = 0; t < 16; t++)
-        if (t < c) {
-          const double w = (k0 + t < m) ? wsrc[rr[t]] : 0.0;
-          wv[t] = w;
-          lsum += w;
-        }
-      double incw = lsum;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, incw, d);
-        if (lane >= d) incw += t;
-      }
-      const double W = __shfl_sync(0xffffffffu, incw, 31);
-      double cum = __shfl_up_sync(0xffffffffu, incw, 1);
-      if (lane == 0) cum = 0.0;
-      const double invW = 1.0 / W, invGm = 1.0 / (double)(G - m);
-      double mx = -INFINITY, mn = INFINITY;
-#pragma unroll
-      for (int t = 0; t < 16; t++)
-        if (t < c) {
-          const int kk = k0 + t;
-          if (kk < m) {
-            cum += wv[t];
-            const int r = (int)rr[t] + 1;
-            const double ps = cum * invW - (double)(r - (kk + 1)) * invGm;
-            const double ng = ps - wv[t] * invW;
-            mx = fmax(mx, ps);
-            mn = fmin(mn, ng);
-          }
-        }
-      mx = warp_max(mx);
-      mn = warp_min(mn);
-      if (lane == 0) {
-        double es = (mx > -mn) ? mx : mn;                      // strict, :833
-        if (W == 0.0 || m == G || m == 0) es = nan("");        // 0/0 in the reference
-        es_col[info.w] = es;
-      }
+      double es;
+      if (m <= 32) es = scan_one_set<1>(wsrc, list, lane, m, G);
+      else if (m <= 64) es = scan_one_set<2>(wsrc, list, lane, m, G);
+      else if (m <= 128) es = scan_one_set<4>(wsrc, list, lane, m, G);
+      else if (m <= 256) es = scan_one_set<8>(wsrc, list, lane, m, G);
+      else es = scan_one_set<16>(wsrc, list, lane, m, G);
+      if (lane == 0) es_col[info.w] = es;
     }
   }
 }
@@ -322,8 +388,11 @@ int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, in
   if (c->opt_force_generic)
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
   const size_t Gp = pitch_of(G);
-  const int wpl = (int)((G + 1023) / 1024) | 1;  // odd stride: conflict-free lane-owned ranges
-  const size_t per_warp = (size_t)32 * wpl * 4;
+  // words per lane: 4 * odd, so the lanes' uint4 loads of their own range are conflict free
+  int wpl = (int)((G + 1023) / 1024);
+  wpl = (wpl + 3) & ~3;
+  if (((wpl >> 2) & 1) == 0) wpl += 4;
+  const size_t per_warp = (size_t)32 * wpl * 6;  // bitmap (4 B/word) + per-word prefix (2 B/word)
   const size_t budget = (size_t)c->smem_optin;
   if (Gp * 2 + per_warp > budget)  // not even one warp fits: the order-free kernel does everything
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
@@ -333,7 +402,7 @@ int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, in
     int nwarps = (int)((budget - Gp * 2) / per_warp);
     if (nwarps > 32) nwarps = 32;
     const size_t smem = Gp * 2 + (size_t)nwarps * per_warp;
-    FGS_TRY(c->es_lists.ensure((size_t)c->list_pitch * C));
+    FGS_TRY(c->es_lists.ensure((size_t)c->list_pitch * C + 1024));  // + slack: vector loads past the last list
     FGS_CUDA(cudaFuncSetAttribute(es_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     es_order_kernel<<<grid, nwarps * 32, smem, c->stream>>>(d_rank16, G, C, c->set_info.p, c->set_idx.p,
                                                             c->S, wpl, c->es_lists.p, c->list_pitch);
