@@ -166,7 +166,7 @@ struct StageTimer {
 // (scores 8G + rank 2G + weights 8G bytes per column) stays ~<= 1.5 GB
 static long long block_columns(fgs_ctx *c, long long C_total) {
   long long cb = c->opt_perm_block > 0 ? c->opt_perm_block : 2048;
-  long long cap = (long long)(3.0e9 / (18.0 * (double)c->G + 2.0 * (double)c->list_pitch + 64));
+  long long cap = (long long)(3.0e9 / (18.0 * (double)c->G + 64));
   if (cap < 1) cap = 1;
   if (cb > cap) cb = cap;
   if (cb > C_total) cb = C_total;

@@ -6,23 +6,17 @@
 //   neg = pos - w[o];  es = max(pos) > -min(neg) ? max(pos) : min(neg)
 // K5 replaces flexgsea_maxmean_ (:725-741) and flexgsea_mean_ (:755-767).
 //
-// Weighted KS runs as two persistent kernels per block of columns (one CTA per
-// SM, a column at a time, a warp per gene set), split so that each phase keeps
-// only what it needs in shared memory and 32 warps fit beside it:
-//  A  es_order_kernel: the column's rank array (uint16) is staged on chip.  A
-//     set's members are ordered by rank WITHOUT a comparison sort: every member
-//     sets one bit of a per-warp bitmap over rank space; lane l owns a
-//     contiguous (odd-strided, bank-conflict-free) range of bitmap words, so a
-//     popcount prefix over lanes gives each hit its ordinal and a walk over the
-//     set bits emits the ranks in order (uint16 lists, 2 nnz bytes per column).
-//     Bits are set with plain byte read-modify-writes; the rare same-byte
-//     collisions inside one warp instruction are found by a read-back and
-//     repaired.
-//  B  es_scan_kernel: the column's rank-ordered hit weights (fp64) are staged on
-//     chip; the running sum over a set's ordered hits is a blocked warp scan.
+// es_wks_kernel: one persistent CTA per SM, a column at a time, a warp per gene
+// set.  The column's rank array (uint16, gene -> rank) and its rank-ordered hit
+// weights (fp64, rank -> |score|^p) are staged in shared memory (10 G bytes).  A
+// warp gathers its set's ranks, sorts them IN REGISTERS with a bitonic network
+// on packed uint16 pairs (no shared-memory scratch, so the warp count is bound
+// by registers only), and then runs the running sum as lane-local sums + one
+// warp scan.  Sets are handled in descending size in five compile-time size
+// classes (32 * {1,2,4,8,16} members).
 //
-// Sets with duplicated members (same rank twice cannot live in a bitmap) or
-// more than ES_LISTCAP members go through es_wks_generic_kernel, an
+// Sets with duplicated members (R keeps them; a pad-free distinct-rank sort
+// cannot) or more than ES_LISTCAP members go through es_wks_generic_kernel, an
 // O(m^2 / 32) warp kernel that needs no ordering at all: max/min over the
 // members of pos/neg is order independent once each member knows its ordinal
 // and prefix weight, which it gets by comparing against every other member.
@@ -45,175 +39,100 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// ---- phase A: order every set's members by rank (no weights needed) ----------
-// Persistent CTA per column, up to 32 warps, a warp per set.  Shared memory:
-// the column's rank array (uint16), and per warp a rank-space bitmap plus a
-// per-word exclusive popcount prefix.  Output: the set's 0-based ranks in
-// increasing order, uint16, at lists[col][loff ..).
-//
-// Per set, with NB = batches of 32 members (compile-time class 1/2/4/8/16):
-//  1. every member sets its bit (byte read-modify-write; bits lost to same-byte
-//     collisions inside one warp instruction are found by a read-back and
-//     repaired),
-//  2. lane l popcounts its own contiguous word range (uint4 loads; the range
-//     stride is 4*odd words, so those are bank-conflict free), a warp scan turns
-//     the lane totals into bases, and the exclusive prefix of every word is
-//     stored,
-//  3. every member reads its word's prefix, adds the popcount of the lower bits
-//     of its word -- that is its ordinal -- and stores its rank at that slot.
-// No comparison sort, no divergent bit walk.
+// ---- in-register bitonic sort of a set's ranks --------------------------------
+// N = 32 * NB uint16 keys per warp, NB per lane, two per 32-bit register
+// (VIMNMX.U16x2 compares both at once).  Blocked layout: element e = lane * NB +
+// slot, so after the sort lane l holds the hits with ordinals [l*NB, l*NB + NB)
+// -- exactly the distribution the running-sum scan wants.  Pads are 0xFFFF.
+__device__ __forceinline__ uint32_t minmax2(uint32_t a, uint32_t b, bool take_min) {
+  return take_min ? __vminu2(a, b) : __vmaxu2(a, b);
+}
+
 template <int NB>
-__device__ __forceinline__ void order_one_set(const uint16_t *__restrict__ s_rank, uint32_t *bm,
-                                              uint16_t *wpre, int lane, int wpl,
-                                              const int *__restrict__ set_idx, int off, int m,
-                                              uint16_t *__restrict__ out) {
-  unsigned char *bm8 = (unsigned char *)bm;
-  uint32_t rv[NB];
+__device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[(NB + 1) / 2], int lane) {
+  constexpr int N = 32 * NB;
+  if constexpr (NB == 1) {
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1)
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, v[0], j);
+        const bool asc = (lane & k) == 0, lower = (lane & j) == 0;
+        v[0] = (asc == lower) ? min(v[0], o) : max(v[0], o);
+      }
+  } else {
+    constexpr int NR = NB / 2;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        if (j >= NB) {  // partner in lane ^ (j / NB), same slot
+          const int lj = j / NB;
+          const bool asc = (lane & (k / NB)) == 0, lower = (lane & lj) == 0;
+          const bool take_min = asc == lower;
+#pragma unroll
+          for (int q = 0; q < NR; q++) {
+            const uint32_t o = __shfl_xor_sync(0xffffffffu, v[q], lj);
+            v[q] = minmax2(v[q], o, take_min);
+          }
+        } else if (j >= 2) {  // partner register q ^ (j / 2), same half
+#pragma unroll
+          for (int q = 0; q < NR; q++) {
+            const int qb = q ^ (j >> 1);
+            if (qb > q) {
+              // direction of element lane * NB + 2q: bit k of it
+              const bool asc = (k >= NB) ? ((lane & (k / NB)) == 0) : (((2 * q) & k) == 0);
+              const uint32_t a = v[q], b = v[qb];
+              v[q] = minmax2(a, b, asc);
+              v[qb] = minmax2(a, b, !asc);
+            }
+          }
+        } else {  // j == 1: the two halves of one register
+#pragma unroll
+          for (int q = 0; q < NR; q++) {
+            const bool asc = (k >= NB) ? ((lane & (k / NB)) == 0) : (((2 * q) & k) == 0);
+            const uint32_t t = __byte_perm(v[q], v[q], 0x1032);
+            const uint32_t lo = minmax2(v[q], t, asc), hi = minmax2(v[q], t, !asc);
+            v[q] = __byte_perm(lo, hi, 0x5410);
+          }
+        }
+      }
+    }
+  }
+}
+
+// One set, one warp: gather the members' ranks, sort them in registers, then the
+// running sum over the ordered hits (lane-local sums, one warp scan, running
+// maxima / minima).  Returns the ES (valid in every lane).
+template <int NB, bool W_SMEM>
+__device__ __forceinline__ double wks_one_set(const uint16_t *__restrict__ s_rank,
+                                              const double *__restrict__ wsrc,
+                                              const int *__restrict__ set_idx, int off, int m, int G,
+                                              int lane) {
+  constexpr int NR = (NB + 1) / 2;
+  uint32_t gid[NB];
 #pragma unroll
   for (int b = 0; b < NB; b++) {  // member ids first: independent loads in flight
     const int j = b * 32 + lane;
-    rv[b] = (j < m) ? (uint32_t)__ldg(set_idx + off + j) : 0xffffffffu;
+    gid[b] = (j < m) ? (uint32_t)__ldg(set_idx + off + j) : 0xffffffffu;
   }
+  uint32_t v[NR];
 #pragma unroll
-  for (int b = 0; b < NB; b++) {
-    if (rv[b] != 0xffffffffu) {
-      const uint32_t r0 = (uint32_t)s_rank[rv[b]] - 1u;
-      const unsigned char v = bm8[r0 >> 3];
-      bm8[r0 >> 3] = v | (unsigned char)(1u << (r0 & 7));
-      rv[b] = r0;
-    }
+  for (int q = 0; q < NR; q++) {
+    uint32_t lo = 0xffffu, hi = 0xffffu;
+    if (gid[2 * q] != 0xffffffffu) lo = (uint32_t)s_rank[gid[2 * q]] - 1u;
+    if (NB > 1) { if (gid[(2 * q + 1) % NB] != 0xffffffffu) hi = (uint32_t)s_rank[gid[(2 * q + 1) % NB]] - 1u; }
+    v[q] = NB > 1 ? (lo | (hi << 16)) : lo;
   }
-  __syncwarp();
-  for (;;) {
-    bool miss = false;
-#pragma unroll
-    for (int b = 0; b < NB; b++) {
-      const uint32_t r0 = rv[b];
-      if (r0 != 0xffffffffu) {
-        const unsigned char v = bm8[r0 >> 3], bit = (unsigned char)(1u << (r0 & 7));
-        if (!(v & bit)) { miss = true; bm8[r0 >> 3] = v | bit; }
-      }
-    }
-    __syncwarp();
-    if (!__any_sync(0xffffffffu, miss)) break;
-  }
-  // per-word exclusive prefix over the lane's range, then the lane bases
-  const int wpl4 = wpl >> 2;
-  uint4 *my4 = (uint4 *)(bm + lane * wpl);
-  uint2 *pre2 = (uint2 *)(wpre + lane * wpl);
-  int cnt = 0;
-  for (int i = 0; i < wpl4; i++) {
-    const uint4 v = my4[i];
-    const int c0 = cnt, c1 = c0 + __popc(v.x), c2 = c1 + __popc(v.y), c3 = c2 + __popc(v.z);
-    cnt = c3 + __popc(v.w);
-    pre2[i] = make_uint2((uint32_t)c0 | ((uint32_t)c1 << 16), (uint32_t)c2 | ((uint32_t)c3 << 16));
-  }
-  int inc = cnt;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc += t;
-  }
-  const int base = inc - cnt;  // hits owned by lower lanes
-  // every lane needs every owner's base: broadcast through the prefix table
-  const uint32_t base2 = (uint32_t)base * 0x00010001u;
-  for (int i = 0; i < wpl4; i++) {
-    uint2 v = pre2[i];
-    v.x += base2; v.y += base2;  // no carry between halves: totals < 65536
-    pre2[i] = v;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int b = 0; b < NB; b++) {
-    const uint32_t r0 = rv[b];
-    if (r0 != 0xffffffffu) {
-      const uint32_t wd = r0 >> 5;
-      const int ord = (int)wpre[wd] + __popc(bm[wd] & ((1u << (r0 & 31)) - 1u));
-      out[ord] = (uint16_t)r0;
-    }
-  }
-  __syncwarp();
-  const uint4 z = make_uint4(0, 0, 0, 0);
-  for (int i = 0; i < wpl4; i++) my4[i] = z;
-}
+  bitonic_sort_ranks<NB>(v, lane);
 
-__global__ void __launch_bounds__(1024, 1)
-es_order_kernel(const uint16_t *__restrict__ rank16, int G, long long C,
-                const int4 *__restrict__ set_info, const int *__restrict__ set_idx, int S, int wpl,
-                uint16_t *__restrict__ lists, long long Lp) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const size_t Gp = pitch_of(G);
-  uint16_t *s_rank = (uint16_t *)smem;
-  uint32_t *bm_all = (uint32_t *)(smem + Gp * 2);
-  uint16_t *pre_all = (uint16_t *)(bm_all + (size_t)nwarps * 32 * wpl);
-  uint32_t *bm = bm_all + (size_t)warp * 32 * wpl;
-  uint16_t *wpre = pre_all + (size_t)warp * 32 * wpl;
-
-  for (int i = tid; i < nwarps * 32 * wpl; i += blockDim.x) bm_all[i] = 0;
-
-  for (long long col = blockIdx.x; col < C; col += gridDim.x) {
-    __syncthreads();
-    {
-      const uint4 *src = (const uint4 *)(rank16 + (size_t)col * Gp);
-      uint4 *dst = (uint4 *)s_rank;
-      for (int i = tid; i < (int)(Gp / 8); i += blockDim.x) dst[i] = __ldg(src + i);
-    }
-    __syncthreads();
-    uint16_t *lcol = lists + (size_t)col * Lp;
-    for (int k = warp; k < S; k += nwarps) {
-      const int4 info = __ldg(set_info + k);  // {member offset, m | slow << 31, list offset, set id}
-      if (info.y < 0) continue;               // es_wks_generic_kernel does these
-      const int off = info.x, m = info.y;
-      uint16_t *out = lcol + info.z;
-      if (m <= 32) order_one_set<1>(s_rank, bm, wpre, lane, wpl, set_idx, off, m, out);
-      else if (m <= 64) order_one_set<2>(s_rank, bm, wpre, lane, wpl, set_idx, off, m, out);
-      else if (m <= 128) order_one_set<4>(s_rank, bm, wpre, lane, wpl, set_idx, off, m, out);
-      else if (m <= 256) order_one_set<8>(s_rank, bm, wpre, lane, wpl, set_idx, off, m, out);
-      else order_one_set<16>(s_rank, bm, wpre, lane, wpl, set_idx, off, m, out);
-    }
-  }
-}
-
-// ---- phase B: running sum over the ordered hits ------------------------------
-// Persistent CTA per column, a warp per set.  Shared memory: the column's
-// rank-ordered hit weights (fp64).  Lane l takes hits [l*NB, l*NB + NB) (one
-// vector load of its uint16 ranks): local sums, one warp scan, then the running
-// maxima / minima.
-template <int NB>
-__device__ __forceinline__ void load_ranks(const uint16_t *__restrict__ p, uint32_t (&rr)[NB]) {
-  if constexpr (NB == 1) {
-    rr[0] = *p;
-  } else if constexpr (NB == 2) {
-    const uint32_t v = *(const uint32_t *)p;
-    rr[0] = v & 0xffffu; rr[1] = v >> 16;
-  } else if constexpr (NB == 4) {
-    const uint2 v = *(const uint2 *)p;
-    rr[0] = v.x & 0xffffu; rr[1] = v.x >> 16; rr[2] = v.y & 0xffffu; rr[3] = v.y >> 16;
-  } else {
-#pragma unroll
-    for (int q = 0; q < NB / 8; q++) {
-      const uint4 v = *(const uint4 *)(p + 8 * q);
-      rr[8 * q + 0] = v.x & 0xffffu; rr[8 * q + 1] = v.x >> 16;
-      rr[8 * q + 2] = v.y & 0xffffu; rr[8 * q + 3] = v.y >> 16;
-      rr[8 * q + 4] = v.z & 0xffffu; rr[8 * q + 5] = v.z >> 16;
-      rr[8 * q + 6] = v.w & 0xffffu; rr[8 * q + 7] = v.w >> 16;
-    }
-  }
-}
-
-template <int NB>
-__device__ __forceinline__ double scan_one_set(const double *__restrict__ wsrc,
-                                               const uint16_t *__restrict__ list, int lane, int m,
-                                               int G) {
   const int k0 = lane * NB;
-  uint32_t rr[NB];
-  load_ranks<NB>(list + k0, rr);
   double wv[NB];
   double lsum = 0.0;
 #pragma unroll
   for (int t = 0; t < NB; t++) {
-    const double w = (k0 + t < m) ? wsrc[rr[t]] : 0.0;
+    const uint32_t r0 = (NB > 1) ? ((v[t >> 1] >> (16 * (t & 1))) & 0xffffu) : v[0];
+    const double w = (k0 + t < m) ? wsrc[r0] : 0.0;
     wv[t] = w;
     lsum += w;
   }
@@ -224,64 +143,73 @@ __device__ __forceinline__ double scan_one_set(const double *__restrict__ wsrc,
     if (lane >= d) incw += t;
   }
   const double W = __shfl_sync(0xffffffffu, incw, 31);
-  double cum = incw - lsum;  // exclusive prefix of the lane (exact: incw = prefix + lsum)
+  double cum = __shfl_up_sync(0xffffffffu, incw, 1);
+  if (lane == 0) cum = 0.0;
   const double invW = 1.0 / W, invGm = 1.0 / (double)(G - m);
   double mx = -INFINITY, mn = INFINITY;
 #pragma unroll
   for (int t = 0; t < NB; t++) {
     const int kk = k0 + t;
     if (kk < m) {
+      const int r0 = (int)((NB > 1) ? ((v[t >> 1] >> (16 * (t & 1))) & 0xffffu) : v[0]);
       cum += wv[t];
-      const double ps = cum * invW - (double)((int)rr[t] - kk) * invGm;  // r - k with r = rr+1, k = kk+1
+      // d_miss = (r - k) / (G - m) with r = r0 + 1, k = kk + 1 (R/flexgsea.R:825-826)
+      const double ps = cum * invW - (double)(r0 - kk) * invGm;
       const double ng = ps - wv[t] * invW;
-      mx = fmax(mx, ps);
-      mn = fmin(mn, ng);
+      mx = (ps > mx) ? ps : mx;
+      mn = (ng < mn) ? ng : mn;
     }
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
-    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    const double a = __shfl_xor_sync(0xffffffffu, mx, o), b = __shfl_xor_sync(0xffffffffu, mn, o);
+    mx = (a > mx) ? a : mx;
+    mn = (b < mn) ? b : mn;
   }
   double es = (mx > -mn) ? mx : mn;                      // strict, :833
   if (W == 0.0 || m == G || m == 0) es = nan("");        // 0/0 in the reference
   return es;
 }
 
-constexpr int ES_SCAN_THREADS = 640;  // 20 warps: up to 102 registers each, no spills
+constexpr int ES_THREADS = 768;  // 24 warps, <= 85 registers each
 template <bool W_SMEM>
-__global__ void __launch_bounds__(ES_SCAN_THREADS, 1)
-es_scan_kernel(const double *__restrict__ sabs, int G, long long C,
-               const int4 *__restrict__ set_info, int S, const uint16_t *__restrict__ lists,
-               long long Lp, double *__restrict__ es_out) {
+__global__ void __launch_bounds__(ES_THREADS, 1)
+es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sabs, int G,
+              long long C, const int4 *__restrict__ set_info, const int *__restrict__ set_idx, int S,
+              double *__restrict__ es_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const size_t Gp = pitch_of(G);
-  double *s_abs = (double *)smem;
+  uint16_t *s_rank = (uint16_t *)smem;
+  double *s_abs = (double *)(smem + Gp * 2);
 
   for (long long col = blockIdx.x; col < C; col += gridDim.x) {
     __syncthreads();
-    if (W_SMEM) {
-      const double2 *ws = (const double2 *)(sabs + (size_t)col * Gp);
-      double2 *wd = (double2 *)s_abs;
-      for (int i = tid; i < (int)(Gp / 2); i += blockDim.x) wd[i] = __ldg(ws + i);
+    {  // stage the column: 16-byte vector copies (rows are 16-byte aligned)
+      const uint4 *src = (const uint4 *)(rank16 + (size_t)col * Gp);
+      uint4 *dst = (uint4 *)s_rank;
+      for (int i = tid; i < (int)(Gp / 8); i += blockDim.x) dst[i] = __ldg(src + i);
+      if (W_SMEM) {
+        const double2 *ws = (const double2 *)(sabs + (size_t)col * Gp);
+        double2 *wd = (double2 *)s_abs;
+        for (int i = tid; i < (int)(Gp / 2); i += blockDim.x) wd[i] = __ldg(ws + i);
+      }
     }
     __syncthreads();
     const double *wsrc = W_SMEM ? s_abs : sabs + (size_t)col * Gp;
-    const uint16_t *lcol = lists + (size_t)col * Lp;
     double *es_col = es_out + (size_t)col * S;
-
+    // sets in descending size, round-robin over warps: similar work per warp and
+    // coherent size classes
     for (int k = warp; k < S; k += nwarps) {
-      const int4 info = __ldg(set_info + k);
-      if (info.y < 0) continue;
-      const int m = info.y;
-      const uint16_t *list = lcol + info.z;
+      const int4 info = __ldg(set_info + k);  // {member offset, m | slow << 31, -, set id}
+      if (info.y < 0) continue;               // es_wks_generic_kernel does these
+      const int off = info.x, m = info.y;
       double es;
-      if (m <= 32) es = scan_one_set<1>(wsrc, list, lane, m, G);
-      else if (m <= 64) es = scan_one_set<2>(wsrc, list, lane, m, G);
-      else if (m <= 128) es = scan_one_set<4>(wsrc, list, lane, m, G);
-      else if (m <= 256) es = scan_one_set<8>(wsrc, list, lane, m, G);
-      else es = scan_one_set<16>(wsrc, list, lane, m, G);
+      if (m <= 32) es = wks_one_set<1, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, lane);
+      else if (m <= 64) es = wks_one_set<2, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, lane);
+      else if (m <= 128) es = wks_one_set<4, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, lane);
+      else if (m <= 256) es = wks_one_set<8, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, lane);
+      else es = wks_one_set<16, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, lane);
       if (lane == 0) es_col[info.w] = es;
     }
   }
@@ -388,41 +316,24 @@ int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, in
   if (c->opt_force_generic)
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
   const size_t Gp = pitch_of(G);
-  // words per lane: 4 * odd, so the lanes' uint4 loads of their own range are conflict free
-  int wpl = (int)((G + 1023) / 1024);
-  wpl = (wpl + 3) & ~3;
-  if (((wpl >> 2) & 1) == 0) wpl += 4;
-  const size_t per_warp = (size_t)32 * wpl * 6;  // bitmap (4 B/word) + per-word prefix (2 B/word)
   const size_t budget = (size_t)c->smem_optin;
-  if (Gp * 2 + per_warp > budget)  // not even one warp fits: the order-free kernel does everything
+  if (Gp * 2 > budget)  // the rank array does not fit on chip: the order-free kernel does everything
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
   int grid = c->num_sms;
   if (grid > C) grid = (int)C;
-  {  // phase A
-    int nwarps = (int)((budget - Gp * 2) / per_warp);
-    if (nwarps > 32) nwarps = 32;
-    const size_t smem = Gp * 2 + (size_t)nwarps * per_warp;
-    FGS_TRY(c->es_lists.ensure((size_t)c->list_pitch * C + 1024));  // + slack: vector loads past the last list
-    FGS_CUDA(cudaFuncSetAttribute(es_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    es_order_kernel<<<grid, nwarps * 32, smem, c->stream>>>(d_rank16, G, C, c->set_info.p, c->set_idx.p,
-                                                            c->S, wpl, c->es_lists.p, c->list_pitch);
-    c->launches++;
-    FGS_CUDA(cudaGetLastError());
+  const bool w_smem = Gp * 10 <= budget;  // rank (2 B) + weight (8 B) per gene on chip
+  const size_t smem = w_smem ? Gp * 10 : Gp * 2;
+  if (w_smem) {
+    auto k = es_wks_kernel<true>;
+    FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx.p, c->S, d_es);
+  } else {
+    auto k = es_wks_kernel<false>;
+    FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx.p, c->S, d_es);
   }
-  {  // phase B
-    const bool w_smem = Gp * 8 <= budget;
-    const size_t smem = w_smem ? Gp * 8 : 0;
-    if (w_smem) {
-      auto k = es_scan_kernel<true>;
-      FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<grid, ES_SCAN_THREADS, smem, c->stream>>>(d_sabs, G, C, c->set_info.p, c->S, c->es_lists.p, c->list_pitch, d_es);
-    } else {
-      es_scan_kernel<false><<<grid * 2, ES_SCAN_THREADS, 0, c->stream>>>(d_sabs, G, C, c->set_info.p, c->S,
-                                                              c->es_lists.p, c->list_pitch, d_es);
-    }
-    c->launches++;
-    FGS_CUDA(cudaGetLastError());
-  }
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
   if (c->n_slow > 0)
     FGS_TRY(launch_es_wks_generic(c, d_rank16, d_sabs, G, C, c->slow_ids.p, c->n_slow, d_es));
   return FGS_OK;
