@@ -286,6 +286,7 @@ int fgs_set_option(fgs_ctx *c, const char *name, long long value) {
   if (!c || !name) return FGS_ERR_ARG;
   if (!strcmp(name, "perm_block")) c->opt_perm_block = (int)value;
   else if (!strcmp(name, "force_generic_es")) c->opt_force_generic = (int)value;
+  else if (!strcmp(name, "force_sort64")) c->opt_sort64 = (int)value;
   else { set_error("unknown option '%s'", name); return FGS_ERR_ARG; }
   return FGS_OK;
 }

@@ -66,6 +66,7 @@ struct fgs_ctx {
   // options
   int opt_perm_block = 0;      // 0 = auto
   int opt_force_generic = 0;
+  int opt_sort64 = 0;          // force the 64-bit global-memory sort (tests)
   int opt_score_ppt = 0;
 
   // expression matrix x [n x G] (gene's samples contiguous)

@@ -206,6 +206,29 @@ def test_rank_ties_and_user_scores(ctx, oracle):
         ctx.es_from_scores(nat.ES_WEIGHTED_KS, bad)
 
 
+def test_sort_paths_agree(ctx, oracle):
+    """the on-chip 32-bit-key sort (+ low-half fix-up, + 64-bit redo of columns
+    with long runs) and the 64-bit global sort give R's ranks on adversarial
+    inputs: values that share their top 32 key bits, exact duplicates, zeros."""
+    rng = np.random.default_rng(12)
+    G = 3000
+    cols = [1.0 + rng.permutation(G) * 2.0 ** -44,                    # one giant run, all distinct
+            np.repeat(rng.normal(size=G // 4), 4)[:G],                # exact ties in groups of 4
+            np.where(rng.random(G) < 0.5, 0.0, -0.0),                 # +-0 only
+            rng.normal(size=G),
+            np.concatenate([rng.normal(size=G - 40), 2.5 + np.arange(40) * 2.0 ** -50])]  # run of 40 < 48
+    sc = np.stack(cols, axis=1)[:, None, :]                           # [G, 1, 5]
+    off, idx = synth.gene_sets_csr(G, 8, (10, 40), "uniform", seed=3)
+    ctx.set_gene_sets(off, idx)
+    want = _ranks(oracle, sc[:, 0, :])
+    for force64 in (0, 1):
+        ctx.set_option("force_sort64", force64)
+        ctx.es_from_scores(nat.ES_WEIGHTED_KS, sc)
+        _, rk = ctx.debug_last(5, G=G)
+        assert np.array_equal(rk, want), force64
+    ctx.set_option("force_sort64", 0)
+
+
 # --------------------------------------- a8: observed extras + the goldens
 def test_weighted_ks_golden_on_device(ctx, oracle):
     """tests/testthat/test_weighted_ks.R through the device path."""
