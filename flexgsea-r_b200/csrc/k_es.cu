@@ -44,8 +44,21 @@ __device__ __forceinline__ double warp_sum(double v) {
 // (VIMNMX.U16x2 compares both at once).  Blocked layout: element e = lane * NB +
 // slot, so after the sort lane l holds the hits with ordinals [l*NB, l*NB + NB)
 // -- exactly the distribution the running-sum scan wants.  Pads are 0xFFFF.
-__device__ __forceinline__ uint32_t minmax2(uint32_t a, uint32_t b, bool take_min) {
-  return take_min ? __vminu2(a, b) : __vmaxu2(a, b);
+//
+// The network is the direction-free form of bitonic sort: level k first
+// compares e with its mirror e ^ (k - 1), then e with e ^ j for j = k/4 .. 1,
+// and EVERY comparator sends the minimum to the lower index.  So all in-lane
+// comparators have a compile-time direction (one VIMNMX each), and only the
+// cross-lane ones depend on the lane's side of the exchange (VIMNMX + 2 LOP3).
+__device__ __forceinline__ uint32_t swap_halves(uint32_t v) { return __byte_perm(v, v, 0x1032); }
+// cross-lane comparator: `hi_mask` is 0 on the lane that keeps the minimum and
+// ~0 on the lane that keeps the maximum; max = min ^ a ^ o, so
+// result = min ^ ((a ^ o) & hi_mask): one VIMNMX + two LOP3, no predicates
+__device__ __forceinline__ uint32_t minmax2_side(uint32_t a, uint32_t o, uint32_t hi_mask) {
+  return hi_mask ? __vmaxu2(a, o) : __vminu2(a, o);
+}
+__device__ __forceinline__ uint32_t minmax1_side(uint32_t a, uint32_t o, uint32_t hi_mask) {
+  return hi_mask ? max(a, o) : min(a, o);
 }
 
 template <int NB>
@@ -53,47 +66,64 @@ __device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[(NB + 1) / 2], 
   constexpr int N = 32 * NB;
   if constexpr (NB == 1) {
 #pragma unroll
-    for (int k = 2; k <= N; k <<= 1)
+    for (int k = 2; k <= N; k <<= 1) {
+      v[0] = minmax1_side(v[0], __shfl_xor_sync(0xffffffffu, v[0], k - 1), 0u - ((lane / (k >> 1)) & 1u));
 #pragma unroll
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        const uint32_t o = __shfl_xor_sync(0xffffffffu, v[0], j);
-        const bool asc = (lane & k) == 0, lower = (lane & j) == 0;
-        v[0] = (asc == lower) ? min(v[0], o) : max(v[0], o);
-      }
+      for (int j = k >> 2; j > 0; j >>= 1)
+        v[0] = minmax1_side(v[0], __shfl_xor_sync(0xffffffffu, v[0], j), 0u - ((lane / j) & 1u));
+    }
   } else {
     constexpr int NR = NB / 2;
 #pragma unroll
     for (int k = 2; k <= N; k <<= 1) {
+      // mirror stage: e <-> e ^ (k - 1)
+      if (k == 2) {
 #pragma unroll
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        if (j >= NB) {  // partner in lane ^ (j / NB), same slot
-          const int lj = j / NB;
-          const bool asc = (lane & (k / NB)) == 0, lower = (lane & lj) == 0;
-          const bool take_min = asc == lower;
+        for (int q = 0; q < NR; q++) {
+          const uint32_t t = swap_halves(v[q]);
+          v[q] = __byte_perm(__vminu2(v[q], t), __vmaxu2(v[q], t), 0x5410);
+        }
+      } else if (k <= NB) {  // slot ^ (k - 1): register q ^ (k/2 - 1), halves swapped
 #pragma unroll
-          for (int q = 0; q < NR; q++) {
-            const uint32_t o = __shfl_xor_sync(0xffffffffu, v[q], lj);
-            v[q] = minmax2(v[q], o, take_min);
+        for (int q = 0; q < NR; q++) {
+          const int qb = q ^ ((k >> 1) - 1);
+          if (qb > q) {
+            const uint32_t a = v[q], t = swap_halves(v[qb]);
+            v[q] = __vminu2(a, t);
+            v[qb] = swap_halves(__vmaxu2(a, t));
           }
+        }
+      } else {  // lane ^ (k / NB - 1), slots reversed: register NR-1-q, halves swapped
+        const uint32_t hi_mask = 0u - ((lane / ((k / NB) >> 1)) & 1u);
+        uint32_t o[NR];
+#pragma unroll
+        for (int q = 0; q < NR; q++)
+          o[q] = swap_halves(__shfl_xor_sync(0xffffffffu, v[NR - 1 - q], (k / NB) - 1));
+#pragma unroll
+        for (int q = 0; q < NR; q++) v[q] = minmax2_side(v[q], o[q], hi_mask);
+      }
+#pragma unroll
+      for (int j = k >> 2; j > 0; j >>= 1) {
+        if (j >= NB) {  // partner lane ^ (j / NB), same slot
+          const uint32_t hi_mask = 0u - ((lane / (j / NB)) & 1u);
+#pragma unroll
+          for (int q = 0; q < NR; q++)
+            v[q] = minmax2_side(v[q], __shfl_xor_sync(0xffffffffu, v[q], j / NB), hi_mask);
         } else if (j >= 2) {  // partner register q ^ (j / 2), same half
 #pragma unroll
           for (int q = 0; q < NR; q++) {
             const int qb = q ^ (j >> 1);
             if (qb > q) {
-              // direction of element lane * NB + 2q: bit k of it
-              const bool asc = (k >= NB) ? ((lane & (k / NB)) == 0) : (((2 * q) & k) == 0);
-              const uint32_t a = v[q], b = v[qb];
-              v[q] = minmax2(a, b, asc);
-              v[qb] = minmax2(a, b, !asc);
+              const uint32_t a = v[q], b2 = v[qb];
+              v[q] = __vminu2(a, b2);
+              v[qb] = __vmaxu2(a, b2);
             }
           }
         } else {  // j == 1: the two halves of one register
 #pragma unroll
           for (int q = 0; q < NR; q++) {
-            const bool asc = (k >= NB) ? ((lane & (k / NB)) == 0) : (((2 * q) & k) == 0);
-            const uint32_t t = __byte_perm(v[q], v[q], 0x1032);
-            const uint32_t lo = minmax2(v[q], t, asc), hi = minmax2(v[q], t, !asc);
-            v[q] = __byte_perm(lo, hi, 0x5410);
+            const uint32_t t = swap_halves(v[q]);
+            v[q] = __byte_perm(__vminu2(v[q], t), __vmaxu2(v[q], t), 0x5410);
           }
         }
       }
