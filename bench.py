@@ -128,7 +128,7 @@ def run_reference(args):
     orc.build()
     c, x, y, off, idx = workload(args.config)
     es_kind = orc.ES_MAXMEAN if args.config == "C4" else orc.ES_WKS
-    cores = orc.num_threads()
+    cores = orc.use_all_cores()
     P_s = args.ref_perms if args.ref_perms else max(cores * 8, 64)
     perm = synth.perm_matrix(c["n"], P_s, seed=4)
     times = []
@@ -224,7 +224,7 @@ def run_gpu(args):
     def e2e_step():
         ctx.set_x(xp); ctx.set_gene_sets(offp, idxp); ctx.set_response_s2n(yp)
         sc = ctx.score_observed(nat.SCORE_S2N)
-        obs = ctx.observed_es(es_kind, sc)
+        obs = ctx.observed_es(es_kind, sc, ragged=False)  # default flexgsea(): return_values = character()
         ctx.perm_null(nat.SCORE_S2N, es_kind, P, perm=pp, want_host=False)
         sig = ctx.calc_sig(obs["es"][:, 0], 0, True, True, False)
         return sig
@@ -242,12 +242,12 @@ def run_gpu(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te[0])
     h2d = x.nbytes + 4 * n + perm_h.nbytes + 4 * (S + 1 + nnz) + 8 * G * R + 8 * S
-    d2h = 8 * G * R + S * R * (8 * 3 + 4 * 2) + (nnz * R * 20 if es_kind == nat.ES_WEIGHTED_KS else 0) + S * (6 * 8 + 4 * 8) + 32
+    d2h = 8 * G * R + S * R * (8 * 3 + 4 * 2) + S * (6 * 8 + 4 * 8) + 32
 
     # ---- multi-GPU: the significance exchange (all-gather sums, all-reduce counts)
     if dist is not None:
         sc = ctx.score_observed(nat.SCORE_S2N)
-        es_obs = ctx.observed_es(es_kind, sc)["es"][:, 0]
+        es_obs = ctx.observed_es(es_kind, sc, ragged=False)["es"][:, 0]
         shard = api._Shard(None)
         r = api.sharded_sig(ctx, shard, fg.flexgsea_calc_sig, es_obs, 0, False, P * world)
         assert np.isfinite(r["fdr"]).all()
@@ -296,7 +296,7 @@ def run_gpu(args):
     if world == 1 and not args.no_cpu:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import pyoracle as orc
-        cores = orc.num_threads()
+        cores = orc.use_all_cores()
         P_s = max(cores * 8, 64)
         ps = synth.perm_matrix(n, P_s, seed=4)
         ok = orc.ES_MAXMEAN if args.config == "C4" else orc.ES_WKS

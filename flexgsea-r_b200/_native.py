@@ -148,7 +148,9 @@ class Context:
         self._check(self._lib.fgs_score_observed(self._h, score_kind, int(abs_flag), _p(out, _dp)))
         return out
 
-    def observed_es(self, es_kind, scores, p=1.0):
+    def observed_es(self, es_kind, scores, p=1.0, ragged=True):
+        """ragged=False skips the per-member arrays (running_es_*), which are
+        only needed when the caller asked for them in return_values."""
         sc = _f(scores)
         G, R = sc.shape
         S, nnz = self.S, self.nnz
@@ -156,8 +158,10 @@ class Context:
         res = {"es": es}
         if es_kind == ES_WEIGHTED_KS:
             mea = np.zeros((S, R), order="F"); lep = np.zeros((S, R), order="F")
-            at = np.zeros((max(nnz, 1), R), dtype=np.int32, order="F")
-            rp = np.zeros((max(nnz, 1), R), order="F"); rn = np.zeros((max(nnz, 1), R), order="F")
+            at = rp = rn = None
+            if ragged:
+                at = np.zeros((max(nnz, 1), R), dtype=np.int32, order="F")
+                rp = np.zeros((max(nnz, 1), R), order="F"); rn = np.zeros((max(nnz, 1), R), order="F")
             lf = np.zeros((S, R), dtype=np.int32, order="F"); lc = np.zeros((S, R), dtype=np.int32, order="F")
             self._check(self._lib.fgs_observed_es(self._h, es_kind, C.c_double(p), _p(sc, _dp), G, R,
                                                   _p(es, _dp), _p(mea, _dp), _p(lep, _dp), _p(at, _ip),

@@ -303,12 +303,15 @@ def _x_values(x):
     return np.asfortranarray(a, dtype=np.float64), None
 
 
-def _observed(ctx, es_fn, scores, p=1.0):
+def _observed(ctx, es_fn, scores, p=1.0, ragged=True):
     """observed ES + extras for scores [G x R] -> dict of [S x R] arrays and
     ragged lists indexed [response][set]."""
-    o = ctx.observed_es(es_fn.kind, scores, p)
+    o = ctx.observed_es(es_fn.kind, scores, p, ragged=ragged)
     res = {"es": o["es"]}
-    if es_fn.kind == nat.ES_WEIGHTED_KS:
+    if es_fn.kind == nat.ES_WEIGHTED_KS and not ragged:
+        res["max_es_at"] = o["max_es_at"]
+        res["le_prop"] = o["le_prop"]
+    elif es_fn.kind == nat.ES_WEIGHTED_KS:
         S, R = o["es"].shape
         off = ctx.offsets
         res["max_es_at"] = o["max_es_at"]
@@ -463,7 +466,7 @@ def flexgsea(x, y, gene_sets, gene_score_fn=flexgsea_s2n, es_fn=flexgsea_weighte
     if verbose:
         print("Calculating ES (Observed)")
     if builtin_es:
-        obs = _observed(ctx, es_fn, scores)
+        obs = _observed(ctx, es_fn, scores, ragged=bool(set(es_fn.extra) & set(return_values)))
         es = obs["es"]
         extra_stats = {k: obs[k] for k in es_fn.extra_stats}
         extra = {k: obs[k] for k in es_fn.extra if k in return_values}

@@ -117,6 +117,7 @@ static int check_problem(fgs_ctx *c, bool need_sets) {
   return FGS_OK;
 }
 
+static constexpr int CERT_OVERFLOW = 1000;  // internal
 // flags buffer: [0, P) per-permutation bits, [n-1] global bits
 static int flags_reset(fgs_ctx *c, long long P) {
   FGS_TRY(c->flags.ensure((size_t)P + 1));
@@ -128,6 +129,7 @@ static int flags_check(fgs_ctx *c, long long P) {
   FGS_CUDA(cudaMemcpyAsync(h.data(), c->flags.p, c->flags.n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   FGS_TRY(sync(c));
   if (h[c->flags.n - 1] & 8) { set_error("permutation matrix holds an index outside [1, n_sample]"); return FGS_ERR_ARG; }
+  if (h[c->flags.n - 1] & 16) return CERT_OVERFLOW;  // certification lists full: caller reruns bit-faithfully
   for (long long p = 0; p < P; p++)
     if (h[p]) {
       set_error("Gene scoring function returned NA or Inf.");  // R/flexgsea.R:400-402
@@ -182,7 +184,23 @@ static int rank_and_es(fgs_ctx *c, int es_kind, double p_exp, int abs_flag, long
     FGS_TRY(c->rank16.ensure(Gp * Cb));
     FGS_TRY(c->sabs.ensure(Gp * Cb));
     long long l0 = c->launches;
-    FGS_TRY(launch_sort(c, c->scores.p, G, Cb, abs_flag, p_exp, c->rank16.p, c->sabs.p));
+    if (c->cur_cert) {
+      // ranks from tensor-core scores: adjacent sorted scores closer than the
+      // contraction's error bound are recomputed exactly and their columns ranked again
+      TieCert tc;
+      tc.list = c->cert_list.p + c->opt_cert_cap; tc.count = c->cert_ctr.p + 1; tc.cap = c->opt_cert_cap;
+      FGS_TRY(c->cert_redo.ensure((size_t)Cb + 8));
+      FGS_CUDA(cudaMemsetAsync(c->cert_redo.p, 0, (size_t)Cb * sizeof(int), c->stream));
+      tc.redo = c->cert_redo.p; tc.overflow = c->flags.p + (c->flags.n - 1);
+      tc.rel_tol = 1e-9; tc.abs_tol = 1e-11;
+      FGS_TRY(launch_sort(c, c->scores.p, G, Cb, abs_flag, p_exp, c->rank16.p, c->sabs.p, nullptr, &tc));
+      FGS_TRY(launch_s2n_exact_entries(c, c->x.p, c->n, G, c->cur_labels, c->n1n2.p, c->s2n_R, tc.list,
+                                       tc.count, c->opt_cert_cap, c->scores.p, c->flags.p + c->cur_flag0));
+      FGS_TRY(launch_sort(c, c->scores.p, G, Cb, abs_flag, p_exp, c->rank16.p, c->sabs.p, c->cert_redo.p,
+                          nullptr));
+    } else {
+      FGS_TRY(launch_sort(c, c->scores.p, G, Cb, abs_flag, p_exp, c->rank16.p, c->sabs.p));
+    }
     c->last_launches[2] += c->launches - l0;
     tm.mark();
     l0 = c->launches;
@@ -254,7 +272,8 @@ int fgs_destroy(fgs_ctx *c) {
   if (!c) return FGS_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->x.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release();
+  c->x.release(); c->xc.release(); c->xtot.release(); c->cert_list.release(); c->cert_ctr.release();
+  c->cert_redo.release(); c->sort_redo.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release();
   c->set_info.release(); c->es_lists.release(); c->slow_ids.release(); c->ybin.release();
   c->n1n2.release(); c->lm_H.release(); c->perm.release(); c->labels.release(); c->lm_B.release();
   c->scores.release(); c->rank16.release(); c->sabs.release(); c->sort_keys.release();
@@ -287,6 +306,8 @@ int fgs_set_option(fgs_ctx *c, const char *name, long long value) {
   if (!strcmp(name, "perm_block")) c->opt_perm_block = (int)value;
   else if (!strcmp(name, "force_generic_es")) c->opt_force_generic = (int)value;
   else if (!strcmp(name, "force_sort64")) c->opt_sort64 = (int)value;
+  else if (!strcmp(name, "s2n_mode")) c->opt_s2n_mode = (int)value;
+  else if (!strcmp(name, "cert_cap")) c->opt_cert_cap = value > 2 ? (int)value : 2;
   else { set_error("unknown option '%s'", name); return FGS_ERR_ARG; }
   return FGS_OK;
 }
@@ -299,6 +320,7 @@ int fgs_set_x(fgs_ctx *c, const double *x, int n_sample, int n_gene) {
   FGS_TRY(h2d(c, c->x.p, x, (size_t)n_sample * n_gene));
   c->n = n_sample; c->G = n_gene;
   c->gene_sd_valid = false;
+  c->xc_valid = false;
   FGS_TRY(sync(c));
   return FGS_OK;
 }
@@ -362,10 +384,11 @@ int fgs_set_response_s2n(fgs_ctx *c, const int *y_bin, int n_sample, int n_respo
   if (!c || !y_bin || n_sample <= 0 || n_response <= 0) { set_error("fgs_set_response_s2n: bad argument"); return FGS_ERR_ARG; }
   FGS_TRY(use_device(c));
   std::vector<int> nn(2 * (size_t)n_response, 0);
+  c->s2n_has_na_pending = false;
   for (int r = 0; r < n_response; r++)
     for (int i = 0; i < n_sample; i++) {
       int v = y_bin[(size_t)r * n_sample + i];
-      if (v == INT_MIN) continue;
+      if (v == INT_MIN) { c->s2n_has_na_pending = true; continue; }
       nn[2 * r + (v ? 0 : 1)]++;
     }
   FGS_TRY(c->ybin.ensure((size_t)n_sample * n_response));
@@ -374,6 +397,7 @@ int fgs_set_response_s2n(fgs_ctx *c, const int *y_bin, int n_sample, int n_respo
   FGS_TRY(h2d(c, c->n1n2.p, nn.data(), nn.size()));
   FGS_TRY(sync(c));
   c->s2n_R = n_response;
+  c->s2n_has_na = c->s2n_has_na_pending;
   if (c->n && c->n != n_sample) { /* checked again at run time */ }
   return FGS_OK;
 }
@@ -406,13 +430,36 @@ int fgs_n_response(fgs_ctx *c, int score_kind, int *n_response) {
 // gene scores of `P` permutations starting at device perm column p0 (d_perm may
 // be NULL = identity) into c->scores [P*R][G]; flags at c->flags + flag0
 static int score_block(fgs_ctx *c, int score_kind, const int *d_perm, const uint32_t *d_labels,
-                       int P, long long flag0) {
+                       int P, long long flag0, bool force_exact = false) {
   const int n = c->n, G = c->G;
   const int R = n_response_of(c, score_kind);
   const long long Cb = (long long)P * R;
   FGS_TRY(c->scores.ensure((size_t)G * Cb));
+  c->cur_cert = false;
   if (score_kind == FGS_SCORE_S2N) {
-    FGS_TRY(launch_s2n(c, c->x.p, n, G, d_labels, c->n1n2.p, R, Cb, c->scores.p, c->flags.p + flag0));
+    const bool tensor = c->opt_s2n_mode == 1 && !c->s2n_has_na && !force_exact;
+    if (tensor) {
+      // K2: FP64 tensor-core contraction; entries whose variance cancelled (or are
+      // not finite) are recomputed with the bit-faithful arithmetic right away
+      if (!c->xc_valid) {
+        FGS_TRY(c->xc.ensure((size_t)n * G));
+        FGS_TRY(c->xtot.ensure((size_t)2 * G));
+        FGS_TRY(launch_center(c, c->x.p, n, G, c->xc.p, c->xtot.p));
+        c->xc_valid = true;
+      }
+      FGS_TRY(c->cert_list.ensure((size_t)2 * c->opt_cert_cap));
+      FGS_TRY(c->cert_ctr.ensure(4));
+      FGS_CUDA(cudaMemsetAsync(c->cert_ctr.p, 0, 4 * sizeof(int), c->stream));
+      FGS_TRY(launch_s2n_mma(c, c->xc.p, c->xtot.p, n, G, d_labels, c->n1n2.p, R, Cb, c->scores.p,
+                             c->cert_list.p, c->cert_ctr.p, c->opt_cert_cap));
+      FGS_TRY(launch_s2n_exact_entries(c, c->x.p, n, G, d_labels, c->n1n2.p, R, c->cert_list.p,
+                                       c->cert_ctr.p, c->opt_cert_cap, c->scores.p, c->flags.p + flag0));
+      c->cur_cert = true;
+      c->cur_labels = d_labels;
+      c->cur_flag0 = flag0;
+    } else {
+      FGS_TRY(launch_s2n(c, c->x.p, n, G, d_labels, c->n1n2.p, R, Cb, c->scores.p, c->flags.p + flag0));
+    }
     FGS_TRY(launch_s2n_patch(c, c->scores.p, G, R, P, c->flags.p + flag0));
   } else {
     if (!c->gene_sd_valid) {
@@ -483,7 +530,7 @@ int fgs_score_observed(fgs_ctx *c, int score_kind, int abs_flag, double *scores)
     FGS_TRY(c->labels.ensure((size_t)R * 2 * W));
     FGS_TRY(launch_labels(c, nullptr, c->ybin.p, n, R, 1, c->labels.p));
   }
-  FGS_TRY(score_block(c, score_kind, nullptr, c->labels.p, 1, 0));
+  FGS_TRY(score_block(c, score_kind, nullptr, c->labels.p, 1, 0, /*force_exact=*/true));
   if (abs_flag) FGS_TRY(launch_abs_inplace(c, c->scores.p, (long long)G * R));
   FGS_TRY(d2h(c, scores, c->scores.p, (size_t)G * R));
   FGS_TRY(flags_check(c, 1));
@@ -544,6 +591,15 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
   tm.finish(pro_ms);
   if (cudaEventSynchronize(c->ev[1]) == cudaSuccess) cudaEventElapsedTime(&c->last_ms[4], c->ev[0], c->ev[1]);
   c->last_launches[4] = c->last_launches[0] + c->last_launches[1] + c->last_launches[2] + c->last_launches[3];
+  if (rc == CERT_OVERFLOW) {
+    // more near-tied scores than the certification lists hold (e.g. thousands of
+    // duplicated genes): run this call with the bit-faithful score kernel instead
+    const int saved = c->opt_s2n_mode;
+    c->opt_s2n_mode = 0;
+    rc = fgs_perm_null(c, score_kind, es_kind, p_exp, abs_flag, perm, seed, perm_id0, n_perm, es_null_out);
+    c->opt_s2n_mode = saved;
+    return rc;
+  }
   if (rc != FGS_OK) return rc;
   if (es_null_out) {
     FGS_TRY(d2h(c, es_null_out, c->es_null.p, (size_t)S * R * P));
@@ -561,6 +617,7 @@ int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scor
   if (c->max_set > n_gene) { set_error("gene set index %d exceeds %d genes", c->max_set, n_gene); return FGS_ERR_ARG; }
   const int saveG = c->G;
   c->G = n_gene;
+  c->cur_cert = false;  // user scores: nothing to certify
   const int S = c->S, R = n_response, P = n_perm;
   const long long C = (long long)R * P;
   for (int i = 0; i < 5; i++) c->last_launches[i] = 0;

@@ -47,6 +47,16 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+// near-tie certification of the ranks derived from tensor-core scores
+struct TieCert {
+  int2 *list = nullptr;   // (column, gene) entries to recompute exactly
+  int *count = nullptr;   // device counter
+  int cap = 0;
+  int *redo = nullptr;    // [C] columns to rank again
+  int *overflow = nullptr;  // bit 16 raised when the list is full
+  double rel_tol = 0, abs_tol = 0;
+};
+
 // error bits accumulated on the device during a run
 enum : int { FLAG_POS_INF = 1, FLAG_NEG_INF = 2, FLAG_NAN = 4 };
 
@@ -67,11 +77,20 @@ struct fgs_ctx {
   int opt_perm_block = 0;      // 0 = auto
   int opt_force_generic = 0;
   int opt_sort64 = 0;          // force the 64-bit global-memory sort (tests)
+  int opt_s2n_mode = 1;        // 1 = tensor-core contraction + rank certification, 0 = bit-faithful kernel
+  int opt_cert_cap = 4 << 20;  // entries per certification list (epilogue list, tie list)
   int opt_score_ppt = 0;
 
   // expression matrix x [n x G] (gene's samples contiguous)
   int n = 0, G = 0;
   fgs::DevBuf<double> x;
+  fgs::DevBuf<double> xc;       // centred expression (tensor-core s2n), [G][n]
+  fgs::DevBuf<double> xtot;     // per gene {sum xc, sum xc^2}
+  bool xc_valid = false;
+  fgs::DevBuf<int2> cert_list;  // (column, gene) entries for exact recomputation
+  fgs::DevBuf<int> cert_ctr;    // [0] epilogue count, [1] tie count
+  fgs::DevBuf<int> cert_redo;   // [Cb]
+  fgs::DevBuf<int> sort_redo;   // [Cb] columns the 32-bit sort hands to the 64-bit sort
   fgs::DevBuf<double> gene_sd;  // sd(x[,g]) for lm
   bool gene_sd_valid = false;
 
@@ -92,6 +111,10 @@ struct fgs_ctx {
 
   // s2n response: y_bin [n x R]
   int s2n_R = 0;
+  bool s2n_has_na = false, s2n_has_na_pending = false;  // NA_LOGICAL present in y_bin
+  bool cur_cert = false;            // scores of the current block came from the tensor-core path
+  const uint32_t *cur_labels = nullptr;
+  long long cur_flag0 = 0;
   fgs::DevBuf<int> ybin;
   fgs::DevBuf<int> n1n2;  // [R][2]
   // lm response
@@ -148,7 +171,15 @@ int launch_check_finite(fgs_ctx *c, const double *d_v, long long len, long long 
 int launch_abs_inplace(fgs_ctx *c, double *d_v, long long len);
 // K3
 int launch_sort(fgs_ctx *c, const double *d_scores, int G, long long C, int abs_flag, double p_exp,
-                uint16_t *d_rank16, double *d_sabs);
+                uint16_t *d_rank16, double *d_sabs, const int *only_cols = nullptr,
+                const TieCert *cert = nullptr);
+int launch_center(fgs_ctx *c, const double *d_x, int n, int G, double *d_xc, double *d_tot);
+int launch_s2n_mma(fgs_ctx *c, const double *d_xc, const double *d_tot, int n, int G,
+                   const uint32_t *d_labels, const int *d_n1n2, int R, long long C, double *d_scores,
+                   int2 *d_list, int *d_count, int cap);
+int launch_s2n_exact_entries(fgs_ctx *c, const double *d_x, int n, int G, const uint32_t *d_labels,
+                             const int *d_n1n2, int R, const int2 *d_list, const int *d_count, int cap,
+                             double *d_scores, int *d_flags);
 // K4 / K5
 int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
                   double *d_es /* [C][S] */);

@@ -21,6 +21,23 @@
 
 namespace fgs {
 
+// adjacent scores of the sorted column closer than this are listed for an exact
+// recomputation (k_s2n_mma.cu); a column with such a pair is ranked again
+__device__ __forceinline__ void certify_pair(const TieCert &tc, long long col, double a, double b,
+                                             uint32_t ga, uint32_t gb) {
+  const double gap = fabs(a - b), scale = fmax(fabs(a), fabs(b));
+  if (gap <= tc.abs_tol || gap <= tc.rel_tol * scale) {
+    const int at = atomicAdd(tc.count, 2);
+    if (at + 1 < tc.cap) {
+      tc.list[at] = make_int2((int)col, (int)ga);
+      tc.list[at + 1] = make_int2((int)col, (int)gb);
+    } else {
+      atomicOr(tc.overflow, 16);
+    }
+    tc.redo[col] = 1;
+  }
+}
+
 constexpr int SORT_THREADS = 512;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 
@@ -40,7 +57,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
 sort_rank_kernel(const double *__restrict__ scores, int G, long long C, int abs_flag, double p_exp,
                  unsigned long long *__restrict__ key_scratch, uint32_t *__restrict__ idx_scratch,
                  uint16_t *__restrict__ rank16, double *__restrict__ sabs,
-                 const int *__restrict__ only_flagged) {
+                 const int *__restrict__ only_flagged, TieCert tc) {
   __shared__ uint32_t cnt[256 * SORT_WARPS];
   __shared__ uint32_t wsum[SORT_WARPS];
   __shared__ int s_skip;
@@ -132,10 +149,12 @@ sort_rank_kernel(const double *__restrict__ scores, int G, long long C, int abs_
     uint16_t *rk = rank16 + (size_t)col * Gp;
     double *sa = sabs + (size_t)col * Gp;
     for (int q = tid; q < G; q += SORT_THREADS) {
-      double w = fabs(key_desc_to_score(kin[q]));
+      const double sq = key_desc_to_score(kin[q]);
+      double w = fabs(sq);
       if (p_exp != 1.0) w = pow(w, p_exp);
       sa[q] = w;
       rk[iin[q]] = (uint16_t)(q + 1);
+      if (tc.list && q + 1 < G) certify_pair(tc, col, sq, key_desc_to_score(kin[q + 1]), iin[q], iin[q + 1]);
     }
     __syncthreads();
   }
@@ -159,7 +178,8 @@ constexpr int SORT_MAX_RUN = 48;
 template <int IPT>
 __global__ void __launch_bounds__(SORT32_THREADS, 1)
 sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int abs_flag, double p_exp,
-                   uint16_t *__restrict__ rank16, double *__restrict__ sabs, int *__restrict__ redo) {
+                   uint16_t *__restrict__ rank16, double *__restrict__ sabs, int *__restrict__ redo,
+                   const int *__restrict__ only_cols, TieCert tc) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int GS = SORT32_THREADS * IPT;  // padded capacity
   uint32_t *skey = (uint32_t *)smem;
@@ -173,6 +193,7 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
   const int wbase = warp * (32 * IPT);  // this warp's slice of the current order
 
   for (long long col = blockIdx.x; col < C; col += gridDim.x) {
+    if (only_cols && !only_cols[col]) continue;  // uniform per CTA
     const double *sc = scores + (size_t)col * G;
     if (tid == 0) s_redo = 0;
     // position q holds gene G-1-q (reverse order: the stable sort then breaks ties
@@ -293,10 +314,18 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
         const int q = tid + i * SORT32_THREADS;
         if (q < G) {
           const uint32_t g = sidx[q];
-          double w = fabs(__ldg(sc + g));
+          double sq = sc[g];
+          if (abs_flag) sq = fabs(sq);
+          double w = fabs(sq);
           if (p_exp != 1.0) w = pow(w, p_exp);
           sa[q] = w;
           rk[g] = (uint16_t)(q + 1);
+          if (tc.list && q + 1 < G) {
+            const uint32_t g2 = sidx[q + 1];
+            double s2 = sc[g2];
+            if (abs_flag) s2 = fabs(s2);
+            certify_pair(tc, col, sq, s2, g, g2);
+          }
         }
       }
     }
@@ -306,18 +335,22 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
 
 template <int IPT>
 static int launch_sort32_t(fgs_ctx *c, const double *d_scores, int G, long long C, int abs_flag,
-                           double p_exp, uint16_t *d_rank16, double *d_sabs, int *d_redo, int grid) {
+                           double p_exp, uint16_t *d_rank16, double *d_sabs, int *d_redo, int grid,
+                           const int *only_cols, const TieCert &tc) {
   const size_t smem = (size_t)SORT32_THREADS * IPT * 6 + (size_t)256 * SORT32_CSTRIDE * 4;
   auto k = sort_rank32_kernel<IPT>;
   FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<grid, SORT32_THREADS, smem, c->stream>>>(d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, d_redo);
+  k<<<grid, SORT32_THREADS, smem, c->stream>>>(d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, d_redo,
+                                               only_cols, tc);
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   return FGS_OK;
 }
 
 int launch_sort(fgs_ctx *c, const double *d_scores, int G, long long C, int abs_flag, double p_exp,
-                uint16_t *d_rank16, double *d_sabs) {
+                uint16_t *d_rank16, double *d_sabs, const int *only_cols, const TieCert *cert) {
+  TieCert tc{};
+  if (cert) tc = *cert;
   if (C <= 0 || G <= 0) return FGS_OK;
   if (G > 65535) {
     set_error("weighted KS ranking supports up to 65535 genes (got %d)", G);
@@ -327,19 +360,21 @@ int launch_sort(fgs_ctx *c, const double *d_scores, int G, long long C, int abs_
   if (G <= 32768 && !c->opt_sort64) {
     int grid = c->num_sms;
     if (grid > C) grid = (int)C;
-    FGS_TRY(c->counters.ensure((size_t)C + 8));
-    int *redo = c->counters.p;
+    FGS_TRY(c->sort_redo.ensure((size_t)C + 8));
+    int *redo = c->sort_redo.p;
     FGS_CUDA(cudaMemsetAsync(redo, 0, (size_t)C * sizeof(int), c->stream));
     const int ipt = (G + SORT32_THREADS - 1) / SORT32_THREADS;
-    if (ipt <= 4) FGS_TRY(launch_sort32_t<4>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid));
-    else if (ipt <= 8) FGS_TRY(launch_sort32_t<8>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid));
-    else if (ipt <= 12) FGS_TRY(launch_sort32_t<12>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid));
-    else if (ipt <= 16) FGS_TRY(launch_sort32_t<16>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid));
-    else if (ipt <= 20) FGS_TRY(launch_sort32_t<20>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid));
-    else if (ipt <= 24) FGS_TRY(launch_sort32_t<24>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid));
-    else if (ipt <= 28) FGS_TRY(launch_sort32_t<28>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid));
-    else FGS_TRY(launch_sort32_t<32>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid));
+    if (ipt <= 4) FGS_TRY(launch_sort32_t<4>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc));
+    else if (ipt <= 8) FGS_TRY(launch_sort32_t<8>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc));
+    else if (ipt <= 12) FGS_TRY(launch_sort32_t<12>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc));
+    else if (ipt <= 16) FGS_TRY(launch_sort32_t<16>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc));
+    else if (ipt <= 20) FGS_TRY(launch_sort32_t<20>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc));
+    else if (ipt <= 24) FGS_TRY(launch_sort32_t<24>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc));
+    else if (ipt <= 28) FGS_TRY(launch_sort32_t<28>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc));
+    else FGS_TRY(launch_sort32_t<32>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc));
     only = redo;  // the 64-bit kernel below only redoes flagged columns
+  } else {
+    only = only_cols;
   }
   int grid = c->num_sms * 3;
   if (grid > C) grid = (int)C;
@@ -347,7 +382,7 @@ int launch_sort(fgs_ctx *c, const double *d_scores, int G, long long C, int abs_
   FGS_TRY(c->sort_idx.ensure((size_t)grid * 2 * G));
   sort_rank_kernel<<<grid, SORT_THREADS, 0, c->stream>>>(d_scores, G, C, abs_flag, p_exp,
                                                          c->sort_keys.p, c->sort_idx.p, d_rank16,
-                                                         d_sabs, only);
+                                                         d_sabs, only, tc);
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   return FGS_OK;

@@ -169,7 +169,10 @@ int fgs_last_timings(fgs_ctx *ctx, float *ms, long long *launches);
 /* enable per-stage event timing (adds stream synchronisation points) */
 int fgs_set_profiling(fgs_ctx *ctx, int enabled);
 /* tuning / test hooks: "perm_block" (permutations per block), "force_generic_es"
- * (route every set through the duplicate-safe O(m^2) kernel) */
+ * (route every set through the duplicate-safe O(m^2) kernel), "force_sort64"
+ * (rank with the 64-bit global-memory sort), "s2n_mode" (1, default: s2n scores
+ * of the null loop by the FP64 tensor-core contraction with rank certification;
+ * 0: the bit-faithful three-pass kernel), "cert_cap" (certification list size) */
 int fgs_set_option(fgs_ctx *ctx, const char *name, long long value);
 
 #ifdef __cplusplus

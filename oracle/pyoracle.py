@@ -67,6 +67,17 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def use_all_cores():
+    """OpenMP threads = the cores this process may run on (torchrun exports
+    OMP_NUM_THREADS=1, which would otherwise throttle the CPU baseline)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_threads(int(n))
+    return num_threads()
+
+
 # Arrays are passed the way R holds them: a Fortran-ordered [rows x cols]
 # matrix is handed over as its flat column-major buffer.
 def _colmajor(a, dtype):

@@ -59,9 +59,14 @@ def test_s2n_bit_exact(ctx, oracle):
 
 
 # ------------------------------------------------- a1/a2/a3/a6/a7: null loop
+@pytest.mark.parametrize("s2n_mode", [0, 1])
 @pytest.mark.parametrize("R", [1, 2])
 @pytest.mark.parametrize("abs_flag", [False, True])
-def test_perm_null_s2n_wks(ctx, oracle, R, abs_flag):
+def test_perm_null_s2n_wks(ctx, oracle, R, abs_flag, s2n_mode):
+    """s2n_mode 0: bit-faithful score kernel (scores bit-exact); s2n_mode 1
+    (default): FP64 tensor-core contraction + certification (scores to 1e-11
+    relative, ranks still bit-exact)."""
+    ctx.set_option("s2n_mode", s2n_mode)
     x, y, perm, off, idx = _case()
     if R == 2:
         rng = np.random.default_rng(9)
@@ -73,14 +78,46 @@ def test_perm_null_s2n_wks(ctx, oracle, R, abs_flag):
                                     abs_flag=abs_flag, return_scores=True)
     assert rc == 0
     gsc, grk = ctx.debug_last(P * R)
+    ctx.set_option("s2n_mode", 1)
     want_sc = sc.reshape(sc.shape[0], -1, order="F")
     if abs_flag:  # the device keeps signed scores and applies abs when ranking
-        assert np.array_equal(np.abs(gsc), want_sc)
-    else:
+        gsc = np.abs(gsc)
+    if s2n_mode == 0:
         assert np.array_equal(gsc, want_sc)                     # bit-exact scores
+    else:
+        assert np.allclose(gsc, want_sc, rtol=1e-11, atol=1e-13)
     assert np.array_equal(grk, _ranks(oracle, want_sc))         # bit-exact ranks
     assert got.shape == want.shape
     assert np.abs(got - want).max() <= ES_TOL
+
+
+def test_tensor_scores_certified_ranks(ctx, oracle):
+    """near ties under the tensor-core score path: duplicated genes (exact ties in
+    the reference), a gene and its 10x copy (1 ulp apart in the reference,
+    tests/testthat/test_s2n.R:44-48), and a gene whose classes are far apart
+    relative to its variance (cancellation in E[x^2] - mean^2).  Ranks must equal
+    the reference's; also when the certification lists overflow (fallback)."""
+    G, n, P = 800, 24, 40
+    x, y = synth.two_class(G, n, seed=11)
+    x = x.copy()
+    x[:, 100] = x[:, 7]; x[:, 101] = x[:, 7]; x[:, 300] = x[:, 299]          # duplicates
+    x[:, 400] = 10.0 * x[:, 8]; x[:, 401] = 1e3 * x[:, 9]                     # scaled copies
+    x[:, 500] = np.where(y[:, 0] == 1, 1e4, -1e4) + 1e-3 * x[:, 10]           # cancellation
+    off, idx = synth.gene_sets_csr(G, 20, (10, 60), "uniform", seed=5)
+    perm = synth.perm_matrix(n, P, seed=2)
+    perm[:, 0] = np.arange(1, n + 1)                                          # identity: the far-apart labelling
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    rc, want, sc = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, oracle.ES_WKS,
+                                    return_scores=True)
+    assert rc == 0
+    want_rk = _ranks(oracle, sc[:, 0, :])
+    for cap in (4 << 20, 16):                                                 # 16: forces the overflow fallback
+        ctx.set_option("cert_cap", cap)
+        got = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm)
+        gsc, grk = ctx.debug_last(P)
+        assert np.array_equal(grk, want_rk), cap
+        assert np.abs(got - want).max() <= ES_TOL
+    ctx.set_option("cert_cap", 4 << 20)
 
 
 def test_perm_null_blocks_and_generic_kernel(ctx, oracle):
