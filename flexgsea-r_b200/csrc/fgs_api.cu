@@ -192,7 +192,7 @@ static int rank_and_es(fgs_ctx *c, int es_kind, double p_exp, int abs_flag, long
       FGS_TRY(c->cert_redo.ensure((size_t)Cb + 8));
       FGS_CUDA(cudaMemsetAsync(c->cert_redo.p, 0, (size_t)Cb * sizeof(int), c->stream));
       tc.redo = c->cert_redo.p; tc.overflow = c->flags.p + (c->flags.n - 1);
-      tc.rel_tol = 1e-9; tc.abs_tol = 1e-11;
+      tc.rel_tol = 1e-10; tc.abs_tol = 1e-12;  // >= 50x the contraction-vs-reference error bound (k_s2n_mma.cu)
       FGS_TRY(launch_sort(c, c->scores.p, G, Cb, abs_flag, p_exp, c->rank16.p, c->sabs.p, nullptr, &tc));
       FGS_TRY(launch_s2n_exact_entries(c, c->x.p, c->n, G, c->cur_labels, c->n1n2.p, c->s2n_R, tc.list,
                                        tc.count, c->opt_cert_cap, c->scores.p, c->flags.p + c->cur_flag0));

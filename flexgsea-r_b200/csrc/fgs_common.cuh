@@ -103,6 +103,7 @@ struct fgs_ctx {
   // [S] in processing order (descending size): {member offset, m | slow << 31,
   // offset of the set's ordered-rank list inside a column's list row, set id}
   fgs::DevBuf<int4> set_info;
+  fgs::DevBuf<double> set_invgm;   // [S] 1 / (G - m), processing order
   long long list_pitch = 0;        // uint16 elements per column of ordered-rank lists
   fgs::DevBuf<uint16_t> es_lists;  // [Cb][list_pitch]
   std::vector<int> h_set_off;

@@ -138,7 +138,7 @@ template <int NB, bool W_SMEM>
 __device__ __forceinline__ double wks_one_set(const uint16_t *__restrict__ s_rank,
                                               const double *__restrict__ wsrc,
                                               const int *__restrict__ set_idx, int off, int m, int G,
-                                              int lane) {
+                                              double invGm, int lane) {
   constexpr int NR = (NB + 1) / 2;
   uint32_t gid[NB];
 #pragma unroll
@@ -146,10 +146,13 @@ __device__ __forceinline__ double wks_one_set(const uint16_t *__restrict__ s_ran
     const int j = b * 32 + lane;
     gid[b] = (j < m) ? (uint32_t)__ldg(set_idx + off + j) : 0xffffffffu;
   }
+  // pads carry rank G: they sort behind every real rank and (weights on chip)
+  // index the zero slot appended to the weight array
+  const uint32_t pad = (uint32_t)G;
   uint32_t v[NR];
 #pragma unroll
   for (int q = 0; q < NR; q++) {
-    uint32_t lo = 0xffffu, hi = 0xffffu;
+    uint32_t lo = pad, hi = pad;
     if (gid[2 * q] != 0xffffffffu) lo = (uint32_t)s_rank[gid[2 * q]] - 1u;
     if (NB > 1) { if (gid[(2 * q + 1) % NB] != 0xffffffffu) hi = (uint32_t)s_rank[gid[(2 * q + 1) % NB]] - 1u; }
     v[q] = NB > 1 ? (lo | (hi << 16)) : lo;
@@ -162,29 +165,39 @@ __device__ __forceinline__ double wks_one_set(const uint16_t *__restrict__ s_ran
 #pragma unroll
   for (int t = 0; t < NB; t++) {
     const uint32_t r0 = (NB > 1) ? ((v[t >> 1] >> (16 * (t & 1))) & 0xffffu) : v[0];
-    const double w = (k0 + t < m) ? wsrc[r0] : 0.0;
+    const double w = W_SMEM ? wsrc[r0] : ((k0 + t < m) ? wsrc[r0] : 0.0);
     wv[t] = w;
     lsum += w;
   }
+  // inclusive warp scan of the lane sums; the shuffle's own in-range predicate
+  // guards the add (no select)
   double incw = lsum;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    const double t = __shfl_up_sync(0xffffffffu, incw, d);
-    if (lane >= d) incw += t;
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, tlo, thi;\n\t.reg .f64 t;\n\t"
+                 "mov.b64 {lo, hi}, %0;\n\t"
+                 "shfl.sync.up.b32 tlo|p, lo, %1, 0, 0xffffffff;\n\t"
+                 "shfl.sync.up.b32 thi|p, hi, %1, 0, 0xffffffff;\n\t"
+                 "mov.b64 t, {tlo, thi};\n\t"
+                 "@p add.f64 %0, %0, t;\n\t}"
+                 : "+d"(incw) : "r"(d));
   }
   const double W = __shfl_sync(0xffffffffu, incw, 31);
-  double cum = __shfl_up_sync(0xffffffffu, incw, 1);
-  if (lane == 0) cum = 0.0;
-  const double invW = 1.0 / W, invGm = 1.0 / (double)(G - m);
+  double cum = incw - lsum;  // exclusive prefix of this lane (one rounding; ES tolerance is 1e-10)
+  const double invW = 1.0 / W;
+  // (r - k) as a double without integer->double conversions: 2^52 + r0 has the
+  // integer in its low mantissa word; subtracting 2^52 + kk is exact
+  const double kbase = 4503599627370496.0 + (double)k0;
   double mx = -INFINITY, mn = INFINITY;
 #pragma unroll
   for (int t = 0; t < NB; t++) {
     const int kk = k0 + t;
     if (kk < m) {
-      const int r0 = (int)((NB > 1) ? ((v[t >> 1] >> (16 * (t & 1))) & 0xffffu) : v[0]);
+      const uint32_t r0 = (NB > 1) ? ((v[t >> 1] >> (16 * (t & 1))) & 0xffffu) : v[0];
       cum += wv[t];
       // d_miss = (r - k) / (G - m) with r = r0 + 1, k = kk + 1 (R/flexgsea.R:825-826)
-      const double ps = cum * invW - (double)(r0 - kk) * invGm;
+      const double rmk = __hiloint2double(0x43300000, (int)r0) - (kbase + (double)t);
+      const double ps = cum * invW - rmk * invGm;
       const double ng = ps - wv[t] * invW;
       mx = (ps > mx) ? ps : mx;
       mn = (ng < mn) ? ng : mn;
@@ -205,13 +218,14 @@ constexpr int ES_THREADS = 768;  // 24 warps, <= 85 registers each
 template <bool W_SMEM>
 __global__ void __launch_bounds__(ES_THREADS, 1)
 es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sabs, int G,
-              long long C, const int4 *__restrict__ set_info, const int *__restrict__ set_idx, int S,
-              double *__restrict__ es_out) {
+              long long C, const int4 *__restrict__ set_info, const int *__restrict__ set_idx,
+              const double *__restrict__ set_invgm, int S, double *__restrict__ es_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const size_t Gp = pitch_of(G);
   uint16_t *s_rank = (uint16_t *)smem;
   double *s_abs = (double *)(smem + Gp * 2);
+  if (W_SMEM && tid < 8) s_abs[G + tid] = 0.0;  // zero slot(s) behind the weights: the pads' weight
 
   for (long long col = blockIdx.x; col < C; col += gridDim.x) {
     __syncthreads();
@@ -220,9 +234,7 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
       uint4 *dst = (uint4 *)s_rank;
       for (int i = tid; i < (int)(Gp / 8); i += blockDim.x) dst[i] = __ldg(src + i);
       if (W_SMEM) {
-        const double2 *ws = (const double2 *)(sabs + (size_t)col * Gp);
-        double2 *wd = (double2 *)s_abs;
-        for (int i = tid; i < (int)(Gp / 2); i += blockDim.x) wd[i] = __ldg(ws + i);
+        for (int i = tid; i < G; i += blockDim.x) s_abs[i] = __ldg(sabs + (size_t)col * Gp + i);
       }
     }
     __syncthreads();
@@ -234,12 +246,13 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
       const int4 info = __ldg(set_info + k);  // {member offset, m | slow << 31, -, set id}
       if (info.y < 0) continue;               // es_wks_generic_kernel does these
       const int off = info.x, m = info.y;
+      const double ig = __ldg(set_invgm + k);  // 1 / (G - m)
       double es;
-      if (m <= 32) es = wks_one_set<1, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, lane);
-      else if (m <= 64) es = wks_one_set<2, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, lane);
-      else if (m <= 128) es = wks_one_set<4, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, lane);
-      else if (m <= 256) es = wks_one_set<8, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, lane);
-      else es = wks_one_set<16, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, lane);
+      if (m <= 32) es = wks_one_set<1, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, ig, lane);
+      else if (m <= 64) es = wks_one_set<2, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, ig, lane);
+      else if (m <= 128) es = wks_one_set<4, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, ig, lane);
+      else if (m <= 256) es = wks_one_set<8, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, ig, lane);
+      else es = wks_one_set<16, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, ig, lane);
       if (lane == 0) es_col[info.w] = es;
     }
   }
@@ -340,6 +353,14 @@ int launch_es_wks_generic(fgs_ctx *c, const uint16_t *d_rank16, const double *d_
   return FGS_OK;
 }
 
+// 1 / (G - m) per set in processing order (G is a launch parameter: user-score
+// calls may rank a different number of genes than the resident x)
+__global__ void fill_invgm_kernel(const int4 *__restrict__ set_info, int S, int G,
+                                  double *__restrict__ invgm) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < S) invgm[k] = 1.0 / (double)(G - (set_info[k].y & 0x7fffffff));
+}
+
 int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
                   double *d_es) {
   if (C <= 0 || c->S <= 0) return FGS_OK;
@@ -351,16 +372,21 @@ int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, in
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
   int grid = c->num_sms;
   if (grid > C) grid = (int)C;
-  const bool w_smem = Gp * 10 <= budget;  // rank (2 B) + weight (8 B) per gene on chip
-  const size_t smem = w_smem ? Gp * 10 : Gp * 2;
+  const bool w_smem = Gp * 10 + 64 <= budget;  // rank (2 B) + weight (8 B) per gene on chip + zero slots
+  const size_t smem = w_smem ? Gp * 10 + 64 : Gp * 2;
+  FGS_TRY(c->set_invgm.ensure(c->S));
+  fill_invgm_kernel<<<ceil_div(c->S, 256), 256, 0, c->stream>>>(c->set_info.p, c->S, G, c->set_invgm.p);
+  c->launches++;
   if (w_smem) {
     auto k = es_wks_kernel<true>;
     FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx.p, c->S, d_es);
+    k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx.p,
+                                             c->set_invgm.p, c->S, d_es);
   } else {
     auto k = es_wks_kernel<false>;
     FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx.p, c->S, d_es);
+    k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx.p,
+                                             c->set_invgm.p, c->S, d_es);
   }
   c->launches++;
   FGS_CUDA(cudaGetLastError());

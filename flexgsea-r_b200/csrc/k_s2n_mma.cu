@@ -17,12 +17,12 @@
 //   * the epilogue lists every (column, gene) whose variance suffered
 //     cancellation (E[x^2] / var > S2N_CANCEL_LIMIT) or is not finite,
 //   * the ranking kernel lists every adjacent pair of the sorted column closer
-//     than S2N_TIE_REL (relative) / S2N_TIE_ABS,
+//     than the tie tolerance (TieCert, set in fgs_api.cu),
 // and s2n_exact_entries_kernel recomputes exactly those entries with the
 // bit-faithful arithmetic of k_s2n.cu; the affected columns are ranked again.
 // Error bound of the contraction after the cancellation guard: n * u * limit
-// ~ 2e-12 relative for n = 200, two orders below the tie threshold, so every
-// pair whose order could differ from the reference's is recomputed exactly.
+// ~ 4e-13 relative for n = 200 (plus ~1e-12 worst case from the class sums), two
+// orders below the tie threshold (1e-10 relative, 1e-12 absolute), so every pair whose order could differ from the reference's is recomputed exactly.
 #include "fgs_common.cuh"
 
 namespace fgs {
@@ -60,7 +60,7 @@ int launch_center(fgs_ctx *c, const double *d_x, int n, int G, double *d_xc, dou
 }
 
 constexpr int SM_BG = 32, SM_BN = 64, SM_BK = 16, SM_PAD = 4;  // genes x columns x samples per tile
-constexpr double S2N_CANCEL_LIMIT = 100.0;
+constexpr double S2N_CANCEL_LIMIT = 16.0;
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -69,9 +69,10 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 }
 
 __device__ __forceinline__ void push_entry(int2 *__restrict__ list, int *__restrict__ count, int cap,
-                                           int col, int gene) {
+                                           int *__restrict__ overflow, int col, int gene) {
   const int at = atomicAdd(count, 1);
   if (at < cap) list[at] = make_int2(col, gene);
+  else atomicOr(overflow, 16);  // the caller reruns the block bit-faithfully
 }
 
 // CTA tile: 32 genes x 64 columns; 8 warps = 2 (gene halves of 16) x 4 (column
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(256)
 s2n_mma_kernel(const double *__restrict__ xc, const double *__restrict__ tot, int n, int G,
                const uint32_t *__restrict__ labels, const int *__restrict__ n1n2, int R, long long C,
                int W, double *__restrict__ scores, int2 *__restrict__ list, int *__restrict__ count,
-               int cap) {
+               int cap, int *__restrict__ overflow) {
   __shared__ double As[SM_BG][SM_BK + SM_PAD];
   __shared__ double Bs[SM_BN][SM_BK + SM_PAD];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -150,7 +151,7 @@ s2n_mma_kernel(const double *__restrict__ xc, const double *__restrict__ tot, in
         const double coef = (m1 - m2) / (sqrt(fmax(v1, 0.0)) + sqrt(fmax(v2, 0.0)));
         scores[(size_t)col * G + g] = coef;
         const bool shaky = !(v1 * S2N_CANCEL_LIMIT > e1) || !(v2 * S2N_CANCEL_LIMIT > e2) || !isfinite(coef);
-        if (shaky) push_entry(list, count, cap, (int)col, g);
+        if (shaky) push_entry(list, count, cap, overflow, (int)col, g);
       }
   }
 }
@@ -161,7 +162,8 @@ int launch_s2n_mma(fgs_ctx *c, const double *d_xc, const double *d_tot, int n, i
   if (C <= 0 || G <= 0) return FGS_OK;
   dim3 grid(ceil_div(G, SM_BG), ceil_div(C, SM_BN));
   s2n_mma_kernel<<<grid, 256, 0, c->stream>>>(d_xc, d_tot, n, G, d_labels, d_n1n2, R, C, (n + 31) / 32,
-                                              d_scores, d_list, d_count, cap);
+                                              d_scores, d_list, d_count, cap,
+                                              c->flags.p + (c->flags.n - 1));
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   return FGS_OK;

@@ -320,7 +320,10 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
           if (p_exp != 1.0) w = pow(w, p_exp);
           sa[q] = w;
           rk[g] = (uint16_t)(q + 1);
-          if (tc.list && q + 1 < G) {
+          // a neighbour whose 32-bit key differs by >= 2 is > 1e-6 away in relative
+          // terms; only closer keys (or scores so small that the absolute tolerance
+          // could bite) need the exact comparison
+          if (tc.list && q + 1 < G && (skey[q + 1] - skey[q] <= 1u || fabs(sq) <= 1e-5)) {
             const uint32_t g2 = sidx[q + 1];
             double s2 = sc[g2];
             if (abs_flag) s2 = fabs(s2);
