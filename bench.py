@@ -286,8 +286,11 @@ def run_gpu(args):
                 "note": "stage time from CUDA events on the library's stream inside the timed region"}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
-        try:
-            roofline["traffic"] = json.load(open(tr)).get(roofline["kernel"])
+        try:  # DRAM bytes per launch from the committed ncu --set full capture (per column x columns per launch)
+            t = json.load(open(tr)).get(roofline["kernel"])
+            if t:
+                roofline["traffic"] = t["dram_bytes_per_column"] * cols / dl["launches_per_step"]
+                roofline["traffic_source"] = t["source"]
         except Exception:
             pass
 

@@ -376,6 +376,7 @@ int fgs_set_gene_sets(fgs_ctx *c, const int *offsets, const int *index, int n_se
   FGS_TRY(h2d(c, c->slow_ids.p, slow_ids.data(), slow_ids.size()));
   FGS_TRY(sync(c));
   c->S = n_sets; c->nnz = nnz; c->max_set = max_idx; c->n_slow = (int)slow_ids.size();
+  c->invgm_G = -1;
   c->h_set_off.assign(offsets, offsets + n_sets + 1);
   return FGS_OK;
 }

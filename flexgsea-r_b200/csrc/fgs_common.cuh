@@ -104,6 +104,7 @@ struct fgs_ctx {
   // offset of the set's ordered-rank list inside a column's list row, set id}
   fgs::DevBuf<int4> set_info;
   fgs::DevBuf<double> set_invgm;   // [S] 1 / (G - m), processing order
+  int invgm_G = -1;                // G the array was filled for (-1: stale)
   long long list_pitch = 0;        // uint16 elements per column of ordered-rank lists
   fgs::DevBuf<uint16_t> es_lists;  // [Cb][list_pitch]
   std::vector<int> h_set_off;

@@ -374,9 +374,12 @@ int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, in
   if (grid > C) grid = (int)C;
   const bool w_smem = Gp * 10 + 64 <= budget;  // rank (2 B) + weight (8 B) per gene on chip + zero slots
   const size_t smem = w_smem ? Gp * 10 + 64 : Gp * 2;
-  FGS_TRY(c->set_invgm.ensure(c->S));
-  fill_invgm_kernel<<<ceil_div(c->S, 256), 256, 0, c->stream>>>(c->set_info.p, c->S, G, c->set_invgm.p);
-  c->launches++;
+  if (c->invgm_G != G) {  // once per (gene sets, G)
+    FGS_TRY(c->set_invgm.ensure(c->S));
+    fill_invgm_kernel<<<ceil_div(c->S, 256), 256, 0, c->stream>>>(c->set_info.p, c->S, G, c->set_invgm.p);
+    c->launches++;
+    c->invgm_G = G;
+  }
   if (w_smem) {
     auto k = es_wks_kernel<true>;
     FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -403,6 +403,67 @@ def test_staged_sig_equals_single(ctx):
     assert np.array_equal(fin["fdr"], one["fdr"])
 
 
+# ------------------------------------------ BASELINE.json sizes (full G, S)
+def test_c2_full_size_parity(ctx, oracle):
+    """BASELINE configs[1] at its real shape (20,000 genes x 200 samples, 8,000
+    sets of 15-500 genes) on 64 of the permutations: ranks bit-exact, ES within
+    1e-10, against the oracle on the same permutation matrix."""
+    c = synth.CONFIGS["C2"]
+    off, idx = synth.gene_sets_csr(c["G"], c["S"], c["sizes"], c["size_dist"], seed=1)
+    x, y = synth.two_class(c["G"], c["n"], off, idx, seed=2)
+    P = 64
+    perm = synth.perm_matrix(c["n"], P, seed=4)
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    got = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm)
+    gsc, grk = ctx.debug_last(P)
+    oracle.use_all_cores()
+    rc, want, sc = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, oracle.ES_WKS,
+                                    return_scores=True)
+    assert rc == 0
+    assert np.allclose(gsc, sc[:, 0, :], rtol=1e-11, atol=1e-13)
+    assert np.array_equal(grk, _ranks(oracle, sc[:, 0, :]))
+    assert np.abs(got - want).max() <= ES_TOL
+
+
+def test_c2_full_nperm_properties(ctx):
+    """size-independent properties at the full nperm = 10,000 of configs[1]:
+    the null of two half shards (global permutation ids) equals the one-shot null
+    bit for bit; every ES is finite and in [-1, 1]; p-values in (0, 1]."""
+    c = synth.CONFIGS["C2"]
+    off, idx = synth.gene_sets_csr(c["G"], c["S"], c["sizes"], c["size_dist"], seed=1)
+    x, y = synth.two_class(c["G"], c["n"], off, idx, seed=2)
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    P, seed = c["P"], 99
+    full = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, seed=seed, perm_id0=0)
+    assert np.isfinite(full).all() and np.abs(full).max() <= 1.0
+    sc = ctx.score_observed(nat.SCORE_S2N)
+    es = ctx.observed_es(nat.ES_WEIGHTED_KS, sc, ragged=False)["es"][:, 0]
+    sig = ctx.calc_sig(es)
+    assert (sig["p"] > 0).all() and (sig["p"] <= 1).all() and (sig["fdr"] > 0).all() and (sig["fdr"] <= 1).all()
+    assert int(sig["glob_counts"][2] + sig["glob_counts"][3]) <= c["S"] * P
+    lo = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P // 2, seed=seed, perm_id0=0)
+    assert np.array_equal(lo, full[:, :, :P // 2])
+    hi = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P - P // 2, seed=seed, perm_id0=P // 2)
+    assert np.array_equal(hi, full[:, :, P // 2:])
+
+
+def test_large_gene_count_paths(ctx, oracle):
+    """G > 32768 (configs[4] has 60,000 transcripts): ranks come from the 64-bit
+    global-memory sort and the ES kernel reads its weights from global memory."""
+    G, n, S, P = 40000, 48, 120, 6
+    off, idx = synth.gene_sets_csr(G, S, (15, 500), "loguniform", seed=7)
+    x, y = synth.two_class(G, n, off, idx, seed=8)
+    perm = synth.perm_matrix(n, P, seed=9)
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    got = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm)
+    _, grk = ctx.debug_last(P)
+    oracle.use_all_cores()
+    rc, want, sc = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, oracle.ES_WKS,
+                                    return_scores=True)
+    assert rc == 0 and np.array_equal(grk, _ranks(oracle, sc[:, 0, :]))
+    assert np.abs(got - want).max() <= ES_TOL
+
+
 # ----------------------------------------------------- the R-API mirror
 def test_flexgsea_end_to_end(ctx, oracle):
     """flexgsea() with flexgsea_s2n + flexgsea_weighted_ks (BASELINE configs[0]
