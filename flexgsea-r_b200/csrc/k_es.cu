@@ -398,16 +398,77 @@ int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, in
   return FGS_OK;
 }
 
+// K5 on chip: persistent CTA per SM, the score column (8 G bytes) staged in shared
+// memory, a warp per set (descending size, round-robin), members gathered from
+// shared memory.  Per member two FP64 adds: sum(v) and sum(|v|); then
+//   mean    = sum(v) / m                                            (:763)
+//   maxmean : pos = (sum|v| + sum v) / 2m, neg = (sum|v| - sum v) / 2m (:734-735),
+//             es = max(pos, neg), negated iff neg > pos               (:736-737)
+constexpr int ESM_THREADS = 1024;
+__global__ void __launch_bounds__(ESM_THREADS, 1)
+es_mean_smem_kernel(const double *__restrict__ scores, int G, long long C,
+                    const int4 *__restrict__ set_info, const int *__restrict__ set_idx, int S,
+                    int es_kind, int abs_flag, double *__restrict__ es_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double *s_sc = (double *)smem;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  for (long long col = blockIdx.x; col < C; col += gridDim.x) {
+    __syncthreads();
+    const double *sc = scores + (size_t)col * G;
+    for (int i = tid; i < G; i += blockDim.x) {
+      const double v = __ldg(sc + i);
+      s_sc[i] = abs_flag ? fabs(v) : v;
+    }
+    __syncthreads();
+    double *es_col = es_out + (size_t)col * S;
+    for (int k = warp; k < S; k += nwarps) {
+      const int4 info = __ldg(set_info + k);
+      const int off = info.x, m = info.y & 0x7fffffff;  // duplicates are just members here
+      double sv = 0.0, sa = 0.0;
+      for (int j = lane; j < m; j += 32) {
+        const double v = s_sc[__ldg(set_idx + off + j)];
+        sv += v;
+        sa += fabs(v);
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+      }
+      if (lane == 0) {
+        double es;
+        if (es_kind == FGS_ES_MEAN) es = sv / m;
+        else {
+          const double ps = (sa + sv) / 2 / m, ng = (sa - sv) / 2 / m;
+          es = fmax(ps, ng);
+          if (isnan(ps) || isnan(ng)) es = nan("");
+          else if (ng > ps) es = -es;
+        }
+        es_col[info.w] = es;
+      }
+    }
+  }
+}
+
 int launch_es_mean(fgs_ctx *c, const double *d_scores, int G, long long C, int es_kind,
                    int abs_flag, double *d_es) {
   if (C <= 0 || c->S <= 0) return FGS_OK;
-  long long units = (long long)c->S * C;
-  long long blocks = (units + 7) / 8;
-  long long cap = (long long)c->num_sms * 32;
-  if (blocks > cap) blocks = cap;
-  es_mean_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(d_scores, G, C, c->set_off.p,
-                                                          c->set_idx.p, c->S, es_kind, abs_flag,
-                                                          d_es);
+  const size_t smem = (size_t)G * 8;
+  if (smem <= (size_t)c->smem_optin) {
+    int grid = c->num_sms;
+    if (grid > C) grid = (int)C;
+    FGS_CUDA(cudaFuncSetAttribute(es_mean_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    es_mean_smem_kernel<<<grid, ESM_THREADS, smem, c->stream>>>(d_scores, G, C, c->set_info.p, c->set_idx.p,
+                                                                c->S, es_kind, abs_flag, d_es);
+  } else {  // column does not fit on chip: gather through L1/L2
+    long long units = (long long)c->S * C;
+    long long blocks = (units + 7) / 8;
+    long long cap = (long long)c->num_sms * 32;
+    if (blocks > cap) blocks = cap;
+    es_mean_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(d_scores, G, C, c->set_off.p,
+                                                            c->set_idx.p, c->S, es_kind, abs_flag,
+                                                            d_es);
+  }
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   return FGS_OK;
