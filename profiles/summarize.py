@@ -30,6 +30,7 @@ here = os.path.dirname(os.path.abspath(__file__))
 tpath = os.path.join(here, "traffic.json")
 traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
 lines = []
+seen = {}
 for rep in reps:
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
@@ -47,6 +48,9 @@ for rep in reps:
                 if key.startswith("dram__bytes"):
                     dram += float(r[i]) * UNIT.get(units[i], 1.0)
         lines.append("")
+        if short in seen and seen[short] >= dram:
+            continue  # keep the heaviest launch of a kernel (e.g. the first ranking pass, not the re-rank)
+        seen[short] = dram
         traffic[short] = {"dram_bytes_per_column": dram / cols_per_launch, "columns_in_capture": cols_per_launch,
                           "source": os.path.basename(rep) + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}
 open(out_md, "w").write("\n".join(lines) + "\n")
