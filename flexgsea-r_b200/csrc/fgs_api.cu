@@ -274,7 +274,7 @@ int fgs_destroy(fgs_ctx *c) {
   cudaStreamSynchronize(c->stream);
   c->x.release(); c->xc.release(); c->xtot.release(); c->cert_list.release(); c->cert_ctr.release();
   c->cert_redo.release(); c->sort_redo.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release();
-  c->set_info.release(); c->es_lists.release(); c->slow_ids.release(); c->ybin.release();
+  c->set_info.release(); c->set_invgm.release(); c->slow_ids.release(); c->ybin.release();
   c->n1n2.release(); c->lm_H.release(); c->perm.release(); c->labels.release(); c->lm_B.release();
   c->scores.release(); c->rank16.release(); c->sabs.release(); c->sort_keys.release();
   c->sort_idx.release(); c->flags.release(); c->counters.release(); c->es_null.release();
@@ -360,14 +360,10 @@ int fgs_set_gene_sets(fgs_ctx *c, const int *offsets, const int *index, int n_se
   FGS_TRY(c->set_off.ensure((size_t)n_sets + 1));
   FGS_TRY(c->set_idx.ensure((size_t)std::max<long long>(nnz, 1)));
   std::vector<int4> info(n_sets);
-  long long lp = 0;
   for (int k = 0; k < n_sets; k++) {
     const int sid = order[k], m = offsets[sid + 1] - offsets[sid];
-    info[k] = make_int4(offsets[sid], slow[sid] ? (m | (int)0x80000000) : m, (int)lp, sid);
-    if (!slow[sid]) lp += (m + 15) & ~15;  // 32-byte aligned list starts (16 ranks per lane max)
+    info[k] = make_int4(offsets[sid], slow[sid] ? (m | (int)0x80000000) : m, 0, sid);
   }
-  if (lp > 0x7fffffffLL) { set_error("gene sets too large"); return FGS_ERR_UNSUPPORTED; }
-  c->list_pitch = std::max<long long>(lp, 8);
   FGS_TRY(c->set_info.ensure(n_sets));
   FGS_TRY(c->slow_ids.ensure(std::max<size_t>(slow_ids.size(), 1)));
   FGS_TRY(h2d(c, c->set_off.p, offsets, (size_t)n_sets + 1));

@@ -100,13 +100,11 @@ struct fgs_ctx {
   int max_set = 0;
   fgs::DevBuf<int> set_off;        // [S+1]
   fgs::DevBuf<int> set_idx;        // [nnz] 0-based gene ids
-  // [S] in processing order (descending size): {member offset, m | slow << 31,
-  // offset of the set's ordered-rank list inside a column's list row, set id}
+  // [S] in processing order (descending size): {member offset, m | slow << 31, 0, set id};
+  // "slow" = duplicated members or more than 512 members (order-free kernel)
   fgs::DevBuf<int4> set_info;
   fgs::DevBuf<double> set_invgm;   // [S] 1 / (G - m), processing order
   int invgm_G = -1;                // G the array was filled for (-1: stale)
-  long long list_pitch = 0;        // uint16 elements per column of ordered-rank lists
-  fgs::DevBuf<uint16_t> es_lists;  // [Cb][list_pitch]
   std::vector<int> h_set_off;
   int n_slow = 0;
   fgs::DevBuf<int> slow_ids;       // [n_slow]

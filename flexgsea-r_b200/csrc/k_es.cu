@@ -16,7 +16,7 @@
 // classes (32 * {1,2,4,8,16} members).
 //
 // Sets with duplicated members (R keeps them; a pad-free distinct-rank sort
-// cannot) or more than ES_LISTCAP members go through es_wks_generic_kernel, an
+// cannot) or more than ES_MAX_SET members go through es_wks_generic_kernel, an
 // O(m^2 / 32) warp kernel that needs no ordering at all: max/min over the
 // members of pos/neg is order independent once each member knows its ordinal
 // and prefix weight, which it gets by comparing against every other member.
@@ -24,7 +24,7 @@
 
 namespace fgs {
 
-constexpr int ES_LISTCAP = 512;  // max members per set in the bitmap kernel (16 per lane)
+constexpr int ES_MAX_SET = 512;  // largest set the bitonic kernel takes (16 ranks per lane); fgs_set_gene_sets flags larger ones
 
 __device__ __forceinline__ double warp_max(double v) {
   for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -214,7 +214,7 @@ __device__ __forceinline__ double wks_one_set(const uint16_t *__restrict__ s_ran
   return es;
 }
 
-constexpr int ES_THREADS = 768;  // 24 warps, <= 85 registers each
+constexpr int ES_THREADS = 768;  // 24 warps, <= 85 registers each (1024 threads at 64 registers: same speed, spills)
 template <bool W_SMEM>
 __global__ void __launch_bounds__(ES_THREADS, 1)
 es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sabs, int G,
@@ -258,8 +258,8 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
   }
 }
 
-// Order-free weighted KS for sets the bitmap kernel cannot take (duplicates,
-// > ES_LISTCAP members).  One warp per (set, column).  Ties in rank (duplicate
+// Order-free weighted KS for sets the bitonic kernel cannot take (duplicates,
+// > ES_MAX_SET members).  One warp per (set, column).  Ties in rank (duplicate
 // members) are ordered by member position, like R's stable order() (:822).
 __global__ void __launch_bounds__(256)
 es_wks_generic_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sabs, int G,

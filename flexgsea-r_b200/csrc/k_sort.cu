@@ -9,8 +9,8 @@
 //
 // One CTA per score column (segment), persistent over columns.  8 passes of
 // 8 bits; a pass in which every key has the same digit is skipped.  Ranking
-// inside a pass is the warp-match scheme: each warp owns a contiguous slice of
-// the current order, per round `__match_any_sync` groups equal digits, and a
+// inside a pass is the warp-peer scheme: each warp owns a contiguous slice of
+// the current order, per round eight ballots group the lanes with equal digits, and a
 // [digit][warp] counter table (scanned digit-major) gives stable destinations.
 //
 // Outputs per column: rank16[g] (1-based descending rank, uint16) and
@@ -36,6 +36,20 @@ __device__ __forceinline__ void certify_pair(const TieCert &tc, long long col, d
     }
     tc.redo[col] = 1;
   }
+}
+
+// lanes holding the same 8-bit digit, by eight ballots (one per digit bit).
+// __match_any_sync gives the same mask but serialises over the distinct values
+// in the warp (~30 of them for random digits), which made it the bottleneck.
+__device__ __forceinline__ uint32_t digit_peers(uint32_t d) {
+  uint32_t peers = 0xffffffffu;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t bit = (d >> i) & 1u;
+    const uint32_t b = __ballot_sync(0xffffffffu, bit);
+    peers &= b ^ (bit - 1u);  // bit set: lanes with the bit; clear: lanes without
+  }
+  return peers;
 }
 
 constexpr int SORT_THREADS = 512;
@@ -96,8 +110,8 @@ sort_rank_kernel(const double *__restrict__ scores, int G, long long C, int abs_
       for (int base = wbeg; base < wend; base += 32) {
         int q = base + lane;
         bool valid = q < wend;
-        uint32_t d = valid ? (uint32_t)((kin[q] >> shift) & 255ull) : 256u + lane;
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t d = valid ? (uint32_t)((kin[q] >> shift) & 255ull) : 0u;
+        uint32_t peers = digit_peers(d) & __ballot_sync(0xffffffffu, valid);
         if (valid && (peers & lt_mask) == 0) cnt[d * SORT_WARPS + warp] += __popc(peers);
         __syncwarp();
       }
@@ -132,8 +146,8 @@ sort_rank_kernel(const double *__restrict__ scores, int G, long long C, int abs_
         bool valid = q < wend;
         unsigned long long key = valid ? kin[q] : 0ull;
         uint32_t id = valid ? iin[q] : 0u;
-        uint32_t d = valid ? (uint32_t)((key >> shift) & 255ull) : 256u + lane;
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t d = valid ? (uint32_t)((key >> shift) & 255ull) : 0u;
+        uint32_t peers = digit_peers(d) & __ballot_sync(0xffffffffu, valid);
         uint32_t dst = 0;
         if (valid) dst = cnt[d * SORT_WARPS + warp] + __popc(peers & lt_mask);
         __syncwarp();
@@ -161,10 +175,11 @@ sort_rank_kernel(const double *__restrict__ scores, int G, long long C, int abs_
 }
 
 // ---------------------------------------------------------------------------
-// Shared-memory variant (G <= 32768): the column is sorted on chip by the TOP
-// 32 bits of the key -- 4 radix passes instead of 8, 6 bytes per gene in shared
-// memory (uint32 key + uint16 gene), items staged in registers between the
-// read and the scatter of a pass -- and the (few, short) runs of equal 32-bit
+// Shared-memory variant (G <= 29696): the column is sorted on chip by the TOP
+// 32 bits of the key -- 6 bytes per gene in shared memory (uint32 key + uint16
+// gene), 8 stable passes of 4 bits with per-thread byte counters (no warp votes),
+// items staged in registers between the read and the scatter of a pass -- and
+// the (few, short) runs of equal 32-bit
 // keys are then put in exact 64-bit order by an insertion sort on the low key
 // halves.  Exact ties need no work: the stable sort from reverse gene order
 // already left them in R's order.  A column with a run longer than
@@ -172,7 +187,7 @@ sort_rank_kernel(const double *__restrict__ scores, int G, long long C, int abs_
 // ---------------------------------------------------------------------------
 constexpr int SORT32_THREADS = 1024;
 constexpr int SORT32_WARPS = 32;
-constexpr int SORT32_CSTRIDE = 33;  // counter row stride: (digit + warp) mod 32 banks
+constexpr int SORT32_MAX_G = 29 * 1024;  // 6 bytes per gene + 48 KB of counters in 227 KB
 constexpr int SORT_MAX_RUN = 48;
 
 template <int IPT>
@@ -184,13 +199,13 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
   constexpr int GS = SORT32_THREADS * IPT;  // padded capacity
   uint32_t *skey = (uint32_t *)smem;
   uint16_t *sidx = (uint16_t *)(skey + GS);
-  uint32_t *cnt = (uint32_t *)(sidx + GS);
+  // per pass: cnt8[digit][thread] (16 x 1024 bytes) -> pre16[digit][thread] (exclusive prefixes)
+  unsigned char *cnt8 = (unsigned char *)(sidx + GS + (GS & 1));
+  uint16_t *pre16 = (uint16_t *)(cnt8 + 16 * SORT32_THREADS);
   __shared__ uint32_t wsum[SORT32_WARPS];
   __shared__ int s_redo;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t lt_mask = (1u << lane) - 1u;
   const size_t Gp = pitch_of(G);
-  const int wbase = warp * (32 * IPT);  // this warp's slice of the current order
 
   for (long long col = blockIdx.x; col < C; col += gridDim.x) {
     if (only_cols && !only_cols[col]) continue;  // uniform per CTA
@@ -213,27 +228,30 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
     }
     __syncthreads();
 
-    for (int pass = 0; pass < 4; pass++) {
-      const int shift = pass * 8;
-      for (int i = tid; i < 256 * SORT32_CSTRIDE; i += SORT32_THREADS) cnt[i] = 0;
-      uint32_t k[IPT];
+    // 8 stable passes of 4 bits.  Thread t owns the IPT consecutive positions
+    // [t*IPT, (t+1)*IPT) of the current order (IPT is odd: conflict-free) and a
+    // private byte counter per digit, so ranking needs no warp votes at all:
+    // destination = prefix over (digit, thread) + arrival order inside the thread.
+    for (int pass = 0; pass < 8; pass++) {
+      const int shift = pass * 4;
+      for (int i = tid; i < 16 * SORT32_THREADS / 4; i += SORT32_THREADS) ((uint32_t *)cnt8)[i] = 0;
+      uint32_t k[IPT], id2[(IPT + 1) / 2];
 #pragma unroll
-      for (int r = 0; r < IPT; r++) k[r] = skey[wbase + r * 32 + lane];
-      __syncthreads();
-      // sweep 1: per-warp digit counts
+      for (int i = 0; i < IPT; i++) k[i] = skey[tid * IPT + i];
 #pragma unroll
-      for (int r = 0; r < IPT; r++) {
-        const uint32_t d = (k[r] >> shift) & 255u;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        if ((peers & lt_mask) == 0) cnt[d * SORT32_CSTRIDE + warp] += __popc(peers);
-        __syncwarp();
+      for (int i = 0; i < IPT; i += 2) {
+        const uint32_t a0 = sidx[tid * IPT + i];
+        const uint32_t b0 = (i + 1 < IPT) ? sidx[tid * IPT + i + 1] : 0u;
+        id2[i >> 1] = a0 | (b0 << 16);
       }
       __syncthreads();
-      {  // exclusive scan over (digit-major, warp-minor): 8 entries per thread
-        const int d = tid >> 2, w0 = (tid & 3) * 8;
-        uint32_t v[8], tot = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) { v[j] = cnt[d * SORT32_CSTRIDE + w0 + j]; tot += v[j]; }
+      for (int i = 0; i < IPT; i++) cnt8[((k[i] >> shift) & 15u) * SORT32_THREADS + tid]++;
+      __syncthreads();
+      {  // exclusive scan over (digit-major, thread-minor): 16 byte counters per thread
+        const uint4 w = ((const uint4 *)cnt8)[tid];
+        const uint32_t tot = __dp4a(w.x, 0x01010101u, __dp4a(w.y, 0x01010101u,
+                              __dp4a(w.z, 0x01010101u, __dp4a(w.w, 0x01010101u, 0u))));
         uint32_t inc = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -242,32 +260,28 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
         }
         if (lane == 31) wsum[warp] = inc;
         __syncthreads();
-        uint32_t woff = 0;
-        for (int w = 0; w < warp; w++) woff += wsum[w];
-        uint32_t run = woff + inc - tot;
+        uint32_t run = inc - tot;
+        for (int w2 = 0; w2 < warp; w2++) run += wsum[w2];
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+        uint32_t outw[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) { cnt[d * SORT32_CSTRIDE + w0 + j] = run; run += v[j]; }
-      }
-      // the gene ids travel with the keys: read them all before anyone scatters
-      uint32_t id2[(IPT + 1) / 2];
-#pragma unroll
-      for (int r = 0; r < IPT; r += 2) {
-        const uint32_t a = sidx[wbase + r * 32 + lane];
-        const uint32_t b = (r + 1 < IPT) ? sidx[wbase + (r + 1) * 32 + lane] : 0u;
-        id2[r >> 1] = a | (b << 16);
+        for (int j = 0; j < 16; j += 2) {
+          const uint32_t c0 = (ws[j >> 2] >> (8 * (j & 3))) & 255u, c1 = (ws[j >> 2] >> (8 * ((j + 1) & 3))) & 255u;
+          outw[j >> 1] = run | ((run + c0) << 16);
+          run += c0 + c1;
+        }
+        uint4 *dst = (uint4 *)(pre16 + 16 * tid);
+        dst[0] = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+        dst[1] = make_uint4(outw[4], outw[5], outw[6], outw[7]);
       }
       __syncthreads();
-      // sweep 2: stable scatter
 #pragma unroll
-      for (int r = 0; r < IPT; r++) {
-        const uint32_t d = (k[r] >> shift) & 255u;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const uint32_t dst = cnt[d * SORT32_CSTRIDE + warp] + __popc(peers & lt_mask);
-        __syncwarp();
-        if ((peers & lt_mask) == 0) cnt[d * SORT32_CSTRIDE + warp] += __popc(peers);
-        __syncwarp();
-        skey[dst] = k[r];
-        sidx[dst] = (uint16_t)(id2[r >> 1] >> (16 * (r & 1)));
+      for (int i = 0; i < IPT; i++) {
+        uint16_t *slot = pre16 + ((k[i] >> shift) & 15u) * SORT32_THREADS + tid;
+        const uint32_t dst = *slot;
+        *slot = (uint16_t)(dst + 1);
+        skey[dst] = k[i];
+        sidx[dst] = (uint16_t)(id2[i >> 1] >> (16 * (i & 1)));
       }
       __syncthreads();
     }
@@ -340,7 +354,7 @@ template <int IPT>
 static int launch_sort32_t(fgs_ctx *c, const double *d_scores, int G, long long C, int abs_flag,
                            double p_exp, uint16_t *d_rank16, double *d_sabs, int *d_redo, int grid,
                            const int *only_cols, const TieCert &tc) {
-  const size_t smem = (size_t)SORT32_THREADS * IPT * 6 + (size_t)256 * SORT32_CSTRIDE * 4;
+  const size_t smem = (size_t)SORT32_THREADS * IPT * 6 + 2 + (size_t)SORT32_THREADS * 16 * 3;
   auto k = sort_rank32_kernel<IPT>;
   FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k<<<grid, SORT32_THREADS, smem, c->stream>>>(d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, d_redo,
@@ -360,21 +374,22 @@ int launch_sort(fgs_ctx *c, const double *d_scores, int G, long long C, int abs_
     return FGS_ERR_UNSUPPORTED;
   }
   const int *only = nullptr;
-  if (G <= 32768 && !c->opt_sort64) {
+  if (G <= SORT32_MAX_G && !c->opt_sort64) {
     int grid = c->num_sms;
     if (grid > C) grid = (int)C;
     FGS_TRY(c->sort_redo.ensure((size_t)C + 8));
     int *redo = c->sort_redo.p;
     FGS_CUDA(cudaMemsetAsync(redo, 0, (size_t)C * sizeof(int), c->stream));
     const int ipt = (G + SORT32_THREADS - 1) / SORT32_THREADS;
-    if (ipt <= 4) FGS_TRY(launch_sort32_t<4>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc));
-    else if (ipt <= 8) FGS_TRY(launch_sort32_t<8>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc));
-    else if (ipt <= 12) FGS_TRY(launch_sort32_t<12>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc));
-    else if (ipt <= 16) FGS_TRY(launch_sort32_t<16>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc));
-    else if (ipt <= 20) FGS_TRY(launch_sort32_t<20>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc));
-    else if (ipt <= 24) FGS_TRY(launch_sort32_t<24>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc));
-    else if (ipt <= 28) FGS_TRY(launch_sort32_t<28>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc));
-    else FGS_TRY(launch_sort32_t<32>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc));
+#define FGS_SORT32(N) FGS_TRY(launch_sort32_t<N>(c, d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, redo, grid, only_cols, tc))
+    if (ipt <= 5) FGS_SORT32(5);
+    else if (ipt <= 9) FGS_SORT32(9);
+    else if (ipt <= 13) FGS_SORT32(13);
+    else if (ipt <= 17) FGS_SORT32(17);
+    else if (ipt <= 21) FGS_SORT32(21);
+    else if (ipt <= 25) FGS_SORT32(25);
+    else FGS_SORT32(29);
+#undef FGS_SORT32
     only = redo;  // the 64-bit kernel below only redoes flagged columns
   } else {
     only = only_cols;
