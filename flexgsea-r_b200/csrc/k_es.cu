@@ -51,6 +51,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 // comparators have a compile-time direction (one VIMNMX each), and only the
 // cross-lane ones depend on the lane's side of the exchange (VIMNMX + 2 LOP3).
 __device__ __forceinline__ uint32_t swap_halves(uint32_t v) { return __byte_perm(v, v, 0x1032); }
+// comparator between the two halves of one register: as 32-bit numbers, the
+// larger of (hi:lo) and (lo:hi) is the one with the larger key on top and the
+// smaller below -- one PRMT and one 32-bit max
+// (`flipped`: smaller key on top instead -- the form the next level's in-lane
+// mirror stage wants for the upper register of each pair, saving its two PRMTs)
+__device__ __forceinline__ uint32_t sort_halves(uint32_t v, bool flipped = false) {
+  return flipped ? min(v, swap_halves(v)) : max(v, swap_halves(v));
+}
 // cross-lane comparator: `hi_mask` is 0 on the lane that keeps the minimum and
 // ~0 on the lane that keeps the maximum; max = min ^ a ^ o, so
 // result = min ^ ((a ^ o) & hi_mask): one VIMNMX + two LOP3, no predicates
@@ -79,18 +87,17 @@ __device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[(NB + 1) / 2], 
       // mirror stage: e <-> e ^ (k - 1)
       if (k == 2) {
 #pragma unroll
-        for (int q = 0; q < NR; q++) {
-          const uint32_t t = swap_halves(v[q]);
-          v[q] = __byte_perm(__vminu2(v[q], t), __vmaxu2(v[q], t), 0x5410);
-        }
+        for (int q = 0; q < NR; q++) v[q] = sort_halves(v[q], 2 * k <= NB && (q & (k >> 1)));
       } else if (k <= NB) {  // slot ^ (k - 1): register q ^ (k/2 - 1), halves swapped
+        // the upper register of each pair arrives with its halves already
+        // exchanged (see sort_halves) and stays so until this level's last stage
 #pragma unroll
         for (int q = 0; q < NR; q++) {
           const int qb = q ^ ((k >> 1) - 1);
           if (qb > q) {
-            const uint32_t a = v[q], t = swap_halves(v[qb]);
+            const uint32_t a = v[q], t = v[qb];
             v[q] = __vminu2(a, t);
-            v[qb] = swap_halves(__vmaxu2(a, t));
+            v[qb] = __vmaxu2(a, t);
           }
         }
       } else {  // lane ^ (k / NB - 1), slots reversed: register NR-1-q, halves swapped
@@ -121,10 +128,7 @@ __device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[(NB + 1) / 2], 
           }
         } else {  // j == 1: the two halves of one register
 #pragma unroll
-          for (int q = 0; q < NR; q++) {
-            const uint32_t t = swap_halves(v[q]);
-            v[q] = __byte_perm(__vminu2(v[q], t), __vmaxu2(v[q], t), 0x5410);
-          }
+          for (int q = 0; q < NR; q++) v[q] = sort_halves(v[q], 2 * k <= NB && (q & (k >> 1)));
         }
       }
     }
