@@ -273,7 +273,7 @@ int fgs_destroy(fgs_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->x.release(); c->xc.release(); c->xtot.release(); c->cert_list.release(); c->cert_ctr.release();
-  c->cert_redo.release(); c->sort_redo.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release();
+  c->cert_redo.release(); c->sort_redo.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release(); c->set_idx16.release();
   c->set_info.release(); c->set_invgm.release(); c->slow_ids.release(); c->ybin.release();
   c->n1n2.release(); c->lm_H.release(); c->perm.release(); c->labels.release(); c->lm_B.release();
   c->scores.release(); c->rank16.release(); c->sabs.release(); c->sort_keys.release();
@@ -351,7 +351,7 @@ int fgs_set_gene_sets(fgs_ctx *c, const int *offsets, const int *index, int n_se
       if (tmp[g] == s) dup = true;
       tmp[g] = s;
     }
-    if (dup || (b - a) > 512) { slow[s] = 1; slow_ids.push_back(s); }
+    if (dup || (b - a) > fgs::ES_MAX_SET) { slow[s] = 1; slow_ids.push_back(s); }
     order[s] = s;
   }
   std::stable_sort(order.begin(), order.end(), [&](int p, int q) {
@@ -360,10 +360,13 @@ int fgs_set_gene_sets(fgs_ctx *c, const int *offsets, const int *index, int n_se
   FGS_TRY(c->set_off.ensure((size_t)n_sets + 1));
   FGS_TRY(c->set_idx.ensure((size_t)std::max<long long>(nnz, 1)));
   std::vector<int4> info(n_sets);
+  long long blocks = 0;  // members as uint16 in 16-byte blocks, processing order (launch_es_wks fills them)
   for (int k = 0; k < n_sets; k++) {
     const int sid = order[k], m = offsets[sid + 1] - offsets[sid];
-    info[k] = make_int4(offsets[sid], slow[sid] ? (m | (int)0x80000000) : m, 0, sid);
+    info[k] = make_int4(offsets[sid], slow[sid] ? (m | (int)0x80000000) : m, (int)blocks, sid);
+    blocks += (m + 7) / 8;
   }
+  c->idx16_blocks = blocks;
   FGS_TRY(c->set_info.ensure(n_sets));
   FGS_TRY(c->slow_ids.ensure(std::max<size_t>(slow_ids.size(), 1)));
   FGS_TRY(h2d(c, c->set_off.p, offsets, (size_t)n_sets + 1));

@@ -100,11 +100,14 @@ struct fgs_ctx {
   int max_set = 0;
   fgs::DevBuf<int> set_off;        // [S+1]
   fgs::DevBuf<int> set_idx;        // [nnz] 0-based gene ids
-  // [S] in processing order (descending size): {member offset, m | slow << 31, 0, set id};
-  // "slow" = duplicated members or more than 512 members (order-free kernel)
+  // [S] in processing order (descending size):
+  //   {member offset, m | slow << 31, offset in set_idx16 in blocks of 8, set id};
+  // "slow" = duplicated members or more than ES_MAX_SET members (order-free kernel)
   fgs::DevBuf<int4> set_info;
   fgs::DevBuf<double> set_invgm;   // [S] 1 / (G - m), processing order
-  int invgm_G = -1;                // G the array was filled for (-1: stale)
+  fgs::DevBuf<uint16_t> set_idx16; // members as uint16, processing order, 8-blocks padded with gene G
+  long long idx16_blocks = 0;
+  int invgm_G = -1;                // G set_invgm / set_idx16 were filled for (-1: stale)
   std::vector<int> h_set_off;
   int n_slow = 0;
   fgs::DevBuf<int> slow_ids;       // [n_slow]
@@ -203,6 +206,8 @@ int launch_sig_finish(fgs_ctx *c, const double *d_nes, const long long *d_null_c
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 // row pitch (elements) of the per-column rank16 / sabs arrays: 16-byte aligned rows
+// largest set the in-register weighted-KS kernel takes (64 ranks per lane on a whole warp)
+constexpr int ES_MAX_SET = 2048;
 __host__ __device__ inline size_t pitch_of(int G) { return ((size_t)G + 7) & ~(size_t)7; }
 
 }  // namespace fgs

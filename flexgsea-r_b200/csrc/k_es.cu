@@ -24,7 +24,7 @@
 
 namespace fgs {
 
-constexpr int ES_MAX_SET = 512;  // largest set the bitonic kernel takes (16 ranks per lane); fgs_set_gene_sets flags larger ones
+// ES_MAX_SET (fgs_common.cuh): largest set the in-register kernel takes
 
 __device__ __forceinline__ double warp_max(double v) {
   for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -40,16 +40,23 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---- in-register bitonic sort of a set's ranks --------------------------------
-// N = 32 * NB uint16 keys per warp, NB per lane, two per 32-bit register
-// (VIMNMX.U16x2 compares both at once).  Blocked layout: element e = lane * NB +
-// slot, so after the sort lane l holds the hits with ordinals [l*NB, l*NB + NB)
-// -- exactly the distribution the running-sum scan wants.  Pads are 0xFFFF.
+// N = LANES * NB uint16 keys held by LANES consecutive lanes, NB per lane, two
+// per 32-bit register (VIMNMX.U16x2 compares both at once).  Blocked layout:
+// element e = lane * NB + slot, so after the sort lane l holds the hits with
+// ordinals [l*NB, l*NB + NB) -- exactly the distribution the running-sum scan
+// wants.  Pads carry the key G.
+//
+// LANES = 8 puts four sets in one warp: a comparator stage between lanes costs
+// five instructions per register (SHFL, two predicated VIMNMX, two moves) but
+// one between registers only one, so the fewer lanes a set spans the cheaper its
+// sort -- 6 cross-lane stages instead of 15 -- and every fixed cost (scan,
+// reduction, set bookkeeping) is shared by four sets.
 //
 // The network is the direction-free form of bitonic sort: level k first
 // compares e with its mirror e ^ (k - 1), then e with e ^ j for j = k/4 .. 1,
 // and EVERY comparator sends the minimum to the lower index.  So all in-lane
 // comparators have a compile-time direction (one VIMNMX each), and only the
-// cross-lane ones depend on the lane's side of the exchange (VIMNMX + 2 LOP3).
+// cross-lane ones depend on the lane's side of the exchange.
 __device__ __forceinline__ uint32_t swap_halves(uint32_t v) { return __byte_perm(v, v, 0x1032); }
 // comparator between the two halves of one register: as 32-bit numbers, the
 // larger of (hi:lo) and (lo:hi) is the one with the larger key on top and the
@@ -60,76 +67,63 @@ __device__ __forceinline__ uint32_t sort_halves(uint32_t v, bool flipped = false
   return flipped ? min(v, swap_halves(v)) : max(v, swap_halves(v));
 }
 // cross-lane comparator: `hi_mask` is 0 on the lane that keeps the minimum and
-// ~0 on the lane that keeps the maximum; max = min ^ a ^ o, so
-// result = min ^ ((a ^ o) & hi_mask): one VIMNMX + two LOP3, no predicates
+// ~0 on the lane that keeps the maximum
 __device__ __forceinline__ uint32_t minmax2_side(uint32_t a, uint32_t o, uint32_t hi_mask) {
   return hi_mask ? __vmaxu2(a, o) : __vminu2(a, o);
 }
-__device__ __forceinline__ uint32_t minmax1_side(uint32_t a, uint32_t o, uint32_t hi_mask) {
-  return hi_mask ? max(a, o) : min(a, o);
-}
 
-template <int NB>
-__device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[(NB + 1) / 2], int lane) {
-  constexpr int N = 32 * NB;
-  if constexpr (NB == 1) {
+template <int LANES, int NB>
+__device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[NB / 2], int lane) {
+  constexpr int N = LANES * NB;
+  constexpr int NR = NB / 2;
+  static_assert(NB >= 2 && LANES <= 32, "packed pairs");
 #pragma unroll
-    for (int k = 2; k <= N; k <<= 1) {
-      v[0] = minmax1_side(v[0], __shfl_xor_sync(0xffffffffu, v[0], k - 1), 0u - ((lane / (k >> 1)) & 1u));
+  for (int k = 2; k <= N; k <<= 1) {
+    // mirror stage: e <-> e ^ (k - 1)
+    if (k == 2) {
 #pragma unroll
-      for (int j = k >> 2; j > 0; j >>= 1)
-        v[0] = minmax1_side(v[0], __shfl_xor_sync(0xffffffffu, v[0], j), 0u - ((lane / j) & 1u));
-    }
-  } else {
-    constexpr int NR = NB / 2;
+      for (int q = 0; q < NR; q++) v[q] = sort_halves(v[q], 2 * k <= NB && (q & (k >> 1)));
+    } else if (k <= NB) {  // slot ^ (k - 1): register q ^ (k/2 - 1), halves swapped
+      // the upper register of each pair arrives with its halves already
+      // exchanged (see sort_halves) and stays so until this level's last stage
 #pragma unroll
-    for (int k = 2; k <= N; k <<= 1) {
-      // mirror stage: e <-> e ^ (k - 1)
-      if (k == 2) {
-#pragma unroll
-        for (int q = 0; q < NR; q++) v[q] = sort_halves(v[q], 2 * k <= NB && (q & (k >> 1)));
-      } else if (k <= NB) {  // slot ^ (k - 1): register q ^ (k/2 - 1), halves swapped
-        // the upper register of each pair arrives with its halves already
-        // exchanged (see sort_halves) and stays so until this level's last stage
-#pragma unroll
-        for (int q = 0; q < NR; q++) {
-          const int qb = q ^ ((k >> 1) - 1);
-          if (qb > q) {
-            const uint32_t a = v[q], t = v[qb];
-            v[q] = __vminu2(a, t);
-            v[qb] = __vmaxu2(a, t);
-          }
+      for (int q = 0; q < NR; q++) {
+        const int qb = q ^ ((k >> 1) - 1);
+        if (qb > q) {
+          const uint32_t a = v[q], t = v[qb];
+          v[q] = __vminu2(a, t);
+          v[qb] = __vmaxu2(a, t);
         }
-      } else {  // lane ^ (k / NB - 1), slots reversed: register NR-1-q, halves swapped
-        const uint32_t hi_mask = 0u - ((lane / ((k / NB) >> 1)) & 1u);
-        uint32_t o[NR];
+      }
+    } else {  // lane ^ (k / NB - 1), slots reversed: register NR-1-q, halves swapped
+      const uint32_t hi_mask = 0u - ((lane / ((k / NB) >> 1)) & 1u);
+      uint32_t o[NR];
+#pragma unroll
+      for (int q = 0; q < NR; q++)
+        o[q] = swap_halves(__shfl_xor_sync(0xffffffffu, v[NR - 1 - q], (k / NB) - 1));
+#pragma unroll
+      for (int q = 0; q < NR; q++) v[q] = minmax2_side(v[q], o[q], hi_mask);
+    }
+#pragma unroll
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      if (j >= NB) {  // partner lane ^ (j / NB), same slot
+        const uint32_t hi_mask = 0u - ((lane / (j / NB)) & 1u);
 #pragma unroll
         for (int q = 0; q < NR; q++)
-          o[q] = swap_halves(__shfl_xor_sync(0xffffffffu, v[NR - 1 - q], (k / NB) - 1));
+          v[q] = minmax2_side(v[q], __shfl_xor_sync(0xffffffffu, v[q], j / NB), hi_mask);
+      } else if (j >= 2) {  // partner register q ^ (j / 2), same half
 #pragma unroll
-        for (int q = 0; q < NR; q++) v[q] = minmax2_side(v[q], o[q], hi_mask);
-      }
-#pragma unroll
-      for (int j = k >> 2; j > 0; j >>= 1) {
-        if (j >= NB) {  // partner lane ^ (j / NB), same slot
-          const uint32_t hi_mask = 0u - ((lane / (j / NB)) & 1u);
-#pragma unroll
-          for (int q = 0; q < NR; q++)
-            v[q] = minmax2_side(v[q], __shfl_xor_sync(0xffffffffu, v[q], j / NB), hi_mask);
-        } else if (j >= 2) {  // partner register q ^ (j / 2), same half
-#pragma unroll
-          for (int q = 0; q < NR; q++) {
-            const int qb = q ^ (j >> 1);
-            if (qb > q) {
-              const uint32_t a = v[q], b2 = v[qb];
-              v[q] = __vminu2(a, b2);
-              v[qb] = __vmaxu2(a, b2);
-            }
+        for (int q = 0; q < NR; q++) {
+          const int qb = q ^ (j >> 1);
+          if (qb > q) {
+            const uint32_t a = v[q], b2 = v[qb];
+            v[q] = __vminu2(a, b2);
+            v[qb] = __vmaxu2(a, b2);
           }
-        } else {  // j == 1: the two halves of one register
-#pragma unroll
-          for (int q = 0; q < NR; q++) v[q] = sort_halves(v[q], 2 * k <= NB && (q & (k >> 1)));
         }
+      } else {  // j == 1: the two halves of one register
+#pragma unroll
+        for (int q = 0; q < NR; q++) v[q] = sort_halves(v[q], 2 * k <= NB && (q & (k >> 1)));
       }
     }
   }
@@ -151,58 +145,79 @@ __device__ __forceinline__ double warp_max_exact(double x) {
   return __hiloint2double((int)(mh ^ (inv | 0x80000000u)), (int)(ml ^ inv));
 }
 
-// One set, one warp: gather the members' ranks, sort them in registers, then the
-// running sum over the ordered hits (lane-local sums, one warp scan, running
-// maxima / minima).  Returns the ES (valid in every lane).
-template <int NB, bool W_SMEM>
-__device__ __forceinline__ double wks_one_set(const uint16_t *__restrict__ s_rank,
-                                              const double *__restrict__ wsrc,
-                                              const int *__restrict__ set_idx, int off, int m, int G,
-                                              double invGm, int lane) {
-  constexpr int NR = (NB + 1) / 2;
-  uint32_t gid[NB];
-#pragma unroll
-  for (int b = 0; b < NB; b++) {  // member ids first: independent loads in flight
-    const int j = b * 32 + lane;
-    gid[b] = (j < m) ? (uint32_t)__ldg(set_idx + off + j) : 0xffffffffu;
-  }
-  // pads carry rank G: they sort behind every real rank and (weights on chip)
-  // index the zero slot appended to the weight array
-  const uint32_t pad = (uint32_t)G;
-  uint32_t v[NR];
-#pragma unroll
-  for (int q = 0; q < NR; q++) {
-    uint32_t lo = pad, hi = pad;
-    if (gid[2 * q] != 0xffffffffu) lo = (uint32_t)s_rank[gid[2 * q]] - 1u;
-    if (NB > 1) { if (gid[(2 * q + 1) % NB] != 0xffffffffu) hi = (uint32_t)s_rank[gid[(2 * q + 1) % NB]] - 1u; }
-    v[q] = NB > 1 ? (lo | (hi << 16)) : lo;
-  }
-  bitonic_sort_ranks<NB>(v, lane);
+// Two members' ranks (0-based, from the staged column) packed in one register.
+__device__ __forceinline__ uint32_t gather2(const uint16_t *__restrict__ s_rank, uint32_t pair) {
+  const uint32_t lo = s_rank[pair & 0xffffu], hi = s_rank[pair >> 16];
+  return __byte_perm(lo, hi, 0x5410);
+}
 
-  const int k0 = lane * NB;
-  double wv[NB];
+template <bool W_SMEM>
+__device__ __forceinline__ double reload_weight(const double *wsrc, uint32_t wsh, uint32_t r0) {
+  double w;
+  if (W_SMEM) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(w) : "r"(wsh + r0 * 8u));
+  else asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(w) : "l"(wsrc + r0));
+  return w;
+}
+
+// One set on LANES consecutive lanes (`ls` = lane within them), SL members per
+// lane: gather the members' ranks, sort them in registers, then the running sum
+// over the ordered hits (lane-local sums, one scan over the LANES lanes, running
+// maxima / minima).  Returns the ES (valid in every lane of the set).
+//   idx16: the set's members as uint16 gene ids in 16-byte blocks of eight,
+//   padded with the pad gene G, whose staged rank is the pad key G.
+template <int LANES, int SL, bool W_SMEM>
+__device__ __forceinline__ double wks_sets(const uint16_t *__restrict__ s_rank,
+                                           const double *__restrict__ wsrc,
+                                           const uint16_t *__restrict__ idx16, int zblk, int m, int G,
+                                           double invGm, int ls) {
+  constexpr int NR = SL / 2;
+  constexpr bool KEEPW = SL <= 16;  // member weights stay in registers between the two passes
+  const uint32_t padpair = (uint32_t)G * 0x10001u;
+  uint32_t v[NR];
+  if constexpr (SL == 4) {  // four members per lane: one 8-byte load
+    uint2 w = make_uint2(padpair, padpair);
+    if (ls * 4 < m) w = __ldg((const uint2 *)(idx16 + (size_t)zblk * 8) + ls);
+    v[0] = gather2(s_rank, w.x);
+    v[1] = gather2(s_rank, w.y);
+  } else {
+#pragma unroll
+    for (int b = 0; b < SL / 8; b++) {  // eight members per 16-byte load
+      const int blk = b * LANES + ls;
+      uint4 w = make_uint4(padpair, padpair, padpair, padpair);
+      if (blk * 8 < m) w = __ldg((const uint4 *)(idx16 + (size_t)zblk * 8) + blk);
+      v[4 * b + 0] = gather2(s_rank, w.x);
+      v[4 * b + 1] = gather2(s_rank, w.y);
+      v[4 * b + 2] = gather2(s_rank, w.z);
+      v[4 * b + 3] = gather2(s_rank, w.w);
+    }
+  }
+  bitonic_sort_ranks<LANES, SL>(v, ls);
+
+  const int k0 = ls * SL;
+  const uint32_t wsh = W_SMEM ? (uint32_t)__cvta_generic_to_shared(wsrc) : 0u;
+  double wv[KEEPW ? SL : 1];
   double lsum = 0.0;
 #pragma unroll
-  for (int t = 0; t < NB; t++) {
-    const uint32_t r0 = (NB > 1) ? ((v[t >> 1] >> (16 * (t & 1))) & 0xffffu) : v[0];
+  for (int t = 0; t < SL; t++) {
+    const uint32_t r0 = (v[t >> 1] >> (16 * (t & 1))) & 0xffffu;
     const double w = W_SMEM ? wsrc[r0] : ((k0 + t < m) ? wsrc[r0] : 0.0);
-    wv[t] = w;
+    if (KEEPW) wv[t] = w;
     lsum += w;
   }
-  // inclusive warp scan of the lane sums; the shuffle's own in-range predicate
-  // guards the add (no select)
+  // inclusive scan of the lane sums over the set's lanes; the shuffle's own
+  // in-range predicate guards the add (no select)
   double incw = lsum;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
+  for (int d = 1; d < LANES; d <<= 1) {
     asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, tlo, thi;\n\t.reg .f64 t;\n\t"
                  "mov.b64 {lo, hi}, %0;\n\t"
-                 "shfl.sync.up.b32 tlo|p, lo, %1, 0, 0xffffffff;\n\t"
-                 "shfl.sync.up.b32 thi|p, hi, %1, 0, 0xffffffff;\n\t"
+                 "shfl.sync.up.b32 tlo|p, lo, %1, %2, 0xffffffff;\n\t"
+                 "shfl.sync.up.b32 thi|p, hi, %1, %2, 0xffffffff;\n\t"
                  "mov.b64 t, {tlo, thi};\n\t"
                  "@p add.f64 %0, %0, t;\n\t}"
-                 : "+d"(incw) : "r"(d));
+                 : "+d"(incw) : "r"(d), "n"((32 - LANES) << 8));
   }
-  const double W = __shfl_sync(0xffffffffu, incw, 31);
+  const double W = __shfl_sync(0xffffffffu, incw, LANES - 1, LANES);
   double cum = incw - lsum;  // exclusive prefix of this lane (one rounding; ES tolerance is 1e-10)
   const double invW = 1.0 / W;
   // (r - k) as a double without integer->double conversions: 2^52 + r0 has the
@@ -210,68 +225,120 @@ __device__ __forceinline__ double wks_one_set(const uint16_t *__restrict__ s_ran
   const double kbase = 4503599627370496.0 + (double)k0;
   double mx = -INFINITY, mn = INFINITY;
 #pragma unroll
-  for (int t = 0; t < NB; t++) {
+  for (int t = 0; t < SL; t++) {
     const int kk = k0 + t;
     if (kk < m) {
-      const uint32_t r0 = (NB > 1) ? ((v[t >> 1] >> (16 * (t & 1))) & 0xffffu) : v[0];
-      cum += wv[t];
+      const uint32_t r0 = (v[t >> 1] >> (16 * (t & 1))) & 0xffffu;
+      // long lanes read the weight a second time (an opaque load: left to itself the
+      // compiler keeps all SL weights of the first pass alive and spills them)
+      const double w = KEEPW ? wv[KEEPW ? t : 0] : reload_weight<W_SMEM>(wsrc, wsh, r0);
+      cum += w;
       // d_miss = (r - k) / (G - m) with r = r0 + 1, k = kk + 1 (R/flexgsea.R:825-826)
       const double rmk = __hiloint2double(0x43300000, (int)r0) - (kbase + (double)t);
       const double ps = cum * invW - rmk * invGm;
-      const double ng = ps - wv[t] * invW;
+      const double ng = ps - w * invW;
       mx = (ps > mx) ? ps : mx;
       mn = (ng < mn) ? ng : mn;
     }
   }
-  mx = warp_max_exact(mx);
-  mn = -warp_max_exact(-mn);
+  if constexpr (LANES == 32) {
+    mx = warp_max_exact(mx);
+    mn = -warp_max_exact(-mn);
+  } else {
+#pragma unroll
+    for (int o = LANES / 2; o; o >>= 1) {
+      const double a = __shfl_xor_sync(0xffffffffu, mx, o), b = __shfl_xor_sync(0xffffffffu, mn, o);
+      mx = (a > mx) ? a : mx;
+      mn = (b < mn) ? b : mn;
+    }
+  }
   double es = (mx > -mn) ? mx : mn;                      // strict, :833
   if (W == 0.0 || m == G || m == 0) es = nan("");        // 0/0 in the reference
   return es;
 }
 
-constexpr int ES_THREADS = 768;  // 24 warps, <= 85 registers each (1024 threads at 64 registers: same speed, spills)
+constexpr int ES_THREADS = 768;  // 24 warps, <= 85 registers each
 template <bool W_SMEM>
 __global__ void __launch_bounds__(ES_THREADS, 1)
 es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sabs, int G,
-              long long C, const int4 *__restrict__ set_info, const int *__restrict__ set_idx,
+              long long C, const int4 *__restrict__ set_info, const uint16_t *__restrict__ idx16,
               const double *__restrict__ set_invgm, int S, double *__restrict__ es_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const size_t Gp = pitch_of(G);
-  uint16_t *s_rank = (uint16_t *)smem;
-  double *s_abs = (double *)(smem + Gp * 2);
+  uint16_t *s_rank = (uint16_t *)smem;                    // [Gp + 8]: 0-based ranks, pad gene at [G]
+  double *s_abs = (double *)(smem + (Gp + 8) * 2);
   if (W_SMEM && tid < 8) s_abs[G + tid] = 0.0;  // zero slot(s) behind the weights: the pads' weight
+  const int seg = lane >> 3, ls = lane & 7;
+  const int nquads = (S + 3) >> 2;
 
   for (long long col = blockIdx.x; col < C; col += gridDim.x) {
     __syncthreads();
-    {  // stage the column: 16-byte vector copies (rows are 16-byte aligned)
+    {  // stage the column: 16-byte vector copies (rows are 16-byte aligned), ranks made 0-based
       const uint4 *src = (const uint4 *)(rank16 + (size_t)col * Gp);
       uint4 *dst = (uint4 *)s_rank;
-      for (int i = tid; i < (int)(Gp / 8); i += blockDim.x) dst[i] = __ldg(src + i);
+      for (int i = tid; i < (int)(Gp / 8); i += blockDim.x) {
+        uint4 r = __ldg(src + i);
+        r.x = __vsub2(r.x, 0x00010001u); r.y = __vsub2(r.y, 0x00010001u);
+        r.z = __vsub2(r.z, 0x00010001u); r.w = __vsub2(r.w, 0x00010001u);
+        dst[i] = r;
+      }
       if (W_SMEM) {
         for (int i = tid; i < G; i += blockDim.x) s_abs[i] = __ldg(sabs + (size_t)col * Gp + i);
       }
     }
     __syncthreads();
+    if (tid == 0) s_rank[G] = (uint16_t)G;  // the pad gene's key (inside the staged row when G < Gp)
+    __syncthreads();
     const double *wsrc = W_SMEM ? s_abs : sabs + (size_t)col * Gp;
     double *es_col = es_out + (size_t)col * S;
-    // sets in descending size, round-robin over warps: similar work per warp and
-    // coherent size classes
-    for (int k = warp; k < S; k += nwarps) {
-      const int4 info = __ldg(set_info + k);  // {member offset, m | slow << 31, -, set id}
-      if (info.y < 0) continue;               // es_wks_generic_kernel does these
-      const int off = info.x, m = info.y;
-      const double ig = __ldg(set_invgm + k);  // 1 / (G - m)
-      double es;
-      if (m <= 32) es = wks_one_set<1, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, ig, lane);
-      else if (m <= 64) es = wks_one_set<2, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, ig, lane);
-      else if (m <= 128) es = wks_one_set<4, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, ig, lane);
-      else if (m <= 256) es = wks_one_set<8, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, ig, lane);
-      else es = wks_one_set<16, W_SMEM>(s_rank, wsrc, set_idx, off, m, G, ig, lane);
-      if (lane == 0) es_col[info.w] = es;
+    // sets in descending size, four per warp (eight lanes each), quads round-robin
+    // over the warps: similar work per warp and one size class per quad
+    for (int q = warp; q < nquads; q += nwarps) {
+      const int k = 4 * q + seg;
+      int4 info = make_int4(0, (int)0x80000000, 0, 0);  // {-, m | slow << 31, member block offset, set id}
+      double ig = 0.0;
+      if (k < S) { info = __ldg(set_info + k); ig = __ldg(set_invgm + k); }  // ig = 1 / (G - m)
+      const bool mine = info.y >= 0;              // slow sets: es_wks_generic_kernel does these
+      const int m = mine ? info.y : 0;
+      int mmax = max(m, __shfl_xor_sync(0xffffffffu, m, 8));
+      mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, 16));
+      if (mmax <= 8 * 64) {
+        double es;
+        if (mmax <= 8 * 4) es = wks_sets<8, 4, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls);
+        else if (mmax <= 8 * 8) es = wks_sets<8, 8, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls);
+        else if (mmax <= 8 * 16) es = wks_sets<8, 16, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls);
+        else if (mmax <= 8 * 32) es = wks_sets<8, 32, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls);
+        else es = wks_sets<8, 64, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls);
+        if (mine && ls == 0) es_col[info.w] = es;
+      } else {  // a quad with a set of 513 .. ES_MAX_SET members: one set at a time on the whole warp
+#pragma unroll 1
+        for (int i = 0; i < 4; i++) {
+          const int mi = __shfl_sync(0xffffffffu, m, 8 * i);
+          const int zi = __shfl_sync(0xffffffffu, info.z, 8 * i), wi = __shfl_sync(0xffffffffu, info.w, 8 * i);
+          const double igi = __shfl_sync(0xffffffffu, ig, 8 * i);
+          const bool on = __shfl_sync(0xffffffffu, (int)mine, 8 * i) != 0;
+          if (!on) continue;
+          double es;
+          if (mi <= 32 * 32) es = wks_sets<32, 32, W_SMEM>(s_rank, wsrc, idx16, zi, mi, G, igi, lane);
+          else es = wks_sets<32, 64, W_SMEM>(s_rank, wsrc, idx16, zi, mi, G, igi, lane);
+          if (lane == 0) es_col[wi] = es;
+        }
+      }
     }
   }
+}
+
+// Members of every set as uint16 gene ids, in processing order, each set in
+// 16-byte blocks of eight padded with the pad gene G (a warp per set).
+__global__ void build_idx16_kernel(const int4 *__restrict__ set_info, const int *__restrict__ set_idx,
+                                   int S, int G, uint16_t *__restrict__ idx16) {
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (k >= S) return;
+  const int4 info = set_info[k];
+  const int m = info.y & 0x7fffffff, mpad = (m + 7) & ~7;
+  for (int j = lane; j < mpad; j += 32)
+    idx16[(size_t)info.z * 8 + j] = (uint16_t)(j < m ? set_idx[info.x + j] : G);
 }
 
 // Order-free weighted KS for sets the bitonic kernel cannot take (duplicates,
@@ -384,27 +451,33 @@ int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, in
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
   const size_t Gp = pitch_of(G);
   const size_t budget = (size_t)c->smem_optin;
-  if (Gp * 2 > budget)  // the rank array does not fit on chip: the order-free kernel does everything
+  if (Gp * 2 + 16 > budget)  // the rank array does not fit on chip: the order-free kernel does everything
+    return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
+  if (G > 65534)  // the pad key G must fit a uint16 next to the ranks
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
   int grid = c->num_sms;
   if (grid > C) grid = (int)C;
-  const bool w_smem = Gp * 10 + 64 <= budget;  // rank (2 B) + weight (8 B) per gene on chip + zero slots
-  const size_t smem = w_smem ? Gp * 10 + 64 : Gp * 2;
+  // rank (2 B) + weight (8 B) per gene on chip, + pad gene, + zero weight slots
+  const bool w_smem = Gp * 10 + 16 + 64 <= budget;
+  const size_t smem = w_smem ? Gp * 10 + 16 + 64 : Gp * 2 + 16;
   if (c->invgm_G != G) {  // once per (gene sets, G)
     FGS_TRY(c->set_invgm.ensure(c->S));
     fill_invgm_kernel<<<ceil_div(c->S, 256), 256, 0, c->stream>>>(c->set_info.p, c->S, G, c->set_invgm.p);
-    c->launches++;
+    FGS_TRY(c->set_idx16.ensure((size_t)std::max<long long>(c->idx16_blocks, 1) * 8));
+    build_idx16_kernel<<<ceil_div(c->S, 8), 256, 0, c->stream>>>(c->set_info.p, c->set_idx.p, c->S, G,
+                                                                 c->set_idx16.p);
+    c->launches += 2;
     c->invgm_G = G;
   }
   if (w_smem) {
     auto k = es_wks_kernel<true>;
     FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx.p,
+    k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx16.p,
                                              c->set_invgm.p, c->S, d_es);
   } else {
     auto k = es_wks_kernel<false>;
     FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx.p,
+    k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx16.p,
                                              c->set_invgm.p, c->S, d_es);
   }
   c->launches++;
