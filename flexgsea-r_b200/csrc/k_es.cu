@@ -221,25 +221,27 @@ __device__ __forceinline__ double wks_sets(const uint16_t *__restrict__ s_rank,
   double cum = incw - lsum;  // exclusive prefix of this lane (one rounding; ES tolerance is 1e-10)
   const double invW = 1.0 / W;
   // (r - k) as a double without integer->double conversions: 2^52 + r0 has the
-  // integer in its low mantissa word; subtracting 2^52 + kk is exact
-  const double kbase = 4503599627370496.0 + (double)k0;
+  // integer in its low mantissa word; subtracting 2^52 + k0 and then t is exact
+  const double kbase = __hiloint2double(0x43300000, k0);
+  const int nvalid = m - k0;  // slots [0, nvalid) of this lane hold members, the rest pads
   double mx = -INFINITY, mn = INFINITY;
 #pragma unroll
   for (int t = 0; t < SL; t++) {
-    const int kk = k0 + t;
-    if (kk < m) {
-      const uint32_t r0 = (v[t >> 1] >> (16 * (t & 1))) & 0xffffu;
-      // long lanes read the weight a second time (an opaque load: left to itself the
-      // compiler keeps all SL weights of the first pass alive and spills them)
-      const double w = KEEPW ? wv[KEEPW ? t : 0] : reload_weight<W_SMEM>(wsrc, wsh, r0);
-      cum += w;
-      // d_miss = (r - k) / (G - m) with r = r0 + 1, k = kk + 1 (R/flexgsea.R:825-826)
-      const double rmk = __hiloint2double(0x43300000, (int)r0) - (kbase + (double)t);
-      const double ps = cum * invW - rmk * invGm;
-      const double ng = ps - w * invW;
-      mx = (ps > mx) ? ps : mx;
-      mn = (ng < mn) ? ng : mn;
-    }
+    const uint32_t r0 = (v[t >> 1] >> (16 * (t & 1))) & 0xffffu;
+    // long lanes read the weight a second time (an opaque load: left to itself the
+    // compiler keeps all SL weights of the first pass alive and spills them)
+    const double w = KEEPW ? wv[KEEPW ? t : 0]
+                           : ((W_SMEM || t < nvalid) ? reload_weight<W_SMEM>(wsrc, wsh, r0) : 0.0);
+    cum += w;
+    // d_miss = (r - k) / (G - m) with r = r0 + 1, k = k0 + t + 1 (R/flexgsea.R:825-826)
+    const double rmk = (__hiloint2double(0x43300000, (int)r0) - kbase) - (double)t;
+    const double ps = cum * invW - rmk * invGm;
+    const double ng = ps - w * invW;
+    // No branch around the pads (key G, weight 0, ordinals >= m): there
+    // pos = neg = (k - m) / (G - m) >= 0 up to rounding, which can never lower the
+    // minimum (neg of the first hit is <= 0), so only the maximum needs the guard.
+    mx = (t < nvalid && ps > mx) ? ps : mx;
+    mn = (ng < mn) ? ng : mn;
   }
   if constexpr (LANES == 32) {
     mx = warp_max_exact(mx);
