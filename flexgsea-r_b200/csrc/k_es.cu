@@ -145,24 +145,25 @@ __device__ __forceinline__ double warp_max_exact(double x) {
   return __hiloint2double((int)(mh ^ (inv | 0x80000000u)), (int)(ml ^ inv));
 }
 
-// Two members' ranks (0-based, from the staged column) packed in one register.
-__device__ __forceinline__ uint32_t gather2(const uint16_t *__restrict__ s_rank, uint32_t pair) {
+// Two members' ranks (0-based, from the staged column) packed in one register;
+// their hit weights (rank-indexed |score|^p; the pad rank G has weight 0) are
+// added to the lane's share of the set's weight total.
+template <bool W_SMEM>
+__device__ __forceinline__ uint32_t gather2(const uint16_t *__restrict__ s_rank,
+                                            const double *__restrict__ wsrc, uint32_t G, uint32_t pair,
+                                            double &w0, double &w1) {
   const uint32_t lo = s_rank[pair & 0xffffu], hi = s_rank[pair >> 16];
+  w0 += W_SMEM ? wsrc[lo] : (lo < G ? wsrc[lo] : 0.0);
+  w1 += W_SMEM ? wsrc[hi] : (hi < G ? wsrc[hi] : 0.0);
   return __byte_perm(lo, hi, 0x5410);
 }
 
-template <bool W_SMEM>
-__device__ __forceinline__ double reload_weight(const double *wsrc, uint32_t wsh, uint32_t r0) {
-  double w;
-  if (W_SMEM) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(w) : "r"(wsh + r0 * 8u));
-  else asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(w) : "l"(wsrc + r0));
-  return w;
-}
-
 // One set on LANES consecutive lanes (`ls` = lane within them), SL members per
-// lane: gather the members' ranks, sort them in registers, then the running sum
-// over the ordered hits (lane-local sums, one scan over the LANES lanes, running
-// maxima / minima).  Returns the ES (valid in every lane of the set).
+// lane.  Gather the members' ranks (and, order-free, the set's total weight W),
+// sort the ranks in registers, then ONE pass over the ordered hits per lane with
+// the lane-local running sum: the weight of the lanes below is a per-lane
+// constant, so it is added to the lane's maximum / minimum afterwards (one scan
+// of the lane totals).  Returns the ES (valid in every lane of the set).
 //   idx16: the set's members as uint16 gene ids in 16-byte blocks of eight,
 //   padded with the pad gene G, whose staged rank is the pad key G.
 template <int LANES, int SL, bool W_SMEM>
@@ -171,42 +172,57 @@ __device__ __forceinline__ double wks_sets(const uint16_t *__restrict__ s_rank,
                                            const uint16_t *__restrict__ idx16, int zblk, int m, int G,
                                            double invGm, int ls) {
   constexpr int NR = SL / 2;
-  constexpr bool KEEPW = SL <= 16;  // member weights stay in registers between the two passes
   const uint32_t padpair = (uint32_t)G * 0x10001u;
   uint32_t v[NR];
+  double w0 = 0.0, w1 = 0.0;
   if constexpr (SL == 4) {  // four members per lane: one 8-byte load
     uint2 w = make_uint2(padpair, padpair);
     if (ls * 4 < m) w = __ldg((const uint2 *)(idx16 + (size_t)zblk * 8) + ls);
-    v[0] = gather2(s_rank, w.x);
-    v[1] = gather2(s_rank, w.y);
+    v[0] = gather2<W_SMEM>(s_rank, wsrc, G, w.x, w0, w1);
+    v[1] = gather2<W_SMEM>(s_rank, wsrc, G, w.y, w0, w1);
   } else {
 #pragma unroll
     for (int b = 0; b < SL / 8; b++) {  // eight members per 16-byte load
       const int blk = b * LANES + ls;
       uint4 w = make_uint4(padpair, padpair, padpair, padpair);
       if (blk * 8 < m) w = __ldg((const uint4 *)(idx16 + (size_t)zblk * 8) + blk);
-      v[4 * b + 0] = gather2(s_rank, w.x);
-      v[4 * b + 1] = gather2(s_rank, w.y);
-      v[4 * b + 2] = gather2(s_rank, w.z);
-      v[4 * b + 3] = gather2(s_rank, w.w);
+      v[4 * b + 0] = gather2<W_SMEM>(s_rank, wsrc, G, w.x, w0, w1);
+      v[4 * b + 1] = gather2<W_SMEM>(s_rank, wsrc, G, w.y, w0, w1);
+      v[4 * b + 2] = gather2<W_SMEM>(s_rank, wsrc, G, w.z, w0, w1);
+      v[4 * b + 3] = gather2<W_SMEM>(s_rank, wsrc, G, w.w, w0, w1);
     }
   }
+  double W = w0 + w1;  // every lane of the set ends with the same bits (commutative butterfly)
+#pragma unroll
+  for (int o = LANES / 2; o; o >>= 1) W += __shfl_xor_sync(0xffffffffu, W, o);
+  const double invW = 1.0 / W;
+
   bitonic_sort_ranks<LANES, SL>(v, ls);
 
   const int k0 = ls * SL;
-  const uint32_t wsh = W_SMEM ? (uint32_t)__cvta_generic_to_shared(wsrc) : 0u;
-  double wv[KEEPW ? SL : 1];
-  double lsum = 0.0;
+  // (r - k) as a double without integer->double conversions: 2^52 + r0 has the
+  // integer in its low mantissa word; subtracting 2^52 + k0 and then t is exact
+  const double kbase = __hiloint2double(0x43300000, k0);
+  const int nvalid = m - k0;  // slots [0, nvalid) of this lane hold members, the rest pads
+  double cl = 0.0, mx = -INFINITY, mn = INFINITY;
 #pragma unroll
   for (int t = 0; t < SL; t++) {
     const uint32_t r0 = (v[t >> 1] >> (16 * (t & 1))) & 0xffffu;
-    const double w = W_SMEM ? wsrc[r0] : ((k0 + t < m) ? wsrc[r0] : 0.0);
-    if (KEEPW) wv[t] = w;
-    lsum += w;
+    const double w = (W_SMEM || t < nvalid) ? wsrc[r0] : 0.0;
+    cl += w;
+    // d_miss = (r - k) / (G - m) with r = r0 + 1, k = k0 + t + 1 (R/flexgsea.R:825-826)
+    const double rmk = (__hiloint2double(0x43300000, (int)r0) - kbase) - (double)t;
+    const double ps = cl * invW - rmk * invGm;
+    const double ng = ps - w * invW;
+    // No branch around the pads (key G, weight 0, ordinals >= m): there
+    // pos = neg = (k - m) / (G - m) >= 0 up to rounding, which can never lower the
+    // minimum (neg of the first hit is <= 0), so only the maximum needs the guard.
+    mx = (t < nvalid && ps > mx) ? ps : mx;
+    mn = (ng < mn) ? ng : mn;
   }
-  // inclusive scan of the lane sums over the set's lanes; the shuffle's own
-  // in-range predicate guards the add (no select)
-  double incw = lsum;
+  // weight of the lanes below: inclusive scan of the lane totals over the set's
+  // lanes; the shuffle's own in-range predicate guards the add (no select)
+  double incw = cl;
 #pragma unroll
   for (int d = 1; d < LANES; d <<= 1) {
     asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, tlo, thi;\n\t.reg .f64 t;\n\t"
@@ -217,32 +233,9 @@ __device__ __forceinline__ double wks_sets(const uint16_t *__restrict__ s_rank,
                  "@p add.f64 %0, %0, t;\n\t}"
                  : "+d"(incw) : "r"(d), "n"((32 - LANES) << 8));
   }
-  const double W = __shfl_sync(0xffffffffu, incw, LANES - 1, LANES);
-  double cum = incw - lsum;  // exclusive prefix of this lane (one rounding; ES tolerance is 1e-10)
-  const double invW = 1.0 / W;
-  // (r - k) as a double without integer->double conversions: 2^52 + r0 has the
-  // integer in its low mantissa word; subtracting 2^52 + k0 and then t is exact
-  const double kbase = __hiloint2double(0x43300000, k0);
-  const int nvalid = m - k0;  // slots [0, nvalid) of this lane hold members, the rest pads
-  double mx = -INFINITY, mn = INFINITY;
-#pragma unroll
-  for (int t = 0; t < SL; t++) {
-    const uint32_t r0 = (v[t >> 1] >> (16 * (t & 1))) & 0xffffu;
-    // long lanes read the weight a second time (an opaque load: left to itself the
-    // compiler keeps all SL weights of the first pass alive and spills them)
-    const double w = KEEPW ? wv[KEEPW ? t : 0]
-                           : ((W_SMEM || t < nvalid) ? reload_weight<W_SMEM>(wsrc, wsh, r0) : 0.0);
-    cum += w;
-    // d_miss = (r - k) / (G - m) with r = r0 + 1, k = k0 + t + 1 (R/flexgsea.R:825-826)
-    const double rmk = (__hiloint2double(0x43300000, (int)r0) - kbase) - (double)t;
-    const double ps = cum * invW - rmk * invGm;
-    const double ng = ps - w * invW;
-    // No branch around the pads (key G, weight 0, ordinals >= m): there
-    // pos = neg = (k - m) / (G - m) >= 0 up to rounding, which can never lower the
-    // minimum (neg of the first hit is <= 0), so only the maximum needs the guard.
-    mx = (t < nvalid && ps > mx) ? ps : mx;
-    mn = (ng < mn) ? ng : mn;
-  }
+  const double below = (incw - cl) * invW;  // one more rounding than a single running sum; ES tolerance is 1e-10
+  mx += below;
+  mn += below;
   if constexpr (LANES == 32) {
     mx = warp_max_exact(mx);
     mn = -warp_max_exact(-mn);
@@ -259,7 +252,7 @@ __device__ __forceinline__ double wks_sets(const uint16_t *__restrict__ s_rank,
   return es;
 }
 
-constexpr int ES_THREADS = 768;  // 24 warps, <= 85 registers each
+constexpr int ES_THREADS = 1024;  // 32 warps at 64 registers: the few spills of the wide classes cost less than the lost occupancy at 768
 template <bool W_SMEM>
 __global__ void __launch_bounds__(ES_THREADS, 1)
 es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sabs, int G,
@@ -311,7 +304,18 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
         else if (mmax <= 8 * 8) es = wks_sets<8, 8, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls);
         else if (mmax <= 8 * 16) es = wks_sets<8, 16, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls);
         else if (mmax <= 8 * 32) es = wks_sets<8, 32, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls);
-        else es = wks_sets<8, 64, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls);
+        else {  // 257 .. 512 members: sixteen lanes per set (32 ranks per lane), the quad as two pairs
+#pragma unroll 1
+          for (int h = 0; h < 2; h++) {
+            const int src = (2 * h + (lane >> 4)) * 8;
+            const int mi = __shfl_sync(0xffffffffu, m, src), zi = __shfl_sync(0xffffffffu, info.z, src);
+            const double igi = __shfl_sync(0xffffffffu, ig, src);
+            const double e2 = wks_sets<16, 32, W_SMEM>(s_rank, wsrc, idx16, zi, mi, G, igi, lane & 15);
+            // hand the result to the set's own eight lanes
+            const double back = __shfl_sync(0xffffffffu, e2, (seg & 1) * 16);
+            if ((seg >> 1) == h) es = back;
+          }
+        }
         if (mine && ls == 0) es_col[info.w] = es;
       } else {  // a quad with a set of 513 .. ES_MAX_SET members: one set at a time on the whole warp
 #pragma unroll 1

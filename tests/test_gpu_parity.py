@@ -158,6 +158,31 @@ def test_duplicates_large_and_edge_sets(ctx, oracle):
     assert np.abs(got[keep] - want[keep]).max() <= ES_TOL
 
 
+def test_wide_sets_and_class_boundaries(ctx, oracle):
+    """every size class of the in-register weighted-KS kernel at its boundaries
+    (8 lanes x {4..32} ranks, 16 x 32, a whole warp x {32, 64}), a set above
+    ES_MAX_SET = 2048 (order-free kernel), quads that mix classes, S % 4 != 0."""
+    G, n, P = 5000, 24, 20
+    rng = np.random.default_rng(11)
+    sizes = [2049, 2048, 1500, 1025, 1024, 700, 513, 512, 300, 257, 256, 255, 129, 128, 127, 65, 64, 63,
+             33, 32, 31, 17, 16, 9, 8, 7, 5, 4, 3, 2, 1, 40, 90, 200, 400, 1000, 12]
+    assert len(sizes) % 4 != 0
+    sets = [rng.choice(G, m, replace=False) + 1 for m in sizes]
+    off, idx = oracle.csr(sets)
+    x, y = synth.two_class(G, n, seed=21)
+    perm = synth.perm_matrix(n, P, seed=4)
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    got = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm)
+    rc, want = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, oracle.ES_WKS)
+    assert rc == 0 and np.abs(got - want).max() <= ES_TOL
+    ctx.set_option("force_generic_es", 1)
+    try:
+        gen = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm)
+    finally:
+        ctx.set_option("force_generic_es", 0)
+    assert np.abs(got - gen).max() <= ES_TOL
+
+
 @pytest.mark.parametrize("es_kind", ["maxmean", "mean"])
 def test_perm_null_mean_maxmean(ctx, oracle, es_kind):
     x, y, perm, off, idx = _case(P=40)
