@@ -450,6 +450,20 @@ __global__ void fill_invgm_kernel(const int4 *__restrict__ set_info, int S, int 
   if (k < S) invgm[k] = 1.0 / (double)(G - (set_info[k].y & 0x7fffffff));
 }
 
+// 1 / (G - m) per set and the uint16 member blocks, both functions of G: once per (gene sets, G)
+static int ensure_set_blocks(fgs_ctx *c, int G) {
+  if (c->invgm_G == G) return FGS_OK;
+  FGS_TRY(c->set_invgm.ensure(c->S));
+  fill_invgm_kernel<<<ceil_div(c->S, 256), 256, 0, c->stream>>>(c->set_info.p, c->S, G, c->set_invgm.p);
+  FGS_TRY(c->set_idx16.ensure((size_t)std::max<long long>(c->idx16_blocks, 1) * 8));
+  build_idx16_kernel<<<ceil_div(c->S, 8), 256, 0, c->stream>>>(c->set_info.p, c->set_idx.p, c->S, G,
+                                                               c->set_idx16.p);
+  c->launches += 2;
+  FGS_CUDA(cudaGetLastError());
+  c->invgm_G = G;
+  return FGS_OK;
+}
+
 int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
                   double *d_es) {
   if (C <= 0 || c->S <= 0) return FGS_OK;
@@ -466,15 +480,7 @@ int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, in
   // rank (2 B) + weight (8 B) per gene on chip, + pad gene, + zero weight slots
   const bool w_smem = Gp * 10 + 16 + 64 <= budget;
   const size_t smem = w_smem ? Gp * 10 + 16 + 64 : Gp * 2 + 16;
-  if (c->invgm_G != G) {  // once per (gene sets, G)
-    FGS_TRY(c->set_invgm.ensure(c->S));
-    fill_invgm_kernel<<<ceil_div(c->S, 256), 256, 0, c->stream>>>(c->set_info.p, c->S, G, c->set_invgm.p);
-    FGS_TRY(c->set_idx16.ensure((size_t)std::max<long long>(c->idx16_blocks, 1) * 8));
-    build_idx16_kernel<<<ceil_div(c->S, 8), 256, 0, c->stream>>>(c->set_info.p, c->set_idx.p, c->S, G,
-                                                                 c->set_idx16.p);
-    c->launches += 2;
-    c->invgm_G = G;
-  }
+  FGS_TRY(ensure_set_blocks(c, G));
   if (w_smem) {
     auto k = es_wks_kernel<true>;
     FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -494,19 +500,25 @@ int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, in
 }
 
 // K5 on chip: persistent CTA per SM, the score column (8 G bytes) staged in shared
-// memory, a warp per set (descending size, round-robin), members gathered from
-// shared memory.  Per member two FP64 adds: sum(v) and sum(|v|); then
+// memory; eight lanes per set, four sets per warp (descending size, quads
+// round-robin over the warps).  A lane takes eight members per 16-byte load of the
+// uint16 member blocks (pads point at a zero slot behind the column).  Per member
+// one or two FP64 adds: sum(v) and, for maxmean, sum(|v|); then
 //   mean    = sum(v) / m                                            (:763)
 //   maxmean : pos = (sum|v| + sum v) / 2m, neg = (sum|v| - sum v) / 2m (:734-735),
 //             es = max(pos, neg), negated iff neg > pos               (:736-737)
 constexpr int ESM_THREADS = 1024;
+template <bool MAXMEAN>
 __global__ void __launch_bounds__(ESM_THREADS, 1)
 es_mean_smem_kernel(const double *__restrict__ scores, int G, long long C,
-                    const int4 *__restrict__ set_info, const int *__restrict__ set_idx, int S,
-                    int es_kind, int abs_flag, double *__restrict__ es_out) {
+                    const int4 *__restrict__ set_info, const uint16_t *__restrict__ idx16, int S,
+                    int abs_flag, double *__restrict__ es_out) {
   extern __shared__ __align__(16) unsigned char smem[];
-  double *s_sc = (double *)smem;
+  double *s_sc = (double *)smem;  // [G + 1]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int seg = lane >> 3, ls = lane & 7;
+  const int nquads = (S + 3) >> 2;
+  if (tid == 0) s_sc[G] = 0.0;  // the pad gene
   for (long long col = blockIdx.x; col < C; col += gridDim.x) {
     __syncthreads();
     const double *sc = scores + (size_t)col * G;
@@ -516,23 +528,39 @@ es_mean_smem_kernel(const double *__restrict__ scores, int G, long long C,
     }
     __syncthreads();
     double *es_col = es_out + (size_t)col * S;
-    for (int k = warp; k < S; k += nwarps) {
-      const int4 info = __ldg(set_info + k);
-      const int off = info.x, m = info.y & 0x7fffffff;  // duplicates are just members here
-      double sv = 0.0, sa = 0.0;
-      for (int j = lane; j < m; j += 32) {
-        const double v = s_sc[__ldg(set_idx + off + j)];
-        sv += v;
-        sa += fabs(v);
-      }
+    for (int q = warp; q < nquads; q += nwarps) {
+      const int k = 4 * q + seg;
+      int4 info = make_int4(0, 0, 0, 0);
+      if (k < S) info = __ldg(set_info + k);
+      const int m = info.y & 0x7fffffff;  // duplicates are just members here
+      const int nblk = (m + 7) >> 3;
+      int nb = (nblk + 7) >> 3;           // 16-byte loads per lane, the same count for the whole warp
+      nb = max(nb, __shfl_xor_sync(0xffffffffu, nb, 8));
+      nb = max(nb, __shfl_xor_sync(0xffffffffu, nb, 16));
+      const uint4 *blocks = (const uint4 *)(idx16 + (size_t)info.z * 8);
+      double sv0 = 0.0, sv1 = 0.0, sa0 = 0.0, sa1 = 0.0;
+      for (int b = 0; b < nb; b++) {
+        const int blk = b * 8 + ls;
+        if (blk < nblk) {
+          const uint4 w = __ldg(blocks + blk);
+          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        sv += __shfl_xor_sync(0xffffffffu, sv, o);
-        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+          for (int i = 0; i < 4; i++) {
+            const double v0 = s_sc[ww[i] & 0xffffu], v1 = s_sc[ww[i] >> 16];
+            sv0 += v0; sv1 += v1;
+            if (MAXMEAN) { sa0 += fabs(v0); sa1 += fabs(v1); }
+          }
+        }
       }
-      if (lane == 0) {
+      double sv = sv0 + sv1, sa = sa0 + sa1;
+#pragma unroll
+      for (int o = 4; o; o >>= 1) {
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        if (MAXMEAN) sa += __shfl_xor_sync(0xffffffffu, sa, o);
+      }
+      if (ls == 0 && k < S) {
         double es;
-        if (es_kind == FGS_ES_MEAN) es = sv / m;
+        if (!MAXMEAN) es = sv / m;
         else {
           const double ps = (sa + sv) / 2 / m, ng = (sa - sv) / 2 / m;
           es = fmax(ps, ng);
@@ -548,13 +576,20 @@ es_mean_smem_kernel(const double *__restrict__ scores, int G, long long C,
 int launch_es_mean(fgs_ctx *c, const double *d_scores, int G, long long C, int es_kind,
                    int abs_flag, double *d_es) {
   if (C <= 0 || c->S <= 0) return FGS_OK;
-  const size_t smem = (size_t)G * 8;
-  if (smem <= (size_t)c->smem_optin) {
+  const size_t smem = ((size_t)G + 2) * 8;
+  if (smem <= (size_t)c->smem_optin && G <= 65534) {
     int grid = c->num_sms;
     if (grid > C) grid = (int)C;
-    FGS_CUDA(cudaFuncSetAttribute(es_mean_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    es_mean_smem_kernel<<<grid, ESM_THREADS, smem, c->stream>>>(d_scores, G, C, c->set_info.p, c->set_idx.p,
-                                                                c->S, es_kind, abs_flag, d_es);
+    FGS_TRY(ensure_set_blocks(c, G));
+    if (es_kind == FGS_ES_MAXMEAN) {
+      auto k = es_mean_smem_kernel<true>;
+      FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, ESM_THREADS, smem, c->stream>>>(d_scores, G, C, c->set_info.p, c->set_idx16.p, c->S, abs_flag, d_es);
+    } else {
+      auto k = es_mean_smem_kernel<false>;
+      FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, ESM_THREADS, smem, c->stream>>>(d_scores, G, C, c->set_info.p, c->set_idx16.p, c->S, abs_flag, d_es);
+    }
   } else {  // column does not fit on chip: gather through L1/L2
     long long units = (long long)c->S * C;
     long long blocks = (units + 7) / 8;
