@@ -6,14 +6,14 @@
 //   neg = pos - w[o];  es = max(pos) > -min(neg) ? max(pos) : min(neg)
 // K5 replaces flexgsea_maxmean_ (:725-741) and flexgsea_mean_ (:755-767).
 //
-// es_wks_kernel: one persistent CTA per SM, a column at a time, a warp per gene
-// set.  The column's rank array (uint16, gene -> rank) and its rank-ordered hit
-// weights (fp64, rank -> |score|^p) are staged in shared memory (10 G bytes).  A
-// warp gathers its set's ranks, sorts them IN REGISTERS with a bitonic network
-// on packed uint16 pairs (no shared-memory scratch, so the warp count is bound
-// by registers only), and then runs the running sum as lane-local sums + one
-// warp scan.  Sets are handled in descending size in five compile-time size
-// classes (32 * {1,2,4,8,16} members).
+// es_wks_kernel: one persistent CTA per SM, a column at a time, EIGHT LANES per
+// gene set (four sets per warp).  The column's rank array (uint16, gene -> rank)
+// and its rank-ordered hit weights (fp64, rank -> |score|^p) are staged in
+// shared memory (10 G bytes).  The lanes of a set gather its ranks, sort them IN
+// REGISTERS with a bitonic network on packed uint16 pairs (no shared-memory
+// scratch), and run the running sum as lane-local sums + one scan of the lane
+// totals.  Sets are handled in descending size in compile-time size classes
+// (8 lanes x {4, 8, 16, 32} ranks, 16 x 32, a whole warp x {32, 64}).
 //
 // Sets with duplicated members (R keeps them; a pad-free distinct-rank sort
 // cannot) or more than ES_MAX_SET members go through es_wks_generic_kernel, an
