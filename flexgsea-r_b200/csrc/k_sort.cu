@@ -199,9 +199,13 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
   constexpr int GS = SORT32_THREADS * IPT;  // padded capacity
   uint32_t *skey = (uint32_t *)smem;
   uint16_t *sidx = (uint16_t *)(skey + GS);
-  // per pass: cnt8[digit][thread] (16 x 1024 bytes) -> pre16[digit][thread] (exclusive prefixes)
+  // per pass: cnt8[digit][thread] (16 rows of 1024 bytes) -> pre16[digit][thread] (exclusive
+  // prefixes).  Rows are 16 bytes longer than their 1024 entries: without the skew the four
+  // lanes that share a counter word's bank collide whenever their digits differ.
+  constexpr int CROW = SORT32_THREADS + 16;  // bytes per cnt8 row
+  constexpr int PROW = SORT32_THREADS + 8;   // uint16 per pre16 row
   unsigned char *cnt8 = (unsigned char *)(sidx + GS + (GS & 1));
-  uint16_t *pre16 = (uint16_t *)(cnt8 + 16 * SORT32_THREADS);
+  uint16_t *pre16 = (uint16_t *)(cnt8 + 16 * CROW);
   __shared__ uint32_t wsum[SORT32_WARPS];
   __shared__ int s_redo;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -234,7 +238,7 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
     // destination = prefix over (digit, thread) + arrival order inside the thread.
     for (int pass = 0; pass < 8; pass++) {
       const int shift = pass * 4;
-      for (int i = tid; i < 16 * SORT32_THREADS / 4; i += SORT32_THREADS) ((uint32_t *)cnt8)[i] = 0;
+      for (int i = tid; i < 16 * CROW / 4; i += SORT32_THREADS) ((uint32_t *)cnt8)[i] = 0;
       uint32_t k[IPT], id2[(IPT + 1) / 2];
 #pragma unroll
       for (int i = 0; i < IPT; i++) k[i] = skey[tid * IPT + i];
@@ -246,10 +250,11 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
       }
       __syncthreads();
 #pragma unroll
-      for (int i = 0; i < IPT; i++) cnt8[((k[i] >> shift) & 15u) * SORT32_THREADS + tid]++;
+      for (int i = 0; i < IPT; i++) cnt8[((k[i] >> shift) & 15u) * CROW + tid]++;
       __syncthreads();
       {  // exclusive scan over (digit-major, thread-minor): 16 byte counters per thread
-        const uint4 w = ((const uint4 *)cnt8)[tid];
+        // thread t scans the 16 entries [16t, 16t + 16) of the digit-major order: row t / 64
+        const uint4 w = ((const uint4 *)cnt8)[(tid >> 6) * (CROW / 16) + (tid & 63)];
         const uint32_t tot = __dp4a(w.x, 0x01010101u, __dp4a(w.y, 0x01010101u,
                               __dp4a(w.z, 0x01010101u, __dp4a(w.w, 0x01010101u, 0u))));
         uint32_t inc = tot;
@@ -270,14 +275,14 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
           outw[j >> 1] = run | ((run + c0) << 16);
           run += c0 + c1;
         }
-        uint4 *dst = (uint4 *)(pre16 + 16 * tid);
+        uint4 *dst = (uint4 *)(pre16 + (tid >> 6) * PROW + 16 * (tid & 63));
         dst[0] = make_uint4(outw[0], outw[1], outw[2], outw[3]);
         dst[1] = make_uint4(outw[4], outw[5], outw[6], outw[7]);
       }
       __syncthreads();
 #pragma unroll
       for (int i = 0; i < IPT; i++) {
-        uint16_t *slot = pre16 + ((k[i] >> shift) & 15u) * SORT32_THREADS + tid;
+        uint16_t *slot = pre16 + ((k[i] >> shift) & 15u) * PROW + tid;
         const uint32_t dst = *slot;
         *slot = (uint16_t)(dst + 1);
         skey[dst] = k[i];
@@ -323,12 +328,26 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
     } else {
       uint16_t *rk = rank16 + (size_t)col * Gp;
       double *sa = sabs + (size_t)col * Gp;
+      // the scores come back from L2 by gene (a gather): several independent loads in
+      // flight per thread, or the phase is one L2 latency per position
+      constexpr int OB = 4;
 #pragma unroll 1
-      for (int i = 0; i < IPT; i++) {
-        const int q = tid + i * SORT32_THREADS;
-        if (q < G) {
-          const uint32_t g = sidx[q];
-          double sq = sc[g];
+      for (int i0 = 0; i0 < IPT; i0 += OB) {
+        uint32_t gq[OB];
+        double sv[OB];
+#pragma unroll
+        for (int u = 0; u < OB; u++) {
+          const int q = tid + (i0 + u) * SORT32_THREADS;
+          gq[u] = (i0 + u < IPT && q < G) ? (uint32_t)sidx[q] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < OB; u++) sv[u] = (gq[u] != 0xffffffffu) ? __ldg(sc + gq[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < OB; u++) {
+          if (gq[u] == 0xffffffffu) continue;
+          const int q = tid + (i0 + u) * SORT32_THREADS;
+          const uint32_t g = gq[u];
+          double sq = sv[u];
           if (abs_flag) sq = fabs(sq);
           double w = fabs(sq);
           if (p_exp != 1.0) w = pow(w, p_exp);
@@ -339,7 +358,7 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
           // could bite) need the exact comparison
           if (tc.list && q + 1 < G && (skey[q + 1] - skey[q] <= 1u || fabs(sq) <= 1e-5)) {
             const uint32_t g2 = sidx[q + 1];
-            double s2 = sc[g2];
+            double s2 = __ldg(sc + g2);
             if (abs_flag) s2 = fabs(s2);
             certify_pair(tc, col, sq, s2, g, g2);
           }
@@ -354,7 +373,7 @@ template <int IPT>
 static int launch_sort32_t(fgs_ctx *c, const double *d_scores, int G, long long C, int abs_flag,
                            double p_exp, uint16_t *d_rank16, double *d_sabs, int *d_redo, int grid,
                            const int *only_cols, const TieCert &tc) {
-  const size_t smem = (size_t)SORT32_THREADS * IPT * 6 + 2 + (size_t)SORT32_THREADS * 16 * 3;
+  const size_t smem = (size_t)SORT32_THREADS * IPT * 6 + 2 + (size_t)(SORT32_THREADS + 16) * 16 * 3;
   auto k = sort_rank32_kernel<IPT>;
   FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k<<<grid, SORT32_THREADS, smem, c->stream>>>(d_scores, G, C, abs_flag, p_exp, d_rank16, d_sabs, d_redo,
