@@ -273,7 +273,7 @@ int fgs_destroy(fgs_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->x.release(); c->xc.release(); c->xtot.release(); c->cert_list.release(); c->cert_ctr.release();
-  c->cert_redo.release(); c->sort_redo.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release(); c->set_idx16.release();
+  c->cert_redo.release(); c->sort_redo.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release(); c->set_idx16.release(); c->sig_lut.release();
   c->set_info.release(); c->set_invgm.release(); c->slow_ids.release(); c->ybin.release();
   c->n1n2.release(); c->lm_H.release(); c->perm.release(); c->labels.release(); c->lm_B.release();
   c->scores.release(); c->rank16.release(); c->sabs.release(); c->sort_keys.release();

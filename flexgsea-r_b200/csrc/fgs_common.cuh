@@ -148,6 +148,7 @@ struct fgs_ctx {
   // significance scratch
   fgs::DevBuf<double> sig_d;
   fgs::DevBuf<long long> sig_i;
+  fgs::DevBuf<int> sig_lut;        // coarse cell index over the sorted NES thresholds (pooled FDR)
 };
 
 namespace fgs {

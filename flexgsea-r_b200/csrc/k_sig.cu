@@ -166,22 +166,42 @@ __global__ void sig_means_kernel(const double *__restrict__ sums_parts, int npar
 
 // ---- ordering helper: stable position of every element within its group ----
 // group(i) in {0 = none, 1, 2}; position among same-group elements by
-// (key ascending, index ascending).  O(S^2) compares, one thread per element.
-__global__ void group_rank_kernel(const double *__restrict__ key, const int *__restrict__ group,
-                                  int n, int *__restrict__ pos, int *__restrict__ group_n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int gi = group[i];
-  const double ki = key[i];
-  int r = 0, tot = 0;
-  for (int j = 0; j < n; j++) {
-    if (group[j] != gi) continue;
-    tot++;
-    const double kj = key[j];
-    r += (kj < ki) || (kj == ki && j < i);
+// (key ascending, index ascending).  S^2 compares, tiled: a block owns 128
+// elements and one chunk of the partners (staged in shared memory), partial
+// positions are added with integer atomics.  pos[] and group_n[] start at zero.
+constexpr int RANK_TI = 128, RANK_TJ = 512;
+__global__ void __launch_bounds__(RANK_TI)
+group_rank_kernel(const double *__restrict__ key, const int *__restrict__ group, int n, int chunk,
+                  int *__restrict__ pos, int *__restrict__ group_n) {
+  __shared__ double sk[RANK_TJ];
+  __shared__ int sg[RANK_TJ];
+  const int i = blockIdx.x * RANK_TI + threadIdx.x;
+  const bool valid = i < n;
+  const int gi = valid ? group[i] : -1;
+  const double ki = valid ? key[i] : 0.0;
+  const int j0 = blockIdx.y * chunk, j1 = min(n, j0 + chunk);
+  int r = 0;
+  for (int jt = j0; jt < j1; jt += RANK_TJ) {
+    const int len = min(RANK_TJ, j1 - jt);
+    __syncthreads();
+    for (int t = threadIdx.x; t < len; t += RANK_TI) { sk[t] = key[jt + t]; sg[t] = group[jt + t]; }
+    __syncthreads();
+    for (int t = 0; t < len; t++) {
+      const double kj = sk[t];
+      r += (sg[t] == gi) && ((kj < ki) || (kj == ki && jt + t < i));
+    }
   }
-  pos[i] = r;
-  if (gi > 0) group_n[gi] = tot;  // same value from every thread of the group
+  if (valid && r) atomicAdd(&pos[i], r);
+  if (valid && blockIdx.y == 0 && gi > 0) atomicAdd(&group_n[gi], 1);
+}
+static void launch_group_rank(fgs_ctx *c, const double *key, const int *group, int n, int *pos, int *gn) {
+  cudaMemsetAsync(pos, 0, (size_t)n * sizeof(int), c->stream);
+  int gy = ceil_div(n, RANK_TJ);
+  if (gy > 32) gy = 32;
+  const int chunk = ceil_div(ceil_div(n, gy), RANK_TJ) * RANK_TJ;
+  gy = ceil_div(n, chunk);
+  dim3 grid(ceil_div(n, RANK_TI), gy);
+  group_rank_kernel<<<grid, RANK_TI, 0, c->stream>>>(key, group, n, chunk, pos, gn);
 }
 
 // thresholds for the pooled-FDR count: group 1 = sets compared with '>'
@@ -208,46 +228,98 @@ __global__ void scatter_sorted_kernel(const double *__restrict__ key, const int 
 //   #{v' > t_j} = sum_{b > j} hist1[b]
 // hist2[b] += 1 where b = #{thresholds2 <= v'}; set at sorted position j gets
 //   #{v' < t_j} = sum_{b <= j} hist2[b]
+// Coarse index over a sorted threshold list: FDR_NC equal cells between its
+// smallest and largest value, lut[c] = #{t < edge(c)} (or <=), so a value's count
+// is bracketed by lut[c], lut[c + 1] and the bisection that finishes the job runs
+// over a cell's population (about one threshold) instead of the whole list.
+constexpr int FDR_NC = 4096;
+__device__ __forceinline__ double lut_edge(double t0, double w, int c) { return __fma_rn((double)c, w, t0); }
+__global__ void fdr_lut_kernel(const double *__restrict__ t, int n, int upper, int *__restrict__ lut) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > FDR_NC) return;
+  if (n <= 0) { lut[c] = 0; return; }
+  if (c == FDR_NC) { lut[c] = n; return; }
+  const double t0 = t[0], w = (t[n - 1] - t[0]) / FDR_NC;
+  const double x = lut_edge(t0, w, c);
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (upper ? (t[mid] <= x) : (t[mid] < x)) lo = mid + 1; else hi = mid;
+  }
+  lut[c] = lo;
+}
+// #{t < v} (UPPER = false) or #{t <= v} (UPPER = true) through the cell index
+template <bool UPPER>
+__device__ __forceinline__ int lut_count(const double *__restrict__ a, int n, const int *__restrict__ lut,
+                                         double t0, double w, double invw, double tmax, double v) {
+  if (n == 0 || v < t0) return 0;
+  if (v > tmax) return n;
+  int lo = 0, hi = n;
+  if (w > 0.0 && w < INFINITY) {  // (a single distinct threshold or an infinite one: plain bisection)
+    int c = min(max((int)((v - t0) * invw), 0), FDR_NC - 1);
+    while (c > 0 && v < lut_edge(t0, w, c)) c--;                  // rounding of the cell guess
+    while (c < FDR_NC - 1 && v >= lut_edge(t0, w, c + 1)) c++;
+    lo = lut[c]; hi = lut[c + 1];
+  }
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (UPPER ? (a[mid] <= v) : (a[mid] < v)) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 template <bool T_SMEM>
 __global__ void __launch_bounds__(256)
 fdr_count_kernel(const double *__restrict__ null, int S, int R, int P, int resp, int abs_flag,
                  const double *__restrict__ mpos, const double *__restrict__ mneg,
                  const double *__restrict__ t1, int n1, const double *__restrict__ t2, int n2,
-                 int chunk_len, unsigned long long *__restrict__ hist1,
+                 const int *__restrict__ lut_g, int chunk_len, unsigned long long *__restrict__ hist1,
                  unsigned long long *__restrict__ hist2, unsigned long long *__restrict__ glob) {
   extern __shared__ __align__(16) unsigned char smem[];
   double *st1 = (double *)smem;
   double *st2 = st1 + (T_SMEM ? n1 : 0);
   unsigned int *h1 = (unsigned int *)(st2 + (T_SMEM ? n2 : 0));
   unsigned int *h2 = h1 + (n1 + 1);
+  int *lut1 = (int *)(h2 + (n2 + 1)), *lut2 = lut1 + (FDR_NC + 1);
   for (int i = threadIdx.x; i < n1 + n2 + 2; i += blockDim.x) h1[i] = 0;
+  for (int i = threadIdx.x; i < 2 * (FDR_NC + 1); i += blockDim.x) lut1[i] = lut_g[i];
   if (T_SMEM) {
     for (int i = threadIdx.x; i < n1; i += blockDim.x) st1[i] = t1[i];
     for (int i = threadIdx.x; i < n2; i += blockDim.x) st2[i] = t2[i];
   }
   __syncthreads();
   const double *a1 = T_SMEM ? st1 : t1, *a2 = T_SMEM ? st2 : t2;
+  const double t10 = n1 > 0 ? t1[0] : 0.0, t1max = n1 > 0 ? t1[n1 - 1] : 0.0, w1 = (t1max - t10) / FDR_NC;
+  const double t20 = n2 > 0 ? t2[0] : 0.0, t2max = n2 > 0 ? t2[n2 - 1] : 0.0, w2 = (t2max - t20) / FDR_NC;
+  const double iw1 = w1 > 0.0 ? 1.0 / w1 : 0.0, iw2 = w2 > 0.0 ? 1.0 / w2 : 0.0;
   const int p0 = blockIdx.y * chunk_len, p1 = min(P, p0 + chunk_len);
+  // a value is searched in ONE threshold list: positive (or abs) values can only
+  // exceed group-1 thresholds, negative ones only undercut group-2 thresholds.
+  // Four permutations in flight per thread hide the global-load latency.
+  constexpr int U = 4;
   unsigned long long gpos = 0, gneg = 0;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
     const double mp = mpos[s], mg = mneg[s];
     const double *base = null + (size_t)s + (size_t)S * resp;
     const size_t stride = (size_t)S * R;
-    for (int p = p0; p < p1; p++) {
-      const double v = base[stride * p];
-      const double nv = abs_flag ? v / mp : v / (v >= 0.0 ? mp : -mg);  // :608-610, :619-621
-      if (nv > 0.0) gpos++;                                             // :503
-      if (nv < 0.0) gneg++;                                             // :504
-      if (isnan(nv)) continue;
-      if (n1 > 0 && nv > a1[0]) {  // #{t1 < nv}: lower bound
-        int lo = 0, hi = n1;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (a1[mid] < nv) lo = mid + 1; else hi = mid; }
-        atomicAdd(&h1[lo], 1u);
-      }
-      if (n2 > 0 && nv < a2[n2 - 1]) {  // #{t2 <= nv}: upper bound
-        int lo = 0, hi = n2;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (a2[mid] <= nv) lo = mid + 1; else hi = mid; }
-        atomicAdd(&h2[lo], 1u);
+    for (int pb = p0; pb < p1; pb += U) {
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) v[u] = (pb + u < p1) ? base[stride * (pb + u)] : nan("");
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const double nv = abs_flag ? v[u] / mp : v[u] / (v[u] >= 0.0 ? mp : -mg);  // :608-610, :619-621
+        if (nv > 0.0) gpos++;                                                      // :503
+        if (nv < 0.0) gneg++;                                                      // :504
+        if (isnan(nv)) continue;
+        // bins that no set's count reads are skipped: they are also the crowded ones
+        if (abs_flag || nv >= 0.0) {
+          const int b = lut_count<false>(a1, n1, lut1, t10, w1, iw1, t1max, nv);   // #{t1 <  nv}
+          if (b > 0) atomicAdd(&h1[b], 1u);
+        } else {
+          const int b = lut_count<true>(a2, n2, lut2, t20, w2, iw2, t2max, nv);    // #{t2 <= nv}
+          if (b < n2) atomicAdd(&h2[b], 1u);
+        }
       }
     }
   }
@@ -261,36 +333,77 @@ fdr_count_kernel(const double *__restrict__ null, int S, int R, int P, int resp,
   if ((threadIdx.x & 31) == 0) { if (gpos) atomicAdd(&glob[0], gpos); if (gneg) atomicAdd(&glob[1], gneg); }
 }
 
-// histogram -> per-set exceedance counts (single CTA; n <= a few 10^4)
-__global__ void hist_to_counts_kernel(const unsigned long long *__restrict__ hist1, const int *id1,
-                                      int n1, const unsigned long long *__restrict__ hist2,
-                                      const int *id2, int n2, int S,
-                                      long long *__restrict__ null_counts) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    unsigned long long run = 0;
-    for (int j = n1 - 1; j >= 0; j--) { run += hist1[j + 1]; null_counts[id1[j]] = (long long)run; }
+// histogram -> per-set exceedance counts: a running sum over the sorted
+// positions (descending for group 1, ascending for group 2); single CTA, every
+// thread owns a contiguous chunk, chunk totals scanned in shared memory
+__device__ void running_sum_scatter(const unsigned long long *__restrict__ hist, int first, int step,
+                                    const int *__restrict__ id, int id_first, int n,
+                                    long long *__restrict__ out, unsigned long long *__restrict__ part) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int per = (n + nt - 1) / nt, t0 = min(n, tid * per), t1 = min(n, t0 + per);
+  unsigned long long sum = 0;
+  for (int t = t0; t < t1; t++) sum += hist[first + step * t];
+  __syncthreads();
+  part[tid] = sum;
+  __syncthreads();
+  unsigned long long run = 0;
+  for (int u = 0; u < tid; u++) run += part[u];
+  for (int t = t0; t < t1; t++) {
+    run += hist[first + step * t];
+    out[id[id_first + step * t]] = (long long)run;
   }
-  if (threadIdx.x == 32 && blockIdx.x == 0) {
-    unsigned long long run = 0;
-    for (int j = 0; j < n2; j++) { run += hist2[j]; null_counts[id2[j]] = (long long)run; }
-  }
+}
+__global__ void __launch_bounds__(256)
+hist_to_counts_kernel(const unsigned long long *__restrict__ hist1, const int *id1, int n1,
+                      const unsigned long long *__restrict__ hist2, const int *id2, int n2, int S,
+                      long long *__restrict__ null_counts) {
+  __shared__ unsigned long long part[256];
+  // group 1: position j = n1-1 .. 0 accumulates hist1[j + 1]
+  running_sum_scatter(hist1, n1, -1, id1, n1 - 1, n1, null_counts, part);
+  // group 2: position j = 0 .. n2-1 accumulates hist2[j]
+  running_sum_scatter(hist2, 0, 1, id2, 0, n2, null_counts, part);
 }
 
 // ---- finish: raw FDR + monotone adjustment ----------------------------------
+// a_i = #{nes > nes_i} (positive side, :519) or #{nes < nes_i} (:523) over all sets,
+// and the sign counts cp = #{nes > 0}, cn = #{nes < 0} (:501-502): S^2 compares, tiled
+// like group_rank_kernel.  acount[] and sign_n[0..1] start at zero.
+__global__ void __launch_bounds__(RANK_TI)
+fdr_exceed_kernel(const double *__restrict__ nes, int S, int abs_flag, int chunk,
+                  int *__restrict__ acount, int *__restrict__ sign_n) {
+  __shared__ double sk[RANK_TJ];
+  const int i = blockIdx.x * RANK_TI + threadIdx.x;
+  const bool valid = i < S;
+  const double v = valid ? nes[i] : 0.0;
+  const bool pos_side = (v >= 0.0) || abs_flag;
+  const int j0 = blockIdx.y * chunk, j1 = min(S, j0 + chunk);
+  int a = 0;
+  for (int jt = j0; jt < j1; jt += RANK_TJ) {
+    const int len = min(RANK_TJ, j1 - jt);
+    __syncthreads();
+    for (int t = threadIdx.x; t < len; t += RANK_TI) sk[t] = nes[jt + t];
+    __syncthreads();
+    for (int t = 0; t < len; t++) {
+      const double w = sk[t];
+      a += pos_side ? (w > v) : (w < v);
+    }
+  }
+  if (valid && a) atomicAdd(&acount[i], a);
+  if (valid && blockIdx.y == 0) {
+    if (v > 0.0) atomicAdd(&sign_n[0], 1);
+    if (v < 0.0) atomicAdd(&sign_n[1], 1);
+  }
+}
 __global__ void fdr_raw_kernel(const double *__restrict__ nes, const long long *__restrict__ null_counts,
-                               const long long *__restrict__ glob, int S, int abs_flag,
+                               const long long *__restrict__ glob, const int *__restrict__ acount,
+                               const int *__restrict__ sign_n, int S, int abs_flag,
                                double *__restrict__ fdr, long long *__restrict__ fdr_counts,
                                long long *__restrict__ glob_counts, int *__restrict__ adj_group) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S) return;
   const double v = nes[i];
-  long long cp = 0, cn = 0, a = 0;
+  const long long cp = sign_n[0], cn = sign_n[1], a = acount[i];
   const bool pos_side = (v >= 0.0) || abs_flag;
-  for (int j = 0; j < S; j++) {
-    const double w = nes[j];
-    cp += w > 0.0; cn += w < 0.0;                     // :501-502
-    a += pos_side ? (w > v) : (w < v);                // :519, :523
-  }
   const long long b = null_counts[i];
   double rel, rel_null;
   if (pos_side) { rel = (double)(a + 1) / (double)cp; rel_null = (double)(b + 1) / (double)glob[0]; }
@@ -385,7 +498,7 @@ int launch_sig_stage2(fgs_ctx *c, const double *d_null, int S, int R, int P, int
   FGS_CUDA(cudaMemsetAsync(d_null_counts, 0, (size_t)S * sizeof(long long), c->stream));
   const int nb = ceil_div(S, 128);
   fdr_groups_kernel<<<nb, 128, 0, c->stream>>>(d_nes, S, abs_flag, group);
-  group_rank_kernel<<<nb, 128, 0, c->stream>>>(d_nes, group, S, pos, gn);
+  launch_group_rank(c, d_nes, group, S, pos, gn);
   scatter_sorted_kernel<<<nb, 128, 0, c->stream>>>(d_nes, group, pos, S, t1, id1, t2, id2);
   c->launches += 3;
   FGS_CUDA(cudaGetLastError());
@@ -399,24 +512,29 @@ int launch_sig_stage2(fgs_ctx *c, const double *d_null, int S, int R, int P, int
     if (gy > P) gy = P;
     int chunk_len = (P + gy - 1) / gy;
     gy = (P + chunk_len - 1) / chunk_len;
-    size_t smem_t = (size_t)(n1 + n2) * 8 + (size_t)(n1 + n2 + 2) * 4;
-    size_t smem_h = (size_t)(n1 + n2 + 2) * 4;
+    FGS_TRY(c->sig_lut.ensure((size_t)2 * (FDR_NC + 1)));
+    fdr_lut_kernel<<<ceil_div(FDR_NC + 1, 256), 256, 0, c->stream>>>(t1, n1, 0, c->sig_lut.p);
+    fdr_lut_kernel<<<ceil_div(FDR_NC + 1, 256), 256, 0, c->stream>>>(t2, n2, 1, c->sig_lut.p + FDR_NC + 1);
+    c->launches += 2;
+    const size_t smem_lut = (size_t)2 * (FDR_NC + 1) * 4;
+    size_t smem_t = (size_t)(n1 + n2) * 8 + (size_t)(n1 + n2 + 2) * 4 + smem_lut;
+    size_t smem_h = (size_t)(n1 + n2 + 2) * 4 + smem_lut;
     dim3 grid(gx, gy);
     if (smem_t <= (size_t)c->smem_optin / 2) {
       auto k = fdr_count_kernel<true>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
       k<<<grid, 256, smem_t, c->stream>>>(d_null, S, R, P, response, abs_flag, d_mpos, d_mneg, t1, n1,
-                                          t2, n2, chunk_len, h1, h2, (unsigned long long *)d_glob);
+                                          t2, n2, c->sig_lut.p, chunk_len, h1, h2, (unsigned long long *)d_glob);
     } else {
       auto k = fdr_count_kernel<false>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
       k<<<grid, 256, smem_h, c->stream>>>(d_null, S, R, P, response, abs_flag, d_mpos, d_mneg, t1, n1,
-                                          t2, n2, chunk_len, h1, h2, (unsigned long long *)d_glob);
+                                          t2, n2, c->sig_lut.p, chunk_len, h1, h2, (unsigned long long *)d_glob);
     }
     c->launches++;
     FGS_CUDA(cudaGetLastError());
   }
-  hist_to_counts_kernel<<<1, 64, 0, c->stream>>>(h1, id1, n1, h2, id2, n2, S, d_null_counts);
+  hist_to_counts_kernel<<<1, 256, 0, c->stream>>>(h1, id1, n1, h2, id2, n2, S, d_null_counts);
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   return FGS_OK;
@@ -430,12 +548,22 @@ int launch_sig_finish(fgs_ctx *c, const double *d_nes, const long long *d_null_c
   FGS_TRY(c->sig_d.ensure((size_t)2 * S + 2));
   double *key = c->sig_d.p;
   const int nb = ceil_div(S, 128);
-  FGS_CUDA(cudaMemsetAsync(gn, 0, 4 * sizeof(int), c->stream));
-  fdr_raw_kernel<<<nb, 128, 0, c->stream>>>(d_nes, d_null_counts, d_glob, S, abs_flag, d_fdr,
+  int *acount = order + S;  // the second half of the order scratch
+  FGS_CUDA(cudaMemsetAsync(gn, 0, 8 * sizeof(int), c->stream));
+  FGS_CUDA(cudaMemsetAsync(acount, 0, (size_t)S * sizeof(int), c->stream));
+  {
+    int gy = ceil_div(S, RANK_TJ);
+    if (gy > 32) gy = 32;
+    const int chunk = ceil_div(ceil_div(S, gy), RANK_TJ) * RANK_TJ;
+    gy = ceil_div(S, chunk);
+    dim3 grid(ceil_div(S, RANK_TI), gy);
+    fdr_exceed_kernel<<<grid, RANK_TI, 0, c->stream>>>(d_nes, S, abs_flag, chunk, acount, gn + 4);
+  }
+  fdr_raw_kernel<<<nb, 128, 0, c->stream>>>(d_nes, d_null_counts, d_glob, acount, gn + 4, S, abs_flag, d_fdr,
                                             d_fdr_counts, d_glob_counts, group);
   negate_group2_kernel<<<nb, 128, 0, c->stream>>>(d_nes, group, S, key);
-  group_rank_kernel<<<nb, 128, 0, c->stream>>>(key, group, S, pos, gn);
-  c->launches += 3;
+  launch_group_rank(c, key, group, S, pos, gn);
+  c->launches += 4;
   FGS_CUDA(cudaGetLastError());
   int h_gn[4];
   FGS_CUDA(cudaMemcpyAsync(h_gn, gn, sizeof(h_gn), cudaMemcpyDeviceToHost, c->stream));
@@ -456,8 +584,9 @@ int launch_bh(fgs_ctx *c, const double *d_p, int S, double *d_fdr) {
   FGS_TRY(c->sig_d.ensure((size_t)2 * S + 2));
   double *key = c->sig_d.p;
   const int nb = ceil_div(S, 128);
+  FGS_CUDA(cudaMemsetAsync(gn, 0, 8 * sizeof(int), c->stream));
   bh_prepare_kernel<<<nb, 128, 0, c->stream>>>(d_p, S, key, group);
-  group_rank_kernel<<<nb, 128, 0, c->stream>>>(key, group, S, pos, gn);
+  launch_group_rank(c, key, group, S, pos, gn);
   bh_scale_kernel<<<nb, 128, 0, c->stream>>>(d_p, pos, S, d_fdr);
   ordered_prefix_min_kernel<<<1, 1024, 0, c->stream>>>(d_fdr, group, pos, S, 1, S, INFINITY, order);
   clamp1_kernel<<<nb, 128, 0, c->stream>>>(d_fdr, S);
