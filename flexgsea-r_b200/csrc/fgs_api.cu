@@ -273,7 +273,10 @@ int fgs_destroy(fgs_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->x.release(); c->xc.release(); c->xtot.release(); c->cert_list.release(); c->cert_ctr.release();
-  c->cert_redo.release(); c->sort_redo.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release(); c->set_idx16.release(); c->sig_lut.release();
+  c->cert_redo.release(); c->sort_redo.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release(); c->set_idx16.release(); c->sig_lut.release(); c->set_slow.release();
+  for (auto &b : c->api_d) b.release();
+  for (auto &b : c->api_i) b.release();
+  c->api_l.release();
   c->set_info.release(); c->set_invgm.release(); c->slow_ids.release(); c->ybin.release();
   c->n1n2.release(); c->lm_H.release(); c->perm.release(); c->labels.release(); c->lm_B.release();
   c->scores.release(); c->rank16.release(); c->sabs.release(); c->sort_keys.release();
@@ -329,36 +332,34 @@ int fgs_set_gene_sets(fgs_ctx *c, const int *offsets, const int *index, int n_se
   if (!c || !offsets || n_sets <= 0) { set_error("fgs_set_gene_sets: bad argument"); return FGS_ERR_ARG; }
   FGS_TRY(use_device(c));
   if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return FGS_ERR_ARG; }
+  for (int s = 0; s < n_sets; s++)
+    if (offsets[s + 1] < offsets[s]) { set_error("offsets not monotone at set %d", s); return FGS_ERR_ARG; }
   const long long nnz = offsets[n_sets];
   if (nnz > 0 && !index) { set_error("fgs_set_gene_sets: index is NULL"); return FGS_ERR_ARG; }
-  std::vector<int> idx0((size_t)nnz), order(n_sets);
-  std::vector<unsigned char> slow(n_sets, 0);
-  std::vector<int> slow_ids, tmp;
-  int max_idx = 0;
-  for (int s = 0; s < n_sets; s++) {
-    const int a = offsets[s], b = offsets[s + 1];
-    if (b < a) { set_error("offsets not monotone at set %d", s); return FGS_ERR_ARG; }
-    for (int j = a; j < b; j++) {
-      if (index[j] < 1) { set_error("gene index %d < 1 in set %d (NA from match()?)", index[j], s); return FGS_ERR_ARG; }
-      idx0[j] = index[j] - 1;
-      max_idx = std::max(max_idx, index[j]);
-    }
-    // duplicate detection in O(m): stamp[gene] = last set that held it
-    bool dup = false;
-    for (int j = a; j < b; j++) {
-      const size_t g = (size_t)idx0[j];
-      if (g >= tmp.size()) tmp.resize(std::max(g + 1, tmp.size() * 2), -1);
-      if (tmp[g] == s) dup = true;
-      tmp[g] = s;
-    }
-    if (dup || (b - a) > fgs::ES_MAX_SET) { slow[s] = 1; slow_ids.push_back(s); }
-    order[s] = s;
+  // The member lists are checked and made 0-based on the device (launch_prep_sets):
+  // the host only orders the sets by size.
+  FGS_TRY(c->set_off.ensure((size_t)n_sets + 1));
+  FGS_TRY(c->set_idx.ensure((size_t)std::max<long long>(nnz, 1)));
+  FGS_TRY(c->set_info.ensure(n_sets));
+  FGS_TRY(c->set_slow.ensure((size_t)n_sets + 16));
+  FGS_TRY(h2d(c, c->set_off.p, offsets, (size_t)n_sets + 1));
+  FGS_TRY(h2d(c, c->set_idx.p, index, (size_t)nnz));  // raw 1-based ids, rewritten in place
+  int status[2];
+  std::vector<unsigned char> slow(n_sets);
+  FGS_TRY(launch_prep_sets(c, n_sets, status, slow.data()));  // synchronises
+  if (status[0] < n_sets) {
+    const int s = status[0];
+    int bad = 0;
+    for (int j = offsets[s]; j < offsets[s + 1]; j++) if (index[j] < 1) { bad = index[j]; break; }
+    set_error("gene index %d < 1 in set %d (NA from match()?)", bad, s);
+    c->S = 0;
+    return FGS_ERR_ARG;
   }
+  std::vector<int> order(n_sets), slow_ids;
+  for (int s = 0; s < n_sets; s++) { order[s] = s; if (slow[s]) slow_ids.push_back(s); }
   std::stable_sort(order.begin(), order.end(), [&](int p, int q) {
     return (offsets[p + 1] - offsets[p]) > (offsets[q + 1] - offsets[q]);
   });
-  FGS_TRY(c->set_off.ensure((size_t)n_sets + 1));
-  FGS_TRY(c->set_idx.ensure((size_t)std::max<long long>(nnz, 1)));
   std::vector<int4> info(n_sets);
   long long blocks = 0;  // members as uint16 in 16-byte blocks, processing order (launch_es_wks fills them)
   for (int k = 0; k < n_sets; k++) {
@@ -367,14 +368,11 @@ int fgs_set_gene_sets(fgs_ctx *c, const int *offsets, const int *index, int n_se
     blocks += (m + 7) / 8;
   }
   c->idx16_blocks = blocks;
-  FGS_TRY(c->set_info.ensure(n_sets));
   FGS_TRY(c->slow_ids.ensure(std::max<size_t>(slow_ids.size(), 1)));
-  FGS_TRY(h2d(c, c->set_off.p, offsets, (size_t)n_sets + 1));
-  FGS_TRY(h2d(c, c->set_idx.p, idx0.data(), (size_t)nnz));
   FGS_TRY(h2d(c, c->set_info.p, info.data(), (size_t)n_sets));
   FGS_TRY(h2d(c, c->slow_ids.p, slow_ids.data(), slow_ids.size()));
   FGS_TRY(sync(c));
-  c->S = n_sets; c->nnz = nnz; c->max_set = max_idx; c->n_slow = (int)slow_ids.size();
+  c->S = n_sets; c->nnz = nnz; c->max_set = status[1]; c->n_slow = (int)slow_ids.size();
   c->invgm_G = -1;
   c->h_set_off.assign(offsets, offsets + n_sets + 1);
   return FGS_OK;
@@ -704,7 +702,9 @@ int fgs_observed_es(fgs_ctx *c, int es_kind, double p_exp, const double *scores,
   FGS_TRY(flags_reset(c, R));
   FGS_TRY(h2d(c, c->scores.p, scores, (size_t)G * R));
   FGS_TRY(launch_check_finite(c, c->scores.p, (long long)G * R, G, c->flags.p));
-  DevBuf<double> d_es, d_mea, d_lep, d_pos, d_neg; DevBuf<int> d_at, d_lf, d_lc;
+  // grow-only scratch of the context (cudaMalloc / cudaFree per call cost more than the kernels)
+  DevBuf<double> &d_es = c->api_d[0], &d_mea = c->api_d[1], &d_lep = c->api_d[2], &d_pos = c->api_d[3], &d_neg = c->api_d[4];
+  DevBuf<int> &d_at = c->api_i[0], &d_lf = c->api_i[1], &d_lc = c->api_i[2];
   auto body = [&]() -> int {
     FGS_TRY(d_es.ensure(SR));
     if (es_kind == FGS_ES_WEIGHTED_KS) {
@@ -729,8 +729,6 @@ int fgs_observed_es(fgs_ctx *c, int es_kind, double p_exp, const double *scores,
   };
   int rc = body();
   cudaStreamSynchronize(c->stream);
-  d_es.release(); d_mea.release(); d_lep.release(); d_pos.release(); d_neg.release();
-  d_at.release(); d_lf.release(); d_lc.release();
   return rc;
 }
 
@@ -748,7 +746,7 @@ int fgs_sig_stage1(fgs_ctx *c, const double *es, int response, int split_p, int 
   FGS_TRY(use_device(c));
   FGS_TRY(sig_check(c, response));
   const int S = c->null_S;
-  DevBuf<double> d_es, d_sums; DevBuf<long long> d_counts;
+  DevBuf<double> &d_es = c->api_d[0], &d_sums = c->api_d[1]; DevBuf<long long> &d_counts = c->api_l;
   auto body = [&]() -> int {
     FGS_TRY(d_es.ensure(S)); FGS_TRY(d_sums.ensure((size_t)S * 4)); FGS_TRY(d_counts.ensure((size_t)S * 6));
     FGS_TRY(h2d(c, d_es.p, es, S));
@@ -758,7 +756,6 @@ int fgs_sig_stage1(fgs_ctx *c, const double *es, int response, int split_p, int 
     return sync(c);
   };
   int rc = body();
-  d_es.release(); d_sums.release(); d_counts.release();
   return rc;
 }
 
@@ -770,7 +767,7 @@ int fgs_sig_stage2(fgs_ctx *c, const double *es, int response, int split_p, int 
   FGS_TRY(use_device(c));
   FGS_TRY(sig_check(c, response));
   const int S = c->null_S;
-  DevBuf<double> d; DevBuf<long long> di;
+  DevBuf<double> &d = c->api_d[0]; DevBuf<long long> &di = c->api_l;
   auto body = [&]() -> int {
     // doubles: es[S] parts[n_parts*S*4] p ph pl mpos mneg nes fwer fdr [8S]
     FGS_TRY(d.ensure((size_t)S * (9 + 4 * (size_t)n_parts)));
@@ -794,7 +791,6 @@ int fgs_sig_stage2(fgs_ctx *c, const double *es, int response, int split_p, int 
     return sync(c);
   };
   int rc = body();
-  d.release(); di.release();
   return rc;
 }
 
@@ -804,7 +800,7 @@ int fgs_sig_finish(fgs_ctx *c, const double *nes, const long long *null_counts,
   if (!c || !nes || !null_counts || !glob || n_sets <= 0) return FGS_ERR_ARG;
   FGS_TRY(use_device(c));
   const int S = n_sets;
-  DevBuf<double> d; DevBuf<long long> di;
+  DevBuf<double> &d = c->api_d[0]; DevBuf<long long> &di = c->api_l;
   auto body = [&]() -> int {
     FGS_TRY(d.ensure((size_t)S * 2)); FGS_TRY(di.ensure((size_t)S * 3 + 8));
     double *d_nes = d.p, *d_fdr = d_nes + S;
@@ -816,7 +812,6 @@ int fgs_sig_finish(fgs_ctx *c, const double *nes, const long long *null_counts,
     return sync(c);
   };
   int rc = body();
-  d.release(); di.release();
   return rc;
 }
 
@@ -828,7 +823,7 @@ int fgs_calc_sig(fgs_ctx *c, const double *es, int response, int split_p, int ca
   FGS_TRY(sig_check(c, response));
   const int S = c->null_S, P = c->null_P;
   if (P == 0) return FGS_OK;  // R/flexgsea.R:575-577
-  DevBuf<double> d; DevBuf<long long> di;
+  DevBuf<double> &d = c->api_d[0]; DevBuf<long long> &di = c->api_l;
   auto body = [&]() -> int {
     // doubles: es sums[4S] p ph pl mpos mneg nes fwer fdr
     FGS_TRY(d.ensure((size_t)S * 13)); FGS_TRY(di.ensure((size_t)S * 9 + 8));
@@ -864,7 +859,6 @@ int fgs_calc_sig(fgs_ctx *c, const double *es, int response, int split_p, int ca
     return sync(c);
   };
   int rc = body();
-  d.release(); di.release();
   return rc;
 }
 

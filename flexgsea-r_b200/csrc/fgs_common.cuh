@@ -105,6 +105,7 @@ struct fgs_ctx {
   // "slow" = duplicated members or more than ES_MAX_SET members (order-free kernel)
   fgs::DevBuf<int4> set_info;
   fgs::DevBuf<double> set_invgm;   // [S] 1 / (G - m), processing order
+  fgs::DevBuf<unsigned char> set_slow;  // [S] flags + [16] status bytes of launch_prep_sets
   fgs::DevBuf<uint16_t> set_idx16; // members as uint16, processing order, 8-blocks padded with gene G
   long long idx16_blocks = 0;
   int invgm_G = -1;                // G set_invgm / set_idx16 were filled for (-1: stale)
@@ -148,6 +149,9 @@ struct fgs_ctx {
   // significance scratch
   fgs::DevBuf<double> sig_d;
   fgs::DevBuf<long long> sig_i;
+  fgs::DevBuf<double> api_d[5];    // grow-only scratch of the observed / significance entry points
+  fgs::DevBuf<int> api_i[3];
+  fgs::DevBuf<long long> api_l;
   fgs::DevBuf<int> sig_lut;        // coarse cell index over the sorted NES thresholds (pooled FDR)
 };
 
@@ -185,6 +189,7 @@ int launch_s2n_exact_entries(fgs_ctx *c, const double *d_x, int n, int G, const 
                              const int *d_n1n2, int R, const int2 *d_list, const int *d_count, int cap,
                              double *d_scores, int *d_flags);
 // K4 / K5
+int launch_prep_sets(fgs_ctx *c, int S, int *h_status, unsigned char *h_slow);
 int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
                   double *d_es /* [C][S] */);
 int launch_es_wks_generic(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G,

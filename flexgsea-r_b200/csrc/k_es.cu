@@ -450,6 +450,53 @@ __global__ void fill_invgm_kernel(const int4 *__restrict__ set_info, int S, int 
   if (k < S) invgm[k] = 1.0 / (double)(G - (set_info[k].y & 0x7fffffff));
 }
 
+// Gene-set intake (fgs_set_gene_sets): a warp per set turns the 1-based ids that
+// match(set, gene.names) produced into 0-based ones in place, reports the first
+// set holding an id < 1 and the largest id, and flags the sets the in-register
+// kernel cannot take: duplicated members (found by comparing every member with
+// its predecessors, O(m^2 / 32)) or more than ES_MAX_SET members.
+__global__ void __launch_bounds__(256)
+prep_sets_kernel(const int *__restrict__ set_off, int *__restrict__ set_idx, int S,
+                 unsigned char *__restrict__ slow, int *__restrict__ status) {
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (s >= S) return;
+  const int a = set_off[s], m = set_off[s + 1] - a;
+  int vmax = 0, bad = 0, dup = 0;
+  for (int j = lane; j < m; j += 32) {
+    const int v = set_idx[a + j];
+    bad |= v < 1;
+    vmax = max(vmax, v);
+  }
+  if (m <= ES_MAX_SET) {
+    for (int j = lane; j < m; j += 32) {
+      const int v = set_idx[a + j];
+      for (int t = 0; t < j; t++) dup |= set_idx[a + t] == v;
+    }
+  }
+  __syncwarp();
+  for (int j = lane; j < m; j += 32) set_idx[a + j] -= 1;
+  bad = __any_sync(0xffffffffu, bad);
+  dup = __any_sync(0xffffffffu, dup);
+  vmax = __reduce_max_sync(0xffffffffu, vmax);
+  if (lane == 0) {
+    slow[s] = (unsigned char)(dup || m > ES_MAX_SET);
+    if (bad) atomicMin(&status[0], s);
+    atomicMax(&status[1], vmax);
+  }
+}
+int launch_prep_sets(fgs_ctx *c, int S, int *h_status, unsigned char *h_slow) {
+  int *status = (int *)(c->set_slow.p + (((size_t)S + 7) & ~(size_t)7));
+  const int init[2] = {S, 0};
+  FGS_CUDA(cudaMemcpyAsync(status, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  prep_sets_kernel<<<ceil_div(S, 8), 256, 0, c->stream>>>(c->set_off.p, c->set_idx.p, S, c->set_slow.p, status);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  FGS_CUDA(cudaMemcpyAsync(h_status, status, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  FGS_CUDA(cudaMemcpyAsync(h_slow, c->set_slow.p, (size_t)S, cudaMemcpyDeviceToHost, c->stream));
+  FGS_CUDA(cudaStreamSynchronize(c->stream));
+  return FGS_OK;
+}
+
 // 1 / (G - m) per set and the uint16 member blocks, both functions of G: once per (gene sets, G)
 static int ensure_set_blocks(fgs_ctx *c, int G) {
   if (c->invgm_G == G) return FGS_OK;
