@@ -329,7 +329,8 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
       uint16_t *rk = rank16 + (size_t)col * Gp;
       double *sa = sabs + (size_t)col * Gp;
       // the scores come back from L2 by gene (a gather): several independent loads in
-      // flight per thread, or the phase is one L2 latency per position
+      // flight per thread.  (Streaming the column through shared memory in coalesced
+      // slices and gathering on chip was measured: no faster.)
       constexpr int OB = 4;
 #pragma unroll 1
       for (int i0 = 0; i0 < IPT; i0 += OB) {
@@ -352,7 +353,6 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
           double w = fabs(sq);
           if (p_exp != 1.0) w = pow(w, p_exp);
           sa[q] = w;
-          rk[g] = (uint16_t)(q + 1);
           // a neighbour whose 32-bit key differs by >= 2 is > 1e-6 away in relative
           // terms; only closer keys (or scores so small that the absolute tolerance
           // could bite) need the exact comparison
@@ -364,6 +364,17 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
           }
         }
       }
+      // ranks: scattered by gene into the (now free) key array, then written out as
+      // one coalesced row -- a 2-byte store per gene straight to L2 is a transaction each
+      __syncthreads();
+      uint16_t *rks = (uint16_t *)skey;
+#pragma unroll 1
+      for (int i = 0; i < IPT; i++) {
+        const int q = tid + i * SORT32_THREADS;
+        if (q < G) rks[sidx[q]] = (uint16_t)(q + 1);
+      }
+      __syncthreads();
+      for (int i = tid; i < (int)(Gp / 8); i += SORT32_THREADS) ((uint4 *)rk)[i] = ((const uint4 *)rks)[i];
     }
     __syncthreads();
   }
