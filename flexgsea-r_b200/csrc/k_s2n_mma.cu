@@ -59,7 +59,7 @@ int launch_center(fgs_ctx *c, const double *d_x, int n, int G, double *d_xc, dou
   return FGS_OK;
 }
 
-constexpr int SM_BG = 32, SM_BN = 64, SM_BK = 16, SM_PAD = 4;  // genes x columns x samples per tile
+constexpr int SM_BG = 32, SM_BN = 128, SM_BK = 16, SM_PAD = 4;  // genes x columns x samples per tile
 constexpr double S2N_CANCEL_LIMIT = 16.0;
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
@@ -75,59 +75,95 @@ __device__ __forceinline__ void push_entry(int2 *__restrict__ list, int *__restr
   else atomicOr(overflow, 16);  // the caller reruns the block bit-faithfully
 }
 
-// CTA tile: 32 genes x 64 columns; 8 warps = 2 (gene halves of 16) x 4 (column
-// quarters of 16).  A warp holds, for its 16 genes and 16 columns, the S1 and the
+// 8-byte asynchronous copy global -> shared, zero-filled when `ok` is false
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src, bool ok) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int nbytes = ok ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(d), "l"(src), "r"(nbytes));
+}
+
+// CTA tile: 32 genes x 128 columns; 8 warps = 2 (gene halves of 16) x 4 (column
+// groups of 32).  A warp holds, for its 16 genes and 32 columns, the S1 and the
 // Q1 accumulators: m-tiles {0,1} multiply xc, m-tiles {2,3} multiply xc^2 (the
 // square is taken on the A fragment, so xc is staged once).
+//   A (centred expression): 32 x 16 tiles, double-buffered in shared memory by
+//     cp.async, so the next tile lands while the tensor pipe works on this one.
+//   B (0/1 class-1 indicator): never materialised.  A lane needs it for four
+//     fixed columns only; it keeps those columns' label words in registers and
+//     builds the 1.0 / 0.0 operand from a bit (two integer instructions).
 __global__ void __launch_bounds__(256)
 s2n_mma_kernel(const double *__restrict__ xc, const double *__restrict__ tot, int n, int G,
                const uint32_t *__restrict__ labels, const int *__restrict__ n1n2, int R, long long C,
                int W, double *__restrict__ scores, int2 *__restrict__ list, int *__restrict__ count,
                int cap, int *__restrict__ overflow) {
-  __shared__ double As[SM_BG][SM_BK + SM_PAD];
-  __shared__ double Bs[SM_BN][SM_BK + SM_PAD];
+  __shared__ __align__(16) double As[2][SM_BG][SM_BK + SM_PAD];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g0 = blockIdx.x * SM_BG;
   const long long c0 = (long long)blockIdx.y * SM_BN;
-  const int wg = (warp & 1) * 16, wn = (warp >> 1) * 16;
+  const int wg = (warp & 1) * 16, wn = (warp >> 1) * 32;
   const int grp = lane >> 2, tig = lane & 3;
-  double acc[4][2][2];
+  double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
-    for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  for (int k0 = 0; k0 < n; k0 += SM_BK) {
-    for (int e = tid; e < SM_BG * SM_BK; e += 256) {
-      const int r = e / SM_BK, k = e % SM_BK, g = g0 + r;
-      As[r][k] = (g < G && k0 + k < n) ? xc[(size_t)g * n + k0 + k] : 0.0;
+  // this lane's B columns (operand fragment: column = grp of each 8-column tile)
+  const uint32_t *lab[4];
+  bool colok[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const long long col = c0 + wn + j * 8 + grp;
+    colok[j] = col < C;
+    lab[j] = labels + (size_t)(colok[j] ? col : 0) * 2 * W;
+  }
+  // staging assignment: thread -> (gene row, two samples) of the 32 x 16 tile
+  const int sr = tid >> 3, sk = (tid & 7) * 2;
+  const bool rowok = g0 + sr < G;
+  const double *srow = xc + (size_t)(rowok ? g0 + sr : 0) * n;
+  auto stage = [&](int buf, int k0) {
+    cp_async8(&As[buf][sr][sk], srow + k0 + sk, rowok && k0 + sk < n);
+    cp_async8(&As[buf][sr][sk + 1], srow + k0 + sk + 1, rowok && k0 + sk + 1 < n);
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+
+  const int ntile = (n + SM_BK - 1) / SM_BK;
+  stage(0, 0);
+  uint32_t wcur[4] = {0u, 0u, 0u, 0u};
+  for (int t = 0; t < ntile; t++) {
+    const int k0 = t * SM_BK;
+    if ((t & 1) == 0) {  // a 32-sample label word covers two 16-sample tiles
+#pragma unroll
+      for (int j = 0; j < 4; j++) wcur[j] = colok[j] ? __ldg(lab[j] + (k0 >> 5)) : 0u;
     }
-    for (int e = tid; e < SM_BN * SM_BK; e += 256) {
-      const int r = e / SM_BK, k = e % SM_BK, i = k0 + k;
-      const long long col = c0 + r;
-      double z = 0.0;
-      if (col < C && i < n) z = (double)((__ldg(labels + (size_t)col * 2 * W + (i >> 5)) >> (i & 31)) & 1u);
-      Bs[r][k] = z;
+    if (t + 1 < ntile) {
+      stage((t + 1) & 1, k0 + SM_BK);
+      asm volatile("cp.async.wait_group 1;\n" ::);
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::);
     }
     __syncthreads();
+    const int buf = t & 1;
+    const int bit0 = (k0 & 31) + tig;
 #pragma unroll
     for (int kk = 0; kk < SM_BK; kk += 4) {
-      double a[2], b[2];
+      double a[2], b[4];
 #pragma unroll
-      for (int i = 0; i < 2; i++) a[i] = As[wg + i * 8 + grp][kk + tig];
+      for (int i = 0; i < 2; i++) a[i] = As[buf][wg + i * 8 + grp][kk + tig];
 #pragma unroll
-      for (int j = 0; j < 2; j++) b[j] = Bs[wn + j * 8 + grp][kk + tig];
+      for (int j = 0; j < 4; j++)  // 1.0 or 0.0 straight from the label bit (samples >= n have bit 0)
+        b[j] = __hiloint2double((int)(((wcur[j] >> (bit0 + kk)) & 1u) * 0x3ff00000u), 0);
 #pragma unroll
       for (int i = 0; i < 2; i++) {
         const double a2 = a[i] * a[i];
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
+        for (int j = 0; j < 4; j++) {
           dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
           dmma884(acc[i + 2][j][0], acc[i + 2][j][1], a2, b[j]);
         }
       }
     }
-    __syncthreads();
+    __syncthreads();  // the buffer is refilled two iterations later
   }
   // accumulator fragment: row = grp (gene), columns 2 * tig + {0, 1}
 #pragma unroll
@@ -136,7 +172,7 @@ s2n_mma_kernel(const double *__restrict__ xc, const double *__restrict__ tot, in
     if (g >= G) continue;
     const double t1 = tot[2 * g], t2 = tot[2 * g + 1];
 #pragma unroll
-    for (int j = 0; j < 2; j++)
+    for (int j = 0; j < 4; j++)
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         const long long col = c0 + wn + j * 8 + 2 * tig + h;
