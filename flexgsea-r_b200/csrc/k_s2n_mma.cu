@@ -178,11 +178,12 @@ s2n_mma_kernel(const double *__restrict__ xc, const double *__restrict__ tot, in
         const long long col = c0 + wn + j * 8 + 2 * tig + h;
         if (col >= C) continue;
         const int r = (int)(col % R);
-        const double dn1 = (double)n1n2[2 * r], dn2 = (double)n1n2[2 * r + 1];
+        // (reciprocal class sizes: the tensor path is certified to 1e-10, not bit-faithful)
+        const double in1 = 1.0 / (double)n1n2[2 * r], in2 = 1.0 / (double)n1n2[2 * r + 1];
         const double s1 = acc[i][j][h], q1 = acc[i + 2][j][h];
         const double s2 = t1 - s1, q2 = t2 - q1;
-        const double m1 = s1 / dn1, m2 = s2 / dn2;
-        const double e1 = q1 / dn1, e2 = q2 / dn2;          // E[xc^2] per class
+        const double m1 = s1 * in1, m2 = s2 * in2;
+        const double e1 = q1 * in1, e2 = q2 * in2;          // E[xc^2] per class
         const double v1 = e1 - m1 * m1, v2 = e2 - m2 * m2;  // population variances
         const double coef = (m1 - m2) / (sqrt(fmax(v1, 0.0)) + sqrt(fmax(v2, 0.0)));
         scores[(size_t)col * G + g] = coef;
