@@ -323,7 +323,7 @@ def run_gpu(args):
                    "permutations": "device Philox4x32-10 (value); host int32 matrix uploaded (e2e)",
                    "l2": "inputs larger than L2: each block streams %d MB of scores/ranks/weights (L2 is 126 MB)"
                          % int(min(P, 2048) * (18 * G) / 1e6),
-                   "score_mode": "bit-faithful s2n (reference operation order, no FMA)"},
+                   "score_mode": "FP64 tensor-core contraction + rank certification (near-tied / cancelled entries recomputed in the reference operation order)"},
         "wall_ms_per_step": wall_ms / args.steps,
         "e2e": {"value": float(S) * R * P * world / e2e_s, "unit": "ES/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,

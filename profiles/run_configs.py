@@ -37,4 +37,4 @@ if "C2" in which: run("C2 s2n+wKS", 20000, 200, 8000, (15, 500), 10000, nat.SCOR
 if "C3" in which: run("C3 lm+wKS (R=4)", 20000, 500, 8000, (15, 500), 10000, nat.SCORE_LM, nat.ES_WEIGHTED_KS)
 if "C4mm" in which: run("C4 s2n+maxmean", 20000, 200, 20000, (15, 300), 50000, nat.SCORE_S2N, nat.ES_MAXMEAN, reps=1)
 if "C4mean" in which: run("C4 s2n+mean", 20000, 200, 20000, (15, 300), 50000, nat.SCORE_S2N, nat.ES_MEAN, reps=1)
-if "C5r" in which: run("C5 shape, 1/8 of one GPU's share (P=1562)", 60000, 1000, 20000, (15, 500), 1562, nat.SCORE_S2N, nat.ES_WEIGHTED_KS, reps=1)
+if "C5r" in which: run("C5 shape, 1/8 of one GPU's share (P=1562)", 60000, 1000, 20000, (15, 500), 1562, nat.SCORE_S2N, nat.ES_WEIGHTED_KS, reps=2)
