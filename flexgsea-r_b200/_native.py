@@ -26,6 +26,8 @@ SYMBOLS = [
     "fgs_es_from_scores", "fgs_debug_last_scores", "fgs_null_device_ptr", "fgs_set_null",
     "fgs_calc_sig", "fgs_sig_stage1", "fgs_sig_stage2", "fgs_sig_finish", "fgs_launch_count",
     "fgs_last_timings", "fgs_set_profiling", "fgs_set_option",
+    "fgs_gmt_parse", "fgs_gmt_read", "fgs_gmt_n_sets", "fgs_gmt_nnz", "fgs_gmt_offsets", "fgs_gmt_index",
+    "fgs_gmt_set_name", "fgs_gmt_stats", "fgs_gmt_free",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -67,6 +69,40 @@ def _f(a):
 
 def _i(a):
     return np.asfortranarray(np.asarray(a, dtype=np.int32))
+
+
+def gmt_to_csr(gmt, gene_names, gs_size_min=10, gs_size_max=300):
+    """read_gmt + filter_gene_sets + match(), natively and once (fgs_gmt_parse /
+    fgs_gmt_read).  `gmt` is a path or literal GMT text.  Returns
+    (set names, offsets[S+1], index[nnz] 1-based, stats dict)."""
+    L = load()
+    L.fgs_gmt_set_name.restype = C.c_char_p
+    L.fgs_gmt_offsets.restype = _ip
+    L.fgs_gmt_index.restype = _ip
+    L.fgs_gmt_nnz.restype = C.c_longlong
+    names = [str(g).encode() for g in gene_names]
+    arr = (C.c_char_p * len(names))(*names)
+    h = C.c_void_p()
+    if isinstance(gmt, (str, os.PathLike)) and os.path.exists(gmt):
+        rc = L.fgs_gmt_read(str(gmt).encode(), arr, len(names), int(gs_size_min), int(gs_size_max), C.byref(h))
+    else:
+        text = gmt if isinstance(gmt, bytes) else str(gmt).encode()
+        rc = L.fgs_gmt_parse(text, C.c_size_t(len(text)), arr, len(names), int(gs_size_min),
+                             int(gs_size_max), C.byref(h))
+    if rc != OK:
+        raise FlexgseaError(rc, L.fgs_last_error().decode())
+    try:
+        S, nnz = L.fgs_gmt_n_sets(h), L.fgs_gmt_nnz(h)
+        offsets = np.ctypeslib.as_array(L.fgs_gmt_offsets(h), shape=(S + 1,)).copy()
+        index = (np.ctypeslib.as_array(L.fgs_gmt_index(h), shape=(nnz,)).copy() if nnz > 0
+                 else np.zeros(0, dtype=np.int32))
+        set_names = [L.fgs_gmt_set_name(h, k).decode() for k in range(S)]
+        gb, ga, sb = C.c_longlong(), C.c_longlong(), C.c_int()
+        L.fgs_gmt_stats(h, C.byref(gb), C.byref(ga), C.byref(sb))
+        stats = {"genes_before": gb.value, "genes_after": ga.value, "sets_before": sb.value}
+    finally:
+        L.fgs_gmt_free(h)
+    return set_names, offsets.astype(np.int32), index.astype(np.int32), stats
 
 
 def device_count():

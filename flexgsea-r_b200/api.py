@@ -410,11 +410,15 @@ def flexgsea(x, y, gene_sets, gene_score_fn=flexgsea_s2n, es_fn=flexgsea_weighte
     if not (np.isscalar(block_size) and block_size > 0):
         raise ValueError("block.size > 0 is not TRUE")  # :176-178
     return_values = [return_values] if isinstance(return_values, str) else list(return_values)
+    gmt_file = None
     if isinstance(gene_sets, (str, os.PathLike)):
         if verbose:
             print("Reading gene sets from file")
-        gene_sets = read_gmt(gene_sets)
-    if not isinstance(gene_sets, dict):
+        if str(gene_sets).endswith(".gz") or not os.path.exists(gene_sets):
+            gene_sets = read_gmt(gene_sets)      # compressed / literal data: host reader
+        else:
+            gmt_file = gene_sets                 # plain file: native GMT -> CSR ingest below
+    elif not isinstance(gene_sets, dict):
         raise TypeError("is.list(gene.sets) is not TRUE")
     if gene_names is not None:
         if len(gene_names) != n_genes:
@@ -426,11 +430,22 @@ def flexgsea(x, y, gene_sets, gene_score_fn=flexgsea_s2n, es_fn=flexgsea_weighte
         raise ValueError("Gene names should be given in gene.name or as colnames of x")  # :225-226
     if verbose:
         print("Filtering gene sets on size in dataset")
-    gene_sets = filter_gene_sets(gene_sets, gene_names, gs_size_min, gs_size_max, verbose)
-    if len(gene_sets) == 0:
-        raise ValueError("No valid gene sets after filtering for size.")  # :238
-    set_names = list(gene_sets.keys())
-    offsets, index = gene_sets_to_csr(gene_sets, gene_names)
+    if gmt_file is not None:
+        # read_gmt + filter_gene_sets + match(), once and natively (fgs_gmt_read)
+        set_names, offsets, index, st = nat.gmt_to_csr(gmt_file, gene_names, gs_size_min, gs_size_max)
+        if verbose:
+            print("Filtered %d of %d genes out" % (st["genes_before"] - st["genes_after"], st["genes_before"]))
+            print("Filtered %d of %d gene sets out" % (st["sets_before"] - len(set_names), st["sets_before"]))
+        if len(set_names) == 0:
+            raise ValueError("No valid gene sets after filtering for size.")  # :238
+        gene_sets = {nm: [gene_names[i - 1] for i in index[offsets[k]:offsets[k + 1]]]
+                     for k, nm in enumerate(set_names)}
+    else:
+        gene_sets = filter_gene_sets(gene_sets, gene_names, gs_size_min, gs_size_max, verbose)
+        if len(gene_sets) == 0:
+            raise ValueError("No valid gene sets after filtering for size.")  # :238
+        set_names = list(gene_sets.keys())
+        offsets, index = gene_sets_to_csr(gene_sets, gene_names)
 
     shard = _Shard(parallel)
     ctx = get_context(device)

@@ -22,6 +22,8 @@
 #ifndef FLEXGSEA_B200_H
 #define FLEXGSEA_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -158,6 +160,28 @@ int fgs_sig_stage2(fgs_ctx *ctx, const double *es, int response, int split_p, in
 int fgs_sig_finish(fgs_ctx *ctx, const double *nes, const long long *null_counts,
                    const long long *glob, int n_sets, int abs_flag, double *fdr,
                    long long *fdr_counts, long long *glob_counts);
+
+/* ---- gene-set ingest (host only, no device work) ------------------------- */
+/* GMT text -> CSR of 1-based gene indices, done once and natively.  Replaces
+ * read_gmt (R/flexgsea.R:966-973: name <tab> description <tab> gene ...),
+ * filter_gene_sets (:939-958: genes absent from gene_names are dropped, then
+ * sets whose remaining size is outside [gs_size_min, gs_size_max]) and the
+ * per-set match(set, gene.names) of :279 / :412 (first occurrence wins for a
+ * duplicated gene name; duplicates inside a set are kept).  The CSR is what
+ * fgs_set_gene_sets takes; set names come back in file order. */
+typedef struct fgs_gmt fgs_gmt;
+int fgs_gmt_parse(const char *text, size_t len, const char *const *gene_names, int n_gene,
+                  int gs_size_min, int gs_size_max, fgs_gmt **out);
+int fgs_gmt_read(const char *path, const char *const *gene_names, int n_gene, int gs_size_min,
+                 int gs_size_max, fgs_gmt **out);
+int fgs_gmt_n_sets(const fgs_gmt *g);
+long long fgs_gmt_nnz(const fgs_gmt *g);
+const int *fgs_gmt_offsets(const fgs_gmt *g); /* [n_sets + 1] */
+const int *fgs_gmt_index(const fgs_gmt *g);   /* [nnz], 1-based */
+const char *fgs_gmt_set_name(const fgs_gmt *g, int k);
+/* the counts filter_gene_sets reports: members before / after the gene filter, sets before the size filter */
+int fgs_gmt_stats(const fgs_gmt *g, long long *genes_before, long long *genes_after, int *sets_before);
+void fgs_gmt_free(fgs_gmt *g);
 
 /* ---- instrumentation --------------------------------------------------- */
 /* number of kernels this library launched on ctx since creation */

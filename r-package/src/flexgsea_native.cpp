@@ -48,6 +48,27 @@ void fgs_upload_(SEXP ctx, NumericMatrix x, IntegerVector offsets, IntegerVector
   check(fgs_set_x(ctx_of(ctx), x.begin(), x.nrow(), x.ncol()));
   check(fgs_set_gene_sets(ctx_of(ctx), offsets.begin(), index.begin(), offsets.size() - 1));
 }
+// gene.sets given as a GMT file: read_gmt + filter_gene_sets + match(set, gene.names)
+// (R/flexgsea.R:966-973, :939-958, :279/:412) natively and once
+// [[Rcpp::export]]
+List fgs_gmt_read_(std::string path, CharacterVector gene_names, int gs_size_min, int gs_size_max) {
+  std::vector<const char *> names(gene_names.size());
+  for (R_xlen_t i = 0; i < gene_names.size(); i++) names[i] = CHAR(STRING_ELT(gene_names, i));
+  fgs_gmt *g = nullptr;
+  check(fgs_gmt_read(path.c_str(), names.data(), (int)names.size(), gs_size_min, gs_size_max, &g));
+  const int S = fgs_gmt_n_sets(g);
+  const long long nnz = fgs_gmt_nnz(g);
+  IntegerVector offsets(fgs_gmt_offsets(g), fgs_gmt_offsets(g) + S + 1);
+  IntegerVector index(fgs_gmt_index(g), fgs_gmt_index(g) + nnz);
+  CharacterVector set_names(S);
+  for (int k = 0; k < S; k++) set_names[k] = fgs_gmt_set_name(g, k);
+  long long gb = 0, ga = 0; int sb = 0;
+  fgs_gmt_stats(g, &gb, &ga, &sb);
+  fgs_gmt_free(g);
+  return List::create(_["names"] = set_names, _["offsets"] = offsets, _["index"] = index,
+                      _["genes_before"] = (double)gb, _["genes_after"] = (double)ga, _["sets_before"] = sb);
+}
+
 // [[Rcpp::export]]
 void fgs_response_s2n_(SEXP ctx, LogicalMatrix y_bin) {
   check(fgs_set_response_s2n(ctx_of(ctx), LOGICAL(y_bin), y_bin.nrow(), y_bin.ncol()));

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import flexgsea_r_b200 as fg
-from flexgsea_r_b200 import api
+from flexgsea_r_b200 import api, _native as nat
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -56,6 +56,57 @@ def test_read_gmt_and_filter(tmp_path):
     # duplicated gene names: match() takes the first (:279)
     off, idx = fg.gene_sets_to_csr({"a": ["g2", "g2"]}, ["g1", "g2", "g2"])
     assert list(idx) == [2, 2]
+
+
+def test_native_gmt_ingest_matches_host_path(tmp_path):
+    """fgs_gmt_parse / fgs_gmt_read (GMT -> CSR, native) against read_gmt +
+    filter_gene_sets + gene_sets_to_csr on a random collection: CRLF lines, an
+    empty line, a set without genes, unknown genes, a gene repeated inside a set,
+    a duplicated gene name in the data (first match wins), duplicated set names."""
+    rng = np.random.default_rng(5)
+    genes = ["G%d" % i for i in range(400)]
+    names = genes[:300] + ["G7"] + genes[300:350]          # G7 twice: match() returns the first
+    lines = []
+    for k in range(120):
+        m = int(rng.integers(0, 40))
+        mem = [genes[i] for i in rng.integers(0, 400, size=m)]  # with repeats, some absent from `names`
+        lines.append("\t".join(["SET%d" % (k % 100), "desc %d" % k] + mem))
+    lines.insert(17, "")
+    lines.append("LONELY\tno genes")
+    text = "\r\n".join(lines) + "\n"
+    for smin, smax in ((1, 300), (5, 20), (10, 300)):
+        # host path (lists keep duplicated set names apart: parse by hand like read_gmt does per line)
+        sets = []
+        for line in text.splitlines():
+            if not line:
+                continue
+            parts = line.split("\t", 2)
+            sets.append((parts[0], parts[2].split("\t") if len(parts) > 2 else []))
+        present = set(names)
+        first = {}
+        for i, g in enumerate(names):
+            first.setdefault(g, i + 1)
+        w_names, w_off, w_idx = [], [0], []
+        for nm, gs in sets:
+            kept = [g for g in gs if g in present]
+            if smin <= len(kept) <= smax:
+                w_names.append(nm); w_idx += [first[g] for g in kept]; w_off.append(len(w_idx))
+        got_names, off, idx, stats = nat.gmt_to_csr(text, names, smin, smax)
+        assert got_names == w_names and list(off) == w_off and list(idx) == w_idx
+        assert stats["sets_before"] == len(sets)
+        assert stats["genes_before"] == sum(len(gs) for _, gs in sets)
+        assert stats["genes_after"] == sum(sum(g in present for g in gs) for _, gs in sets)
+    p = tmp_path / "c.gmt"
+    p.write_bytes(text.encode())
+    a = nat.gmt_to_csr(str(p), names, 5, 20)
+    b = nat.gmt_to_csr(text, names, 5, 20)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    # and the same answer as the documented Python helpers when set names are unique
+    uniq = "A\tx\tG1\tG2\tG999\nB\tx\tG3\n"
+    gs = fg.filter_gene_sets(fg.read_gmt(uniq), names, 1, 300, verbose=False)
+    o2, i2 = fg.gene_sets_to_csr(gs, names)
+    n3, o3, i3, _ = nat.gmt_to_csr(uniq, names, 1, 300)
+    assert n3 == list(gs) and np.array_equal(o2, o3) and np.array_equal(i2, i3)
 
 
 def test_binarise_like_flexgsea_s2n():
@@ -104,7 +155,7 @@ import os, sys, numpy as np
 sys.path.insert(0, %r)
 import torch.distributed as dist
 import flexgsea_r_b200 as fg
-from flexgsea_r_b200 import api
+from flexgsea_r_b200 import api, _native as nat
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%d" %% int(sys.argv[2]), rank=int(sys.argv[1]), world_size=2)
 sh = api._Shard(None)
 assert (sh.rank, sh.world) == (int(sys.argv[1]), 2)
