@@ -167,9 +167,17 @@ struct StageTimer {
 // columns (score vectors) processed per block: bounded so the scratch
 // (scores 8G + rank 2G + weights 8G bytes per column) stays ~<= 1.5 GB
 static long long block_columns(fgs_ctx *c, long long C_total) {
-  long long cb = c->opt_perm_block > 0 ? c->opt_perm_block : 2048;
   long long cap = (long long)(3.0e9 / (18.0 * (double)c->G + 64));
   if (cap < 1) cap = 1;
+  long long cb = c->opt_perm_block;
+  if (cb <= 0) {
+    // the rank and ES kernels are persistent (a CTA per SM takes a column at a time): a
+    // block that is a whole number of rounds over the SMs has no idle tail
+    cb = 2048;
+    if (cb > cap) cb = cap;
+    if (cb > c->num_sms) cb = ((cb + c->num_sms / 2) / c->num_sms) * c->num_sms;
+    if (cb > cap) cb -= c->num_sms;
+  }
   if (cb > cap) cb = cap;
   if (cb > C_total) cb = C_total;
   return cb < 1 ? 1 : cb;
