@@ -105,6 +105,9 @@ struct fgs_ctx {
   // "slow" = duplicated members or more than ES_MAX_SET members (order-free kernel)
   fgs::DevBuf<int4> set_info;
   fgs::DevBuf<double> set_invgm;   // [S] 1 / (G - m), processing order
+  fgs::DevBuf<int2> tie_list;      // (column, set) units whose es_pos and -es_neg tied: redone exactly
+  fgs::DevBuf<int> tie_ctr;
+  int tie_cap = 0;
   fgs::DevBuf<unsigned char> set_slow;  // [S] flags + [16] status bytes of launch_prep_sets
   fgs::DevBuf<uint16_t> set_idx16; // members as uint16, processing order, 8-blocks padded with gene G
   long long idx16_blocks = 0;

@@ -145,6 +145,13 @@ __device__ __forceinline__ double warp_max_exact(double x) {
   return __hiloint2double((int)(mh ^ (inv | 0x80000000u)), (int)(ml ^ inv));
 }
 
+constexpr double ES_TIE_REL = 1e-9;  // |es_pos + es_neg| below this fraction of their size: redo exactly
+__device__ __forceinline__ void tie_push(int2 *__restrict__ list, int *__restrict__ ctr, int cap, int col,
+                                         int set_id) {
+  const int at = atomicAdd(ctr, 1);  // a count above cap makes es_wks_tie_kernel redo every unit
+  if (at < cap) list[at] = make_int2(col, set_id);
+}
+
 // Two members' ranks (0-based, from the staged column) packed in one register;
 // their hit weights (rank-indexed |score|^p; the pad rank G has weight 0) are
 // added to the lane's share of the set's weight total.
@@ -170,7 +177,7 @@ template <int LANES, int SL, bool W_SMEM>
 __device__ __forceinline__ double wks_sets(const uint16_t *__restrict__ s_rank,
                                            const double *__restrict__ wsrc,
                                            const uint16_t *__restrict__ idx16, int zblk, int m, int G,
-                                           double invGm, int ls) {
+                                           double invGm, int ls, bool &tie) {
   constexpr int NR = SL / 2;
   const uint32_t padpair = (uint32_t)G * 0x10001u;
   uint32_t v[NR];
@@ -248,7 +255,11 @@ __device__ __forceinline__ double wks_sets(const uint16_t *__restrict__ s_rank,
     }
   }
   double es = (mx > -mn) ? mx : mn;                      // strict, :833
-  if (W == 0.0 || m == G || m == 0) es = nan("");        // 0/0 in the reference
+  // es_pos and -es_neg equal up to rounding (a structural tie: e.g. the unweighted
+  // statistic, p = 0): which side wins is decided by the reference's own rounding,
+  // so the unit is redone in the reference's operation order (es_wks_tie_kernel)
+  tie = fabs(mx + mn) <= ES_TIE_REL * fmax(fabs(mx), fabs(mn));
+  if (W == 0.0 || m == G || m == 0) { es = nan(""); tie = false; }  // 0/0 in the reference
   return es;
 }
 
@@ -257,7 +268,8 @@ template <bool W_SMEM>
 __global__ void __launch_bounds__(ES_THREADS, 1)
 es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sabs, int G,
               long long C, const int4 *__restrict__ set_info, const uint16_t *__restrict__ idx16,
-              const double *__restrict__ set_invgm, int S, double *__restrict__ es_out) {
+              const double *__restrict__ set_invgm, int S, double *__restrict__ es_out,
+              int2 *__restrict__ tie_list, int *__restrict__ tie_ctr, int tie_cap) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const size_t Gp = pitch_of(G);
@@ -300,23 +312,29 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
       mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, 16));
       if (mmax <= 8 * 64) {
         double es;
-        if (mmax <= 8 * 4) es = wks_sets<8, 4, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls);
-        else if (mmax <= 8 * 8) es = wks_sets<8, 8, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls);
-        else if (mmax <= 8 * 16) es = wks_sets<8, 16, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls);
-        else if (mmax <= 8 * 32) es = wks_sets<8, 32, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls);
+        bool tie = false;
+        if (mmax <= 8 * 4) es = wks_sets<8, 4, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie);
+        else if (mmax <= 8 * 8) es = wks_sets<8, 8, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie);
+        else if (mmax <= 8 * 16) es = wks_sets<8, 16, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie);
+        else if (mmax <= 8 * 32) es = wks_sets<8, 32, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie);
         else {  // 257 .. 512 members: sixteen lanes per set (32 ranks per lane), the quad as two pairs
 #pragma unroll 1
           for (int h = 0; h < 2; h++) {
             const int src = (2 * h + (lane >> 4)) * 8;
             const int mi = __shfl_sync(0xffffffffu, m, src), zi = __shfl_sync(0xffffffffu, info.z, src);
             const double igi = __shfl_sync(0xffffffffu, ig, src);
-            const double e2 = wks_sets<16, 32, W_SMEM>(s_rank, wsrc, idx16, zi, mi, G, igi, lane & 15);
+            bool t2 = false;
+            const double e2 = wks_sets<16, 32, W_SMEM>(s_rank, wsrc, idx16, zi, mi, G, igi, lane & 15, t2);
             // hand the result to the set's own eight lanes
             const double back = __shfl_sync(0xffffffffu, e2, (seg & 1) * 16);
-            if ((seg >> 1) == h) es = back;
+            const bool tback = __shfl_sync(0xffffffffu, (int)t2, (seg & 1) * 16) != 0;
+            if ((seg >> 1) == h) { es = back; tie = tback; }
           }
         }
-        if (mine && ls == 0) es_col[info.w] = es;
+        if (mine && ls == 0) {
+          es_col[info.w] = es;
+          if (tie) tie_push(tie_list, tie_ctr, tie_cap, (int)col, info.w);
+        }
       } else {  // a quad with a set of 513 .. ES_MAX_SET members: one set at a time on the whole warp
 #pragma unroll 1
         for (int i = 0; i < 4; i++) {
@@ -326,9 +344,13 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
           const bool on = __shfl_sync(0xffffffffu, (int)mine, 8 * i) != 0;
           if (!on) continue;
           double es;
-          if (mi <= 32 * 32) es = wks_sets<32, 32, W_SMEM>(s_rank, wsrc, idx16, zi, mi, G, igi, lane);
-          else es = wks_sets<32, 64, W_SMEM>(s_rank, wsrc, idx16, zi, mi, G, igi, lane);
-          if (lane == 0) es_col[wi] = es;
+          bool tie = false;
+          if (mi <= 32 * 32) es = wks_sets<32, 32, W_SMEM>(s_rank, wsrc, idx16, zi, mi, G, igi, lane, tie);
+          else es = wks_sets<32, 64, W_SMEM>(s_rank, wsrc, idx16, zi, mi, G, igi, lane, tie);
+          if (lane == 0) {
+            es_col[wi] = es;
+            if (tie) tie_push(tie_list, tie_ctr, tie_cap, (int)col, wi);
+          }
         }
       }
     }
@@ -353,7 +375,8 @@ __global__ void build_idx16_kernel(const int4 *__restrict__ set_info, const int 
 __global__ void __launch_bounds__(256)
 es_wks_generic_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sabs, int G,
                       long long C, const int *__restrict__ set_off, const int *__restrict__ set_idx,
-                      const int *__restrict__ set_ids, int n_ids, int S, double *__restrict__ es_out) {
+                      const int *__restrict__ set_ids, int n_ids, int S, double *__restrict__ es_out,
+                      int2 *__restrict__ tie_list, int *__restrict__ tie_ctr, int tie_cap) {
   const int lane = threadIdx.x & 31;
   const long long unit = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (unit >= (long long)n_ids * C) return;
@@ -386,8 +409,79 @@ es_wks_generic_kernel(const uint16_t *__restrict__ rank16, const double *__restr
   mn = warp_min(mn);
   if (lane == 0) {
     double es = (mx > -mn) ? mx : mn;
-    if (W == 0.0 || m == G || m == 0) es = nan("");
+    const bool degenerate = W == 0.0 || m == G || m == 0;
+    if (degenerate) es = nan("");
     es_out[(size_t)col * S + s] = es;
+    if (!degenerate && fabs(mx + mn) <= ES_TIE_REL * fmax(fabs(mx), fabs(mn)))
+      tie_push(tie_list, tie_ctr, tie_cap, (int)col, s);
+  }
+}
+
+// es_pos == -es_neg up to rounding: the sign of the result is the reference's
+// rounding, so these units are redone in the reference's own operation order
+// (the arithmetic of observed_wks_kernel / R/flexgsea.R:819-838): w / sum(w) per
+// member, a running sum that rounds like R's long-double cumsum (double-double
+// here: exact whenever the tie is structural, e.g. equal weights), then
+// d_hit - d_miss with d_miss = (r - k) / (G - m) as a division.  A warp per
+// listed (column, set); every unit when the list overflowed.  O(m^2 / 32) with
+// no scratch: each member sums the weights of the members ranked before it.
+struct dd2 { double hi, lo; };
+__device__ __forceinline__ dd2 dd2_add(dd2 a, double b) {
+  const double s = __dadd_rn(a.hi, b);
+  const double bb = __dsub_rn(s, a.hi);
+  double e = __dadd_rn(__dsub_rn(a.hi, __dsub_rn(s, bb)), __dsub_rn(b, bb));
+  e = __dadd_rn(e, a.lo);
+  const double hi = __dadd_rn(s, e);
+  return {hi, __dsub_rn(e, __dsub_rn(hi, s))};
+}
+__global__ void __launch_bounds__(256)
+es_wks_tie_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sabs, int G,
+                  long long C, const int *__restrict__ set_off, const int *__restrict__ set_idx, int S,
+                  const int2 *__restrict__ list, const int *__restrict__ ctr, int cap,
+                  double *__restrict__ es_out) {
+  const int lane = threadIdx.x & 31;
+  const int listed = *ctr;
+  const bool all = listed > cap;
+  const long long nunit = all ? (long long)S * C : listed;
+  const size_t Gp = pitch_of(G);
+  for (long long u = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < nunit;
+       u += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const long long col = all ? u / S : list[u].x;
+    const int s = all ? (int)(u % S) : list[u].y;
+    const uint16_t *rk = rank16 + (size_t)col * Gp;
+    const double *sa = sabs + (size_t)col * Gp;
+    const int off = set_off[s], m = set_off[s + 1] - off;
+    dd2 tot = {0.0, 0.0};  // sum(w) in member order (R: long double)
+    if (lane == 0)
+      for (int j = 0; j < m; j++) tot = dd2_add(tot, sa[rk[set_idx[off + j]] - 1]);
+    const double W = __shfl_sync(0xffffffffu, tot.hi, 0);
+    const double denom = (double)(G - m);
+    double mx = -INFINITY, mn = INFINITY;
+    bool has_nan = false;
+    for (int j = lane; j < m; j += 32) {
+      const int rj = rk[set_idx[off + j]];
+      int kord = 0;
+      dd2 cum = {0.0, 0.0};
+      for (int t = 0; t < m; t++) {
+        const int rt = rk[set_idx[off + t]];
+        if (rt < rj || (rt == rj && t <= j)) { kord++; cum = dd2_add(cum, __ddiv_rn(sa[rt - 1], W)); }
+      }
+      const double wo = __ddiv_rn(sa[rj - 1], W);
+      const double d_miss = __ddiv_rn((double)(rj - kord), denom);
+      const double ps = __dsub_rn(cum.hi, d_miss);
+      const double ng = __dsub_rn(ps, wo);
+      if (isnan(ps) || isnan(ng)) has_nan = true;
+      if (ps > mx) mx = ps;
+      if (ng < mn) mn = ng;
+    }
+    mx = warp_max(mx);
+    mn = warp_min(mn);
+    has_nan = __any_sync(0xffffffffu, has_nan);
+    if (lane == 0) {
+      double es = (mx > -mn) ? mx : mn;  // :833
+      if (has_nan || m == 0) es = nan("");
+      es_out[(size_t)col * S + s] = es;
+    }
   }
 }
 
@@ -436,7 +530,8 @@ int launch_es_wks_generic(fgs_ctx *c, const uint16_t *d_rank16, const double *d_
   long long blocks = (units + 7) / 8;
   if (blocks > 0x7fffffffLL) { set_error("too many (set, column) units"); return FGS_ERR_ARG; }
   es_wks_generic_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(
-      d_rank16, d_sabs, G, C, c->set_off.p, c->set_idx.p, d_set_ids, n_ids, c->S, d_es);
+      d_rank16, d_sabs, G, C, c->set_off.p, c->set_idx.p, d_set_ids, n_ids, c->S, d_es,
+      c->tie_list.p, c->tie_ctr.p, c->tie_cap);
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   return FGS_OK;
@@ -511,9 +606,8 @@ static int ensure_set_blocks(fgs_ctx *c, int G) {
   return FGS_OK;
 }
 
-int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
-                  double *d_es) {
-  if (C <= 0 || c->S <= 0) return FGS_OK;
+static int launch_es_wks_inner(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G,
+                               long long C, double *d_es) {
   if (c->opt_force_generic)
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
   const size_t Gp = pitch_of(G);
@@ -532,17 +626,39 @@ int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, in
     auto k = es_wks_kernel<true>;
     FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx16.p,
-                                             c->set_invgm.p, c->S, d_es);
+                                             c->set_invgm.p, c->S, d_es, c->tie_list.p, c->tie_ctr.p,
+                                             c->tie_cap);
   } else {
     auto k = es_wks_kernel<false>;
     FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx16.p,
-                                             c->set_invgm.p, c->S, d_es);
+                                             c->set_invgm.p, c->S, d_es, c->tie_list.p, c->tie_ctr.p,
+                                             c->tie_cap);
   }
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   if (c->n_slow > 0)
     FGS_TRY(launch_es_wks_generic(c, d_rank16, d_sabs, G, C, c->slow_ids.p, c->n_slow, d_es));
+  return FGS_OK;
+}
+
+// Weighted KS of C score columns: the in-register kernel (or the order-free one),
+// then the exact redo of the units whose two extremes tied.
+int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
+                  double *d_es) {
+  if (C <= 0 || c->S <= 0) return FGS_OK;
+  if (c->tie_cap == 0) {
+    c->tie_cap = 1 << 20;
+    FGS_TRY(c->tie_list.ensure((size_t)c->tie_cap));
+    FGS_TRY(c->tie_ctr.ensure(4));
+  }
+  FGS_CUDA(cudaMemsetAsync(c->tie_ctr.p, 0, 4 * sizeof(int), c->stream));
+  FGS_TRY(launch_es_wks_inner(c, d_rank16, d_sabs, G, C, d_es));
+  int grid = c->num_sms * 4;  // grid-stride over the device-side count (usually zero)
+  es_wks_tie_kernel<<<grid, 256, 0, c->stream>>>(d_rank16, d_sabs, G, C, c->set_off.p, c->set_idx.p, c->S,
+                                                 c->tie_list.p, c->tie_ctr.p, c->tie_cap, d_es);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
   return FGS_OK;
 }
 

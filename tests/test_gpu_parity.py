@@ -91,6 +91,17 @@ def test_perm_null_s2n_wks(ctx, oracle, R, abs_flag, s2n_mode):
     assert np.abs(got - want).max() <= ES_TOL
 
 
+@pytest.mark.parametrize("p_exp", [0.0, 0.5, 2.0])
+def test_weighted_ks_weight_exponent(ctx, oracle, p_exp):
+    """w = |s|^p (R/flexgsea.R:819) for p != 1: p = 0 is the classic unweighted KS
+    (0^0 = 1 as in R), fractional and > 1 exponents go through pow()."""
+    x, y, perm, off, idx = _case(G=600, S=40, P=32, sizes=(5, 90))
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    got = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, 32, perm=perm, p=p_exp)
+    rc, want = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, oracle.ES_WKS, p=p_exp)
+    assert rc == 0 and np.abs(got - want).max() <= ES_TOL
+
+
 def test_tensor_scores_certified_ranks(ctx, oracle):
     """near ties under the tensor-core score path: duplicated genes (exact ties in
     the reference), a gene and its 10x copy (1 ulp apart in the reference,
