@@ -37,6 +37,17 @@ __device__ __forceinline__ double dd_div_n(dd a, double n) {
   return q + r / n;
 }
 
+// A null ES within rounding of the set's observed ES is taken as equal to it.  They
+// come from permutations that reproduce the observed labelling (common when there
+// are few samples); the reference computes both with the same code, so there they
+// are bit-identical and its `<=` / `>=` / `>` counts see a tie.  Here the observed ES
+// is made by the exact kernel and the null by the tensor-core / in-register path,
+// which agree to ~1e-13 only.
+constexpr double SIG_SNAP_REL = 1e-11;
+__device__ __forceinline__ double snap_to_observed(double v, double e) {
+  return fabs(v - e) <= SIG_SNAP_REL * fabs(e) ? e : v;
+}
+
 constexpr int SIG_NF = 4;  // sums per set: pos hi, pos lo, neg hi, neg lo
 constexpr int SIG_NC = 6;  // counts per set
 
@@ -57,7 +68,7 @@ sig_partial_kernel(const double *__restrict__ null, int S, int R, int P, int res
   const double *base = null + (size_t)s + (size_t)S * resp;
   const size_t stride = (size_t)S * R;
   for (int p = p0; p < p1; p++) {
-    const double v = base[stride * p];
+    const double v = snap_to_observed(base[stride * p], e);
     if (v >= 0.0) { c0++; sp = dd_add_d(sp, v); }
     if (v < 0.0) { c1++; sn = dd_add_d(sn, v); }
     if (v <= 0.0) c2++;
@@ -271,7 +282,8 @@ __device__ __forceinline__ int lut_count(const double *__restrict__ a, int n, co
 template <bool T_SMEM>
 __global__ void __launch_bounds__(256)
 fdr_count_kernel(const double *__restrict__ null, int S, int R, int P, int resp, int abs_flag,
-                 const double *__restrict__ mpos, const double *__restrict__ mneg,
+                 const double *__restrict__ es, const double *__restrict__ mpos,
+                 const double *__restrict__ mneg,
                  const double *__restrict__ t1, int n1, const double *__restrict__ t2, int n2,
                  const int *__restrict__ lut_g, int chunk_len, unsigned long long *__restrict__ hist1,
                  unsigned long long *__restrict__ hist2, unsigned long long *__restrict__ glob) {
@@ -299,13 +311,13 @@ fdr_count_kernel(const double *__restrict__ null, int S, int R, int P, int resp,
   constexpr int U = 4;
   unsigned long long gpos = 0, gneg = 0;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
-    const double mp = mpos[s], mg = mneg[s];
+    const double mp = mpos[s], mg = mneg[s], e = es[s];
     const double *base = null + (size_t)s + (size_t)S * resp;
     const size_t stride = (size_t)S * R;
     for (int pb = p0; pb < p1; pb += U) {
       double v[U];
 #pragma unroll
-      for (int u = 0; u < U; u++) v[u] = (pb + u < p1) ? base[stride * (pb + u)] : nan("");
+      for (int u = 0; u < U; u++) v[u] = (pb + u < p1) ? snap_to_observed(base[stride * (pb + u)], e) : nan("");
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const double nv = abs_flag ? v[u] / mp : v[u] / (v[u] >= 0.0 ? mp : -mg);  // :608-610, :619-621
@@ -483,7 +495,6 @@ int launch_sig_means(fgs_ctx *c, const double *d_sums_parts, int nparts, const l
 int launch_sig_stage2(fgs_ctx *c, const double *d_null, int S, int R, int P, int response,
                       const double *d_es, int abs_flag, const double *d_mpos, const double *d_mneg,
                       double *d_nes, long long *d_null_counts, long long *d_glob) {
-  (void)d_es;
   // scratch: group[S], pos[S], gn[4], id1[S], id2[S] (ints); t1[S], t2[S] (doubles);
   // hist1[S+1], hist2[S+1] (u64)
   FGS_TRY(c->counters.ensure((size_t)4 * S + 8));
@@ -523,12 +534,12 @@ int launch_sig_stage2(fgs_ctx *c, const double *d_null, int S, int R, int P, int
     if (smem_t <= (size_t)c->smem_optin / 2) {
       auto k = fdr_count_kernel<true>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-      k<<<grid, 256, smem_t, c->stream>>>(d_null, S, R, P, response, abs_flag, d_mpos, d_mneg, t1, n1,
+      k<<<grid, 256, smem_t, c->stream>>>(d_null, S, R, P, response, abs_flag, d_es, d_mpos, d_mneg, t1, n1,
                                           t2, n2, c->sig_lut.p, chunk_len, h1, h2, (unsigned long long *)d_glob);
     } else {
       auto k = fdr_count_kernel<false>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
-      k<<<grid, 256, smem_h, c->stream>>>(d_null, S, R, P, response, abs_flag, d_mpos, d_mneg, t1, n1,
+      k<<<grid, 256, smem_h, c->stream>>>(d_null, S, R, P, response, abs_flag, d_es, d_mpos, d_mneg, t1, n1,
                                           t2, n2, c->sig_lut.p, chunk_len, h1, h2, (unsigned long long *)d_glob);
     }
     c->launches++;

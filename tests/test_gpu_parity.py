@@ -402,6 +402,38 @@ def test_calc_sig_counts_identical(ctx, oracle, simple, abs_flag):
         assert np.allclose(got["fdr"], want["fdr"], rtol=1e-12, atol=0)
 
 
+def test_small_n_label_preserving_permutations(ctx, oracle):
+    """Six samples, 3 + 3: one permutation in twenty reproduces the observed
+    labelling, and the reference then gets a null ES bit-identical to the observed
+    one (same code, same numbers), which its `<=` / `>=` counts see as equal.  Here
+    the observed ES comes from the exact kernel and the null from the tensor-core /
+    in-register path, so the significance kernels take null values within rounding
+    of the observed ES as equal to it: p and FDR counts must match the reference."""
+    G, n, S, P = 300, 6, 25, 400
+    off, idx = synth.gene_sets_csr(G, S, (8, 40), "uniform", seed=3)
+    x, y = synth.two_class(G, n, off, idx, seed=4)
+    perm = synth.perm_matrix(n, P, seed=6)
+    yb = y.astype(np.int32)
+    same = sum(np.array_equal(yb[perm[:, p] - 1, 0], yb[:, 0]) for p in range(P))
+    assert same >= 5                                    # the case is really exercised
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(yb)
+    sc = ctx.score_observed(nat.SCORE_S2N)
+    obs = ctx.observed_es(nat.ES_WEIGHTED_KS, sc, ragged=False)["es"][:, 0]
+    ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm, want_host=False)
+    got = ctx.calc_sig(obs, 0, True, True, False)
+    o_sc = oracle.s2n_post(oracle.s2n_C(x, yb))
+    rc, o_obs = oracle.es_from_scores(oracle.ES_WKS, o_sc.reshape(G, 1, 1), off, idx)
+    rc2, o_null = oracle.perm_null(x, oracle.SCORE_S2N, yb, False, perm, off, idx, oracle.ES_WKS)
+    assert rc == 0 and rc2 == 0
+    want = oracle.calc_sig(o_obs[:, 0, 0], o_null[:, 0, :], True, True, False)
+    assert np.abs(obs - o_obs[:, 0, 0]).max() <= ES_TOL
+    assert np.array_equal(got["p_counts"], want["p_counts"])
+    assert np.array_equal(got["fdr_counts"], want["fdr_counts"])
+    assert np.array_equal(got["glob_counts"], want["glob_counts"])
+    assert np.allclose(got["p"], want["p"], rtol=1e-14, atol=0)
+    assert np.allclose(got["fdr"], want["fdr"], rtol=1e-10, atol=0)
+
+
 def test_fdr_reference_properties_on_device(ctx):
     """tests/testthat/test_fdr.R:20-54 through the device path."""
     from test_oracle_golden import _fdr_inputs
