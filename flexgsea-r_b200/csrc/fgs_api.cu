@@ -212,7 +212,20 @@ static int rank_and_es(fgs_ctx *c, int es_kind, double p_exp, int abs_flag, long
     c->last_launches[2] += c->launches - l0;
     tm.mark();
     l0 = c->launches;
-    FGS_TRY(launch_es_wks(c, c->rank16.p, c->sabs.p, G, Cb, d_es));
+    FGS_TRY(launch_es_wks(c, c->rank16.p, c->sabs.p, G, Cb, d_es, c->cur_cert));
+    if (c->cur_cert) {
+      // structural ties between es_pos and -es_neg hang on the last bit of the weights:
+      // the tied units' member scores are recomputed in the reference's operation order
+      // before the exact redo (list region 0 of the certification buffers is free again)
+      int2 *list = c->cert_list.p;
+      int *cnt = c->cert_ctr.p + 2;
+      FGS_TRY(launch_tie_members(c, list, cnt, c->opt_cert_cap, c->flags.p + (c->flags.n - 1)));
+      FGS_TRY(launch_s2n_exact_entries(c, c->x.p, c->n, G, c->cur_labels, c->n1n2.p, c->s2n_R, list, cnt,
+                                       c->opt_cert_cap, c->scores.p, c->flags.p + c->cur_flag0));
+      FGS_TRY(launch_tie_refresh_weights(c, list, cnt, c->opt_cert_cap, c->scores.p, c->rank16.p, c->sabs.p,
+                                         G, p_exp));
+      FGS_TRY(launch_es_wks_ties(c, c->rank16.p, c->sabs.p, G, Cb, d_es));
+    }
     c->last_launches[3] += c->launches - l0;
     tm.mark();
   } else if (es_kind == FGS_ES_MAXMEAN || es_kind == FGS_ES_MEAN) {

@@ -194,7 +194,13 @@ int launch_s2n_exact_entries(fgs_ctx *c, const double *d_x, int n, int G, const 
 // K4 / K5
 int launch_prep_sets(fgs_ctx *c, int S, int *h_status, unsigned char *h_slow);
 int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
-                  double *d_es /* [C][S] */);
+                  double *d_es, bool defer_ties = false);
+int launch_es_wks_ties(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
+                       double *d_es);
+int launch_tie_members(fgs_ctx *c, int2 *d_out, int *d_out_ctr, int out_cap, int *d_overflow);
+int launch_tie_refresh_weights(fgs_ctx *c, const int2 *d_list, const int *d_ctr, int cap,
+                               const double *d_scores, const uint16_t *d_rank16, double *d_sabs, int G,
+                               double p_exp);
 int launch_es_wks_generic(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G,
                           long long C, const int *d_set_ids, int n_ids, double *d_es);
 int launch_es_mean(fgs_ctx *c, const double *d_scores, int G, long long C, int es_kind,

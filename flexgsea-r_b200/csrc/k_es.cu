@@ -642,10 +642,86 @@ static int launch_es_wks_inner(fgs_ctx *c, const uint16_t *d_rank16, const doubl
   return FGS_OK;
 }
 
+// The member genes of the tied units as (column, gene) entries, for
+// s2n_exact_entries_kernel: with tensor-core scores the weights are only ~1e-13
+// from the reference's, and at a structural tie the sign of the result hangs on
+// their last bit.  Overflow (of this list or of the tie list) raises the flag
+// that makes the caller rerun the call with the bit-faithful score kernel.
+__global__ void __launch_bounds__(256)
+tie_members_kernel(const int2 *__restrict__ tie_list, const int *__restrict__ tie_ctr, int tie_cap,
+                   const int *__restrict__ set_off, const int *__restrict__ set_idx,
+                   int2 *__restrict__ out, int *__restrict__ out_ctr, int out_cap,
+                   int *__restrict__ overflow) {
+  const int lane = threadIdx.x & 31;
+  const int listed = *tie_ctr;
+  if (listed > tie_cap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(overflow, 16);
+    return;
+  }
+  for (int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < listed;
+       u += gridDim.x * (blockDim.x >> 5)) {
+    const int col = tie_list[u].x, s = tie_list[u].y;
+    const int off = set_off[s], m = set_off[s + 1] - off;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(out_ctr, m);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((long long)base + m > out_cap) {
+      if (lane == 0) atomicOr(overflow, 16);
+      continue;
+    }
+    for (int j = lane; j < m; j += 32) out[base + j] = make_int2(col, set_idx[off + j]);
+  }
+}
+// ... and their hit weights rewritten from the exact scores (ranks are certified, so
+// the rank-ordered weight array only changes in value)
+__global__ void tie_refresh_weights_kernel(const int2 *__restrict__ list, const int *__restrict__ ctr,
+                                           int cap, const double *__restrict__ scores,
+                                           const uint16_t *__restrict__ rank16, double *__restrict__ sabs,
+                                           int G, double p_exp) {
+  const int n = min(*ctr, cap);
+  const size_t Gp = pitch_of(G);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int col = list[i].x, g = list[i].y;
+    double w = fabs(scores[(size_t)col * G + g]);
+    if (p_exp != 1.0) w = pow(w, p_exp);
+    sabs[(size_t)col * Gp + rank16[(size_t)col * Gp + g] - 1] = w;
+  }
+}
+int launch_tie_members(fgs_ctx *c, int2 *d_out, int *d_out_ctr, int out_cap, int *d_overflow) {
+  tie_members_kernel<<<c->num_sms * 2, 256, 0, c->stream>>>(c->tie_list.p, c->tie_ctr.p, c->tie_cap,
+                                                            c->set_off.p, c->set_idx.p, d_out, d_out_ctr,
+                                                            out_cap, d_overflow);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
+}
+int launch_tie_refresh_weights(fgs_ctx *c, const int2 *d_list, const int *d_ctr, int cap,
+                               const double *d_scores, const uint16_t *d_rank16, double *d_sabs, int G,
+                               double p_exp) {
+  tie_refresh_weights_kernel<<<c->num_sms * 2, 256, 0, c->stream>>>(d_list, d_ctr, cap, d_scores, d_rank16,
+                                                                    d_sabs, G, p_exp);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
+}
+
+// the exact redo of the units whose two extremes tied (see es_wks_tie_kernel)
+int launch_es_wks_ties(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
+                       double *d_es) {
+  if (C <= 0 || c->S <= 0) return FGS_OK;
+  int grid = c->num_sms * 4;  // grid-stride over the device-side count (usually zero)
+  es_wks_tie_kernel<<<grid, 256, 0, c->stream>>>(d_rank16, d_sabs, G, C, c->set_off.p, c->set_idx.p, c->S,
+                                                 c->tie_list.p, c->tie_ctr.p, c->tie_cap, d_es);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
+}
+
 // Weighted KS of C score columns: the in-register kernel (or the order-free one),
-// then the exact redo of the units whose two extremes tied.
+// then -- unless the caller first wants to refresh the tied units' weights
+// (defer_ties) -- the exact redo of the units whose two extremes tied.
 int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
-                  double *d_es) {
+                  double *d_es, bool defer_ties) {
   if (C <= 0 || c->S <= 0) return FGS_OK;
   if (c->tie_cap == 0) {
     c->tie_cap = 1 << 20;
@@ -654,11 +730,7 @@ int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, in
   }
   FGS_CUDA(cudaMemsetAsync(c->tie_ctr.p, 0, 4 * sizeof(int), c->stream));
   FGS_TRY(launch_es_wks_inner(c, d_rank16, d_sabs, G, C, d_es));
-  int grid = c->num_sms * 4;  // grid-stride over the device-side count (usually zero)
-  es_wks_tie_kernel<<<grid, 256, 0, c->stream>>>(d_rank16, d_sabs, G, C, c->set_off.p, c->set_idx.p, c->S,
-                                                 c->tie_list.p, c->tie_ctr.p, c->tie_cap, d_es);
-  c->launches++;
-  FGS_CUDA(cudaGetLastError());
+  if (!defer_ties) FGS_TRY(launch_es_wks_ties(c, d_rank16, d_sabs, G, C, d_es));
   return FGS_OK;
 }
 

@@ -102,6 +102,30 @@ def test_weighted_ks_weight_exponent(ctx, oracle, p_exp):
     assert rc == 0 and np.abs(got - want).max() <= ES_TOL
 
 
+@pytest.mark.parametrize("G", [11, 21, 64])
+def test_tiny_universe_structural_ties(ctx, oracle, G):
+    """few genes and sets of 1-4 members: es_pos = -es_neg exactly for many units
+    (a single gene at the median rank of an odd universe, symmetric pairs), with
+    p = 1 and p = 0, signed and abs scores.  The sign must be the reference's."""
+    rng = np.random.default_rng(G)
+    n, P = 12, 120
+    sets = [rng.choice(G, m, replace=False) + 1 for m in (1, 1, 1, 2, 2, 3, 4, 1, 2, 3, G - 1, G // 2)]
+    off, idx = oracle.csr(sets)
+    x = np.asfortranarray(rng.normal(size=(n, G)))
+    y = np.zeros((n, 1), dtype=np.int32); y[: n // 2] = 1
+    perm = synth.perm_matrix(n, P, seed=G + 1)
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    for p_exp in (1.0, 0.0):
+        for abs_flag in (False, True):
+            got = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm, p=p_exp, abs_flag=abs_flag)
+            rc, want = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, oracle.ES_WKS,
+                                        p=p_exp, abs_flag=abs_flag)
+            assert rc == 0
+            assert np.array_equal(np.isnan(got), np.isnan(want))
+            ok = ~np.isnan(want)
+            assert np.abs(got[ok] - want[ok]).max() <= ES_TOL, (p_exp, abs_flag)
+
+
 def test_tensor_scores_certified_ranks(ctx, oracle):
     """near ties under the tensor-core score path: duplicated genes (exact ties in
     the reference), a gene and its 10x copy (1 ulp apart in the reference,
