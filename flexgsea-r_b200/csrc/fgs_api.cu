@@ -173,7 +173,7 @@ static long long block_columns(fgs_ctx *c, long long C_total) {
   if (cb <= 0) {
     // the rank and ES kernels are persistent (a CTA per SM takes a column at a time): a
     // block that is a whole number of rounds over the SMs has no idle tail
-    cb = 2048;
+    cb = 4096;
     if (cb > cap) cb = cap;
     if (cb > c->num_sms) cb = ((cb + c->num_sms / 2) / c->num_sms) * c->num_sms;
     if (cb > cap) cb -= c->num_sms;
