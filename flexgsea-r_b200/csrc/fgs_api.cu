@@ -294,7 +294,7 @@ int fgs_destroy(fgs_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->x.release(); c->xc.release(); c->xtot.release(); c->cert_list.release(); c->cert_ctr.release();
-  c->cert_redo.release(); c->sort_redo.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release(); c->set_idx16.release(); c->sig_lut.release(); c->set_slow.release(); c->tie_list.release(); c->tie_ctr.release();
+  c->cert_redo.release(); c->sort_redo.release(); c->sort_glist.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release(); c->set_idx16.release(); c->sig_lut.release(); c->set_slow.release(); c->tie_list.release(); c->tie_ctr.release();
   for (auto &b : c->api_d) b.release();
   for (auto &b : c->api_i) b.release();
   c->api_l.release();

@@ -90,6 +90,7 @@ struct fgs_ctx {
   fgs::DevBuf<int2> cert_list;  // (column, gene) entries for exact recomputation
   fgs::DevBuf<int> cert_ctr;    // [0] epilogue count, [1] tie count
   fgs::DevBuf<int> cert_redo;   // [Cb]
+  fgs::DevBuf<uint16_t> sort_glist;  // [grid][Gp] gene lists of the score-range buckets (long columns)
   fgs::DevBuf<int> sort_redo;   // [Cb] columns the 32-bit sort hands to the 64-bit sort
   fgs::DevBuf<double> gene_sd;  // sd(x[,g]) for lm
   bool gene_sd_valid = false;

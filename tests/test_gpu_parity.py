@@ -539,9 +539,40 @@ def test_c2_full_nperm_properties(ctx):
     assert np.array_equal(hi, full[:, :, P // 2:])
 
 
+@pytest.mark.parametrize("G", [30000, 40000, 60000, 65534])
+def test_long_column_user_scores(ctx, oracle, G):
+    """columns too long for the on-chip sort in one piece (score-range buckets, each
+    sorted on chip): ranks bit-exact on user scores with heavy ties, -0.0, a value
+    shared by a third of the genes (a bucket that cannot fit: 64-bit fallback for
+    that column only) and plain continuous columns; force_sort64 agrees."""
+    rng = np.random.default_rng(G)
+    P = 5
+    sc = rng.normal(size=(G, 1, P))
+    sc[:, 0, 1] = np.round(sc[:, 0, 1], 2)                 # heavy ties
+    sc[rng.integers(0, G, G // 3), 0, 2] = 0.25            # one value for a third of the genes
+    sc[::7, 0, 3] = -0.0; sc[1::7, 0, 3] = 0.0
+    sc[:, 0, 4] = rng.normal(size=G) * 1e-3 + 1.0          # every gene inside a few key bins
+    S = 40
+    off, idx = synth.gene_sets_csr(G, S, (15, 300), "loguniform", seed=3)
+    ctx.set_gene_sets(off, idx)
+    got = ctx.es_from_scores(nat.ES_WEIGHTED_KS, sc)
+    _, grk = ctx.debug_last(P, G=G)
+    oracle.use_all_cores()
+    assert np.array_equal(grk, _ranks(oracle, sc[:, 0, :]))
+    rc, want = oracle.es_from_scores(oracle.ES_WKS, sc, off, idx)
+    assert rc == 0 and np.abs(got - want).max() <= ES_TOL
+    ctx.set_option("force_sort64", 1)
+    try:
+        got64 = ctx.es_from_scores(nat.ES_WEIGHTED_KS, sc)
+        _, grk64 = ctx.debug_last(P, G=G)
+    finally:
+        ctx.set_option("force_sort64", 0)
+    assert np.array_equal(grk, grk64) and np.array_equal(got, got64)
+
+
 def test_large_gene_count_paths(ctx, oracle):
-    """G > 32768 (configs[4] has 60,000 transcripts): ranks come from the 64-bit
-    global-memory sort and the ES kernel reads its weights from global memory."""
+    """G > 29696 (configs[4] has 60,000 transcripts): ranks come from the bucketed
+    on-chip sort and the ES kernel reads its weights from global memory."""
     G, n, S, P = 40000, 48, 120, 6
     off, idx = synth.gene_sets_csr(G, S, (15, 500), "loguniform", seed=7)
     x, y = synth.two_class(G, n, off, idx, seed=8)
