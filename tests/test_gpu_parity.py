@@ -218,15 +218,25 @@ def test_wide_sets_and_class_boundaries(ctx, oracle):
     assert np.abs(got - gen).max() <= ES_TOL
 
 
+@pytest.mark.parametrize("abs_flag", [False, True])
 @pytest.mark.parametrize("es_kind", ["maxmean", "mean"])
-def test_perm_null_mean_maxmean(ctx, oracle, es_kind):
-    x, y, perm, off, idx = _case(P=40)
+def test_perm_null_mean_maxmean(ctx, oracle, es_kind, abs_flag):
+    """two responses, sets of 1 .. 700 members (more than one 16-byte member block
+    per lane), an empty-ish tail (S % 4 != 0), signed and abs scores"""
+    G, n, P = 1500, 20, 40
+    rng = np.random.default_rng(17)
+    sizes = [1, 2, 7, 8, 9, 63, 64, 65, 700, 300, 33, 5, 120, 16, 17]
+    sets = [rng.choice(G, m, replace=False) + 1 for m in sizes] + [np.array([4, 4, 9, 4])]  # duplicates count
+    off, idx = oracle.csr(sets)
+    x, y = synth.two_class(G, n, seed=12)
+    y = np.column_stack([y[:, 0], rng.permutation(y[:, 0])])
+    perm = synth.perm_matrix(n, P, seed=13)
     ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
     k = nat.ES_MAXMEAN if es_kind == "maxmean" else nat.ES_MEAN
     ok = oracle.ES_MAXMEAN if es_kind == "maxmean" else oracle.ES_MEAN
-    got = ctx.perm_null(nat.SCORE_S2N, k, 40, perm=perm)
-    rc, want = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, ok)
-    assert rc == 0 and np.abs(got - want).max() <= ES_TOL
+    got = ctx.perm_null(nat.SCORE_S2N, k, P, perm=perm, abs_flag=abs_flag)
+    rc, want = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, ok, abs_flag=abs_flag)
+    assert rc == 0 and got.shape == want.shape and np.abs(got - want).max() <= ES_TOL
     assert np.array_equal(np.sign(got), np.sign(want))
 
 
