@@ -13,7 +13,7 @@
 // REGISTERS with a bitonic network on packed uint16 pairs (no shared-memory
 // scratch), and run the running sum as lane-local sums + one scan of the lane
 // totals.  Sets are handled in descending size in compile-time size classes
-// (8 lanes x {4, 8, 16, 32} ranks, 16 x 32, a whole warp x {32, 64}).
+// (8 lanes x {4, 8, 16, 32, 64} ranks, a whole warp x {32, 64}).
 //
 // Sets with duplicated members (R keeps them; a pad-free distinct-rank sort
 // cannot) or more than ES_MAX_SET members go through es_wks_generic_kernel, an
@@ -97,12 +97,18 @@ __device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[NB / 2], int la
       }
     } else {  // lane ^ (k / NB - 1), slots reversed: register NR-1-q, halves swapped
       const uint32_t hi_mask = 0u - ((lane / ((k / NB) >> 1)) & 1u);
-      uint32_t o[NR];
+      if constexpr (NR == 1) {
+        v[0] = minmax2_side(v[0], swap_halves(__shfl_xor_sync(0xffffffffu, v[0], (k / NB) - 1)), hi_mask);
+      } else {
 #pragma unroll
-      for (int q = 0; q < NR; q++)
-        o[q] = swap_halves(__shfl_xor_sync(0xffffffffu, v[NR - 1 - q], (k / NB) - 1));
-#pragma unroll
-      for (int q = 0; q < NR; q++) v[q] = minmax2_side(v[q], o[q], hi_mask);
+        for (int q = 0; q < NR / 2; q++) {  // registers q and NR-1-q exchange with each other's mirror
+          const uint32_t a = v[q], b = v[NR - 1 - q];
+          const uint32_t oa = swap_halves(__shfl_xor_sync(0xffffffffu, b, (k / NB) - 1));
+          const uint32_t ob = swap_halves(__shfl_xor_sync(0xffffffffu, a, (k / NB) - 1));
+          v[q] = minmax2_side(a, oa, hi_mask);
+          v[NR - 1 - q] = minmax2_side(b, ob, hi_mask);
+        }
+      }
     }
 #pragma unroll
     for (int j = k >> 2; j > 0; j >>= 1) {
@@ -317,20 +323,7 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
         else if (mmax <= 8 * 8) es = wks_sets<8, 8, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie);
         else if (mmax <= 8 * 16) es = wks_sets<8, 16, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie);
         else if (mmax <= 8 * 32) es = wks_sets<8, 32, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie);
-        else {  // 257 .. 512 members: sixteen lanes per set (32 ranks per lane), the quad as two pairs
-#pragma unroll 1
-          for (int h = 0; h < 2; h++) {
-            const int src = (2 * h + (lane >> 4)) * 8;
-            const int mi = __shfl_sync(0xffffffffu, m, src), zi = __shfl_sync(0xffffffffu, info.z, src);
-            const double igi = __shfl_sync(0xffffffffu, ig, src);
-            bool t2 = false;
-            const double e2 = wks_sets<16, 32, W_SMEM>(s_rank, wsrc, idx16, zi, mi, G, igi, lane & 15, t2);
-            // hand the result to the set's own eight lanes
-            const double back = __shfl_sync(0xffffffffu, e2, (seg & 1) * 16);
-            const bool tback = __shfl_sync(0xffffffffu, (int)t2, (seg & 1) * 16) != 0;
-            if ((seg >> 1) == h) { es = back; tie = tback; }
-          }
-        }
+        else es = wks_sets<8, 64, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie);  // 257 .. 512 members
         if (mine && ls == 0) {
           es_col[info.w] = es;
           if (tie) tie_push(tie_list, tie_ctr, tie_cap, (int)col, info.w);
