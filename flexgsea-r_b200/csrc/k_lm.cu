@@ -91,12 +91,21 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
                : "d"(a), "d"(b));
 }
 
+// 8-byte asynchronous copy global -> shared, zero-filled when `ok` is false
+__device__ __forceinline__ void lm_cp_async8(void *dst_smem, const void *src, bool ok) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int nbytes = ok ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(d), "l"(src), "r"(nbytes));
+}
+
 __global__ void __launch_bounds__(256)
 lm_gemm_kernel(const double *__restrict__ x, int n, int G, const double *__restrict__ B, long long C,
                const double *__restrict__ sd, int R, double *__restrict__ scores,
                int *__restrict__ flags) {
-  __shared__ double As[LM_BM][LM_BK + LM_PAD];  // [gene][k]
-  __shared__ double Bs[LM_BN][LM_BK + LM_PAD];  // [col][k]
+  // both operand tiles are double-buffered by cp.async: the next 16-sample slab lands while
+  // the tensor pipe works on this one
+  __shared__ __align__(16) double As[2][LM_BM][LM_BK + LM_PAD];  // [gene][k]
+  __shared__ __align__(16) double Bs[2][LM_BN][LM_BK + LM_PAD];  // [col][k]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g0 = blockIdx.x * LM_BM;
   const long long c0 = (long long)blockIdx.y * LM_BN;
@@ -108,30 +117,45 @@ lm_gemm_kernel(const double *__restrict__ x, int n, int G, const double *__restr
 #pragma unroll
     for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  for (int k0 = 0; k0 < n; k0 += LM_BK) {
-    // 64 x 16 doubles per tile = 1024 elements, 4 per thread; k is contiguous in
-    // both sources
-    for (int e = tid; e < LM_BM * LM_BK; e += 256) {
+  // 64 x 16 doubles per tile = 1024 elements, 4 per thread and matrix; k is contiguous in
+  // both sources
+  auto stage = [&](int buf, int k0) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int e = tid + u * 256;
       const int r = e / LM_BK, k = e % LM_BK;
       const int g = g0 + r;
-      As[r][k] = (g < G && k0 + k < n) ? x[(size_t)g * n + k0 + k] : 0.0;
       const long long col = c0 + r;
-      Bs[r][k] = (col < C && k0 + k < n) ? B[(size_t)col * n + k0 + k] : 0.0;
+      const bool ka = k0 + k < n;
+      lm_cp_async8(&As[buf][r][k], x + (size_t)(g < G ? g : 0) * n + (ka ? k0 + k : 0), g < G && ka);
+      lm_cp_async8(&Bs[buf][r][k], B + (size_t)(col < C ? col : 0) * n + (ka ? k0 + k : 0), col < C && ka);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  const int ntile = (n + LM_BK - 1) / LM_BK;
+  stage(0, 0);
+  for (int t = 0; t < ntile; t++) {
+    if (t + 1 < ntile) {
+      stage((t + 1) & 1, (t + 1) * LM_BK);
+      asm volatile("cp.async.wait_group 1;\n" ::);
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::);
     }
     __syncthreads();
+    const int buf = t & 1;
 #pragma unroll
     for (int kk = 0; kk < LM_BK; kk += 4) {
       double a[4], b[2];
 #pragma unroll
-      for (int i = 0; i < 4; i++) a[i] = As[wm + i * 8 + grp][kk + tig];
+      for (int i = 0; i < 4; i++) a[i] = As[buf][wm + i * 8 + grp][kk + tig];
 #pragma unroll
-      for (int j = 0; j < 2; j++) b[j] = Bs[wn + j * 8 + grp][kk + tig];
+      for (int j = 0; j < 2; j++) b[j] = Bs[buf][wn + j * 8 + grp][kk + tig];
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 2; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
-    __syncthreads();
+    __syncthreads();  // the buffer is refilled two iterations later
   }
   // accumulator fragment: row = grp, cols = 2 * tig + {0, 1}
 #pragma unroll
