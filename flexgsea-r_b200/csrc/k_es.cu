@@ -352,14 +352,34 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
 
 // Members of every set as uint16 gene ids, in processing order, each set in
 // 16-byte blocks of eight padded with the pad gene G (a warp per set).
+//
+// The ES kernels read these lists eight lanes at a time with a stride of eight
+// members (lane l takes block l of a 64-member chunk), and use the gene id as an
+// index into shared memory.  The order of a set's members is free (sums and
+// sorts do not care), so every 64-member chunk is stored sorted by gene id mod 16:
+// members eight apart then fall into different bank pairs of the fp64 score
+// column (mean / maxmean kernel) instead of colliding at random.
 __global__ void build_idx16_kernel(const int4 *__restrict__ set_info, const int *__restrict__ set_idx,
                                    int S, int G, uint16_t *__restrict__ idx16) {
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (k >= S) return;
   const int4 info = set_info[k];
   const int m = info.y & 0x7fffffff, mpad = (m + 7) & ~7;
-  for (int j = lane; j < mpad; j += 32)
-    idx16[(size_t)info.z * 8 + j] = (uint16_t)(j < m ? set_idx[info.x + j] : G);
+  uint16_t *out = idx16 + (size_t)info.z * 8;
+  for (int c0 = 0; c0 < mpad; c0 += 64) {
+    // two members per lane; key = (class, position) is unique, pads sort last
+    const int j0 = c0 + lane, j1 = c0 + 32 + lane;
+    const int g0 = j0 < m ? set_idx[info.x + j0] : G, g1 = j1 < m ? set_idx[info.x + j1] : G;
+    const int key0 = ((j0 < m ? (g0 & 15) : 16) << 8) | lane, key1 = ((j1 < m ? (g1 & 15) : 16) << 8) | (32 + lane);
+    int p0 = 0, p1 = 0;
+    for (int f = 0; f < 32; f++) {
+      const int a = __shfl_sync(0xffffffffu, key0, f), b = __shfl_sync(0xffffffffu, key1, f);
+      p0 += (a < key0) + (b < key0);
+      p1 += (a < key1) + (b < key1);
+    }
+    if (c0 + p0 < mpad) out[c0 + p0] = (uint16_t)g0;
+    if (c0 + p1 < mpad) out[c0 + p1] = (uint16_t)g1;
+  }
 }
 
 // Order-free weighted KS for sets the bitonic kernel cannot take (duplicates,
