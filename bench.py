@@ -278,8 +278,8 @@ def run_gpu(args):
     dl = roof[dom]
     per_launch_bytes = dl["alg_bytes_per_step"] / dl["launches_per_step"]
     per_launch_ms = dl["ms_per_step"] / dl["launches_per_step"]
-    roofline = {"bound": "hbm", "kernel": {"score": "s2n_kernel", "rank": "sort_rank_kernel",
-                                            "es": "es_wks_kernel" if es_kind == nat.ES_WEIGHTED_KS else "es_mean_kernel"}[dom],
+    roofline = {"bound": "hbm", "kernel": {"score": "s2n_mma_kernel", "rank": "sort_rank32_kernel",
+                                            "es": "es_wks_kernel" if es_kind == nat.ES_WEIGHTED_KS else "es_mean_smem_kernel"}[dom],
                 "achieved": dl["achieved_gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": dl["achieved_gbs"] / peak, "traffic": None,
                 "alg_bytes_per_launch": per_launch_bytes, "launch_ms": per_launch_ms,
@@ -291,6 +291,8 @@ def run_gpu(args):
             if t:
                 roofline["traffic"] = t["dram_bytes_per_column"] * cols / dl["launches_per_step"]
                 roofline["traffic_source"] = t["source"]
+                if t.get("pipes"):  # what actually binds the kernel (ncu, same capture): not DRAM
+                    roofline["pipes_pct_of_peak"] = t["pipes"]
         except Exception:
             pass
 

@@ -53,6 +53,19 @@ for rep in reps:
         seen[short] = dram
         traffic[short] = {"dram_bytes_per_column": dram / cols_per_launch, "columns_in_capture": cols_per_launch,
                           "source": os.path.basename(rep) + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}
+        pipes = {}
+        for key, label in (("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu_pipe_pct"),
+                           ("l1tex__throughput.avg.pct_of_peak_sustained_active", "l1_smem_pct"),
+                           ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_pct"),
+                           ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
+                           ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64_pipe_pct"),
+                           ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct")):
+            if key in hdr:
+                try:
+                    pipes[label] = round(float(r[hdr.index(key)]), 1)
+                except ValueError:
+                    pass
+        traffic[short]["pipes"] = pipes
 open(out_md, "w").write("\n".join(lines) + "\n")
 json.dump(traffic, open(tpath, "w"), indent=1)
 print("wrote", out_md, "and", tpath)
