@@ -203,7 +203,8 @@ static int rank_and_es(fgs_ctx *c, int es_kind, double p_exp, int abs_flag, long
       tc.rel_tol = 1e-10; tc.abs_tol = 1e-12;  // >= 50x the contraction-vs-reference error bound (k_s2n_mma.cu)
       FGS_TRY(launch_sort(c, c->scores.p, G, Cb, abs_flag, p_exp, c->rank16.p, c->sabs.p, nullptr, &tc));
       FGS_TRY(launch_s2n_exact_entries(c, c->x.p, c->n, G, c->cur_labels, c->n1n2.p, c->s2n_R, tc.list,
-                                       tc.count, c->opt_cert_cap, c->scores.p, c->flags.p + c->cur_flag0));
+                                       tc.count, c->opt_cert_cap, c->scores.p, c->flags.p + c->cur_flag0,
+                                       /*after_patch=*/true));
       FGS_TRY(launch_sort(c, c->scores.p, G, Cb, abs_flag, p_exp, c->rank16.p, c->sabs.p, c->cert_redo.p,
                           nullptr));
     } else {
@@ -221,7 +222,8 @@ static int rank_and_es(fgs_ctx *c, int es_kind, double p_exp, int abs_flag, long
       int *cnt = c->cert_ctr.p + 2;
       FGS_TRY(launch_tie_members(c, list, cnt, c->opt_cert_cap, c->flags.p + (c->flags.n - 1)));
       FGS_TRY(launch_s2n_exact_entries(c, c->x.p, c->n, G, c->cur_labels, c->n1n2.p, c->s2n_R, list, cnt,
-                                       c->opt_cert_cap, c->scores.p, c->flags.p + c->cur_flag0));
+                                       c->opt_cert_cap, c->scores.p, c->flags.p + c->cur_flag0,
+                                       /*after_patch=*/true));
       FGS_TRY(launch_tie_refresh_weights(c, list, cnt, c->opt_cert_cap, c->scores.p, c->rank16.p, c->sabs.p,
                                          G, p_exp));
       FGS_TRY(launch_es_wks_ties(c, c->rank16.p, c->sabs.p, G, Cb, d_es));

@@ -191,7 +191,7 @@ int launch_s2n_mma(fgs_ctx *c, const double *d_xc, const double *d_tot, int n, i
                    int2 *d_list, int *d_count, int cap);
 int launch_s2n_exact_entries(fgs_ctx *c, const double *d_x, int n, int G, const uint32_t *d_labels,
                              const int *d_n1n2, int R, const int2 *d_list, const int *d_count, int cap,
-                             double *d_scores, int *d_flags);
+                             double *d_scores, int *d_flags, bool after_patch = false);
 // K4 / K5
 int launch_prep_sets(fgs_ctx *c, int S, int *h_status, unsigned char *h_slow);
 int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
@@ -222,6 +222,16 @@ int launch_sig_finish(fgs_ctx *c, const double *d_nes, const long long *d_null_c
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 // row pitch (elements) of the per-column rank16 / sabs arrays: 16-byte aligned rows
+// hit weight |s|^p (R/flexgsea.R:819).  R's `^` returns x * x for p == 2 and calls the C
+// library's pow otherwise; CUDA's pow is good to 2 ulp, glibc's to ~0.5, so only the
+// exponents with an exact form (0, 1, 2) give bit-identical weights -- enough for the
+// result everywhere (ES tolerance 1e-10) except the sign at an exact structural tie.
+__device__ __forceinline__ double hit_weight(double a, double p_exp) {
+  if (p_exp == 1.0) return a;
+  if (p_exp == 2.0) return __dmul_rn(a, a);
+  return pow(a, p_exp);
+}
+
 // largest set the in-register weighted-KS kernel takes (64 ranks per lane on a whole warp)
 constexpr int ES_MAX_SET = 2048;
 __host__ __device__ inline size_t pitch_of(int G) { return ((size_t)G + 7) & ~(size_t)7; }

@@ -404,6 +404,7 @@ es_wks_generic_kernel(const uint16_t *__restrict__ rank16, const double *__restr
   const double W = warp_sum(lsum);
   const double invW = 1.0 / W, invGm = 1.0 / (double)(G - m);
   double mx = -INFINITY, mn = INFINITY;
+  bool has_nan = false;
   for (int j = lane; j < m; j += 32) {
     const int rj = rk[set_idx[off + j]];
     const double wj = sa[rj - 1];
@@ -413,16 +414,21 @@ es_wks_generic_kernel(const uint16_t *__restrict__ rank16, const double *__restr
       const int rt = rk[set_idx[off + t]];
       if (rt < rj || (rt == rj && t <= j)) { kord++; cum += sa[rt - 1]; }
     }
+    // G == m (possible with FEWER than G distinct genes when members repeat): the
+    // reference divides by zero, NaN where r == k and +-Inf elsewhere, and max() / min()
+    // return NaN as soon as one element is; 0 * Inf and n * Inf behave the same here
     const double ps = cum * invW - (double)(rj - kord) * invGm;
     const double ng = ps - wj * invW;
+    has_nan |= isnan(ps) || isnan(ng);
     mx = fmax(mx, ps);
     mn = fmin(mn, ng);
   }
   mx = warp_max(mx);
   mn = warp_min(mn);
+  has_nan = __any_sync(0xffffffffu, has_nan);
   if (lane == 0) {
     double es = (mx > -mn) ? mx : mn;
-    const bool degenerate = W == 0.0 || m == G || m == 0;
+    const bool degenerate = W == 0.0 || m == 0 || has_nan;
     if (degenerate) es = nan("");
     es_out[(size_t)col * S + s] = es;
     if (!degenerate && fabs(mx + mn) <= ES_TIE_REL * fmax(fabs(mx), fabs(mn)))
@@ -696,7 +702,7 @@ __global__ void tie_refresh_weights_kernel(const int2 *__restrict__ list, const 
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int col = list[i].x, g = list[i].y;
     double w = fabs(scores[(size_t)col * G + g]);
-    if (p_exp != 1.0) w = pow(w, p_exp);
+    w = hit_weight(w, p_exp);
     sabs[(size_t)col * Gp + rank16[(size_t)col * Gp + g] - 1] = w;
   }
 }

@@ -187,7 +187,11 @@ s2n_mma_kernel(const double *__restrict__ xc, const double *__restrict__ tot, in
         const double v1 = e1 - m1 * m1, v2 = e2 - m2 * m2;  // population variances
         const double coef = (m1 - m2) / (sqrt(fmax(v1, 0.0)) + sqrt(fmax(v2, 0.0)));
         scores[(size_t)col * G + g] = coef;
-        const bool shaky = !(v1 * S2N_CANCEL_LIMIT > e1) || !(v2 * S2N_CANCEL_LIMIT > e2) || !isfinite(coef);
+        // (a score this close to zero is either an exact zero in the reference -- equal class
+        // means, e.g. tied data -- or lost to cancellation in m1 - m2: an exact zero must stay
+        // one, it is the weight 0 of the weighted KS)
+        const bool shaky = !(v1 * S2N_CANCEL_LIMIT > e1) || !(v2 * S2N_CANCEL_LIMIT > e2) || !isfinite(coef) ||
+                           fabs(coef) <= 1e-9;
         if (shaky) push_entry(list, count, cap, overflow, (int)col, g);
       }
   }
@@ -213,7 +217,8 @@ __global__ void s2n_exact_entries_kernel(const double *__restrict__ x, int n, in
                                          const uint32_t *__restrict__ labels,
                                          const int *__restrict__ n1n2, int R, int W,
                                          const int2 *__restrict__ list, const int *__restrict__ count,
-                                         int cap, double *__restrict__ scores, int *__restrict__ flags) {
+                                         int cap, double *__restrict__ scores, int *__restrict__ flags,
+                                         int after_patch) {
   int total = *count;
   if (total > cap) total = cap;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -240,6 +245,11 @@ __global__ void s2n_exact_entries_kernel(const double *__restrict__ x, int n, in
     }
     const double coef = __ddiv_rn(__dsub_rn(mean1, mean2),
                                   __dadd_rn(__dsqrt_rn(__ddiv_rn(s1, dn1)), __dsqrt_rn(__ddiv_rn(s2, dn2))));
+    // +-Inf is replaced by 1.1 * the permutation's largest / smallest finite score
+    // (s2n_patch_kernel, R/flexgsea.R:715-716) right after the first scoring pass.  An
+    // entry recomputed later (rank certification, tied ES units) that is infinite has
+    // been patched then: its patched value stays
+    if (after_patch && isinf(coef)) continue;
     scores[(size_t)col * G + g] = coef;
     if (!isfinite(coef)) {
       const int bit = isnan(coef) ? FLAG_NAN : (coef > 0 ? FLAG_POS_INF : FLAG_NEG_INF);
@@ -250,10 +260,10 @@ __global__ void s2n_exact_entries_kernel(const double *__restrict__ x, int n, in
 
 int launch_s2n_exact_entries(fgs_ctx *c, const double *d_x, int n, int G, const uint32_t *d_labels,
                              const int *d_n1n2, int R, const int2 *d_list, const int *d_count, int cap,
-                             double *d_scores, int *d_flags) {
+                             double *d_scores, int *d_flags, bool after_patch) {
   s2n_exact_entries_kernel<<<c->num_sms * 4, 128, 0, c->stream>>>(d_x, n, G, d_labels, d_n1n2, R,
                                                                   (n + 31) / 32, d_list, d_count, cap,
-                                                                  d_scores, d_flags);
+                                                                  d_scores, d_flags, after_patch ? 1 : 0);
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   return FGS_OK;

@@ -165,7 +165,7 @@ sort_rank_kernel(const double *__restrict__ scores, int G, long long C, int abs_
     for (int q = tid; q < G; q += SORT_THREADS) {
       const double sq = key_desc_to_score(kin[q]);
       double w = fabs(sq);
-      if (p_exp != 1.0) w = pow(w, p_exp);
+      w = hit_weight(w, p_exp);
       sa[q] = w;
       rk[iin[q]] = (uint16_t)(q + 1);
       if (tc.list && q + 1 < G) certify_pair(tc, col, sq, key_desc_to_score(kin[q + 1]), iin[q], iin[q + 1]);
@@ -365,7 +365,7 @@ sort_rank32_kernel(const double *__restrict__ scores, int G, long long C, int ab
           double sq = sv[u];
           if (abs_flag) sq = fabs(sq);
           double w = fabs(sq);
-          if (p_exp != 1.0) w = pow(w, p_exp);
+          w = hit_weight(w, p_exp);
           sa[q] = w;
           // a neighbour whose 32-bit key differs by >= 2 is > 1e-6 away in relative
           // terms; only closer keys (or scores so small that the absolute tolerance
@@ -601,7 +601,7 @@ sort_rank_big_kernel(const double *__restrict__ scores, int G, long long C, int 
           double sq = sv[u];
           if (abs_flag) sq = fabs(sq);
           double w = fabs(sq);
-          if (p_exp != 1.0) w = pow(w, p_exp);
+          w = hit_weight(w, p_exp);
           sa[base + q] = w;
           rk[g] = (uint16_t)(base + q + 1);
           if (tc.list && q + 1 < nb && (skey[q + 1] - skey[q] <= 1u || fabs(sq) <= 1e-5)) {

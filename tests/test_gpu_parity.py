@@ -126,6 +126,22 @@ def test_tiny_universe_structural_ties(ctx, oracle, G):
             assert np.abs(got[ok] - want[ok]).max() <= ES_TOL, (p_exp, abs_flag)
 
 
+def test_random_small_shapes(ctx):
+    """2 200 random small problems (profiles/stress_parity.py: 7-3000 genes, 4-40
+    samples, sets with duplicates, tied / rounded data, weight exponents 0 / 1 / 2,
+    abs, mean / maxmean / weighted KS, both score modes) against the oracle, NaN
+    pattern included.  This sweep found, and now pins: exact-zero scores that the
+    tensor path made 1e-17 (weight 0 -> NaN ES in the reference), +-Inf scores
+    re-certified after the 1.1 * max patch, G == m reached through duplicated
+    members, |s|^2 as s * s."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "stress_parity", os.path.join(os.path.dirname(__file__), "..", "profiles", "stress_parity.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(2200, 7, ctx) == 0
+
+
 def test_tensor_scores_certified_ranks(ctx, oracle):
     """near ties under the tensor-core score path: duplicated genes (exact ties in
     the reference), a gene and its 10x copy (1 ulp apart in the reference,
