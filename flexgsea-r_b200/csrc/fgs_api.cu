@@ -296,7 +296,7 @@ int fgs_destroy(fgs_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->x.release(); c->xc.release(); c->xtot.release(); c->cert_list.release(); c->cert_ctr.release();
-  c->cert_redo.release(); c->sort_redo.release(); c->sort_glist.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release(); c->set_idx16.release(); c->sig_lut.release(); c->set_slow.release(); c->tie_list.release(); c->tie_ctr.release();
+  c->cert_redo.release(); c->sort_redo.release(); c->sort_glist.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release(); c->set_idx16.release(); c->sig_lut.release(); c->set_slow.release(); c->tie_list.release(); c->tie_ctr.release(); c->obs_es.release();
   for (auto &b : c->api_d) b.release();
   for (auto &b : c->api_i) b.release();
   c->api_l.release();
@@ -345,6 +345,7 @@ int fgs_set_x(fgs_ctx *c, const double *x, int n_sample, int n_gene) {
   FGS_TRY(c->x.ensure((size_t)n_sample * n_gene));
   FGS_TRY(h2d(c, c->x.p, x, (size_t)n_sample * n_gene));
   c->n = n_sample; c->G = n_gene;
+  c->obs_valid = false;
   c->gene_sd_valid = false;
   c->xc_valid = false;
   FGS_TRY(sync(c));
@@ -397,6 +398,7 @@ int fgs_set_gene_sets(fgs_ctx *c, const int *offsets, const int *index, int n_se
   FGS_TRY(sync(c));
   c->S = n_sets; c->nnz = nnz; c->max_set = status[1]; c->n_slow = (int)slow_ids.size();
   c->invgm_G = -1;
+  c->obs_valid = false;
   c->h_set_off.assign(offsets, offsets + n_sets + 1);
   return FGS_OK;
 }
@@ -418,6 +420,7 @@ int fgs_set_response_s2n(fgs_ctx *c, const int *y_bin, int n_sample, int n_respo
   FGS_TRY(h2d(c, c->n1n2.p, nn.data(), nn.size()));
   FGS_TRY(sync(c));
   c->s2n_R = n_response;
+  c->obs_valid = false;
   c->s2n_has_na = c->s2n_has_na_pending;
   if (c->n && c->n != n_sample) { /* checked again at run time */ }
   return FGS_OK;
@@ -437,6 +440,7 @@ int fgs_set_response_lm(fgs_ctx *c, const double *design, int n_sample, int n_co
   FGS_TRY(h2d(c, c->lm_H.p, H.data() + (has_intercept ? n_sample : 0), (size_t)R * n_sample));
   FGS_TRY(sync(c));
   c->lm_q = n_col; c->lm_R = R; c->lm_icpt = has_intercept ? 1 : 0;
+  c->obs_valid = false;
   c->h_design.swap(D);
   return FGS_OK;
 }
@@ -570,6 +574,11 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
   for (int i = 0; i < 5; i++) c->last_launches[i] = 0;
   FGS_TRY(c->es_null.ensure(std::max<size_t>((size_t)S * R * P, 1)));
   c->null_S = S; c->null_R = R; c->null_P = P;
+  // the observed ES of this problem, if fgs_observed_es made one: null units that come out
+  // within rounding of it are redone in the reference's arithmetic (see es_wks_tie_kernel)
+  c->cur_obs = (es_kind == FGS_ES_WEIGHTED_KS && c->obs_valid && c->obs_S == S && c->obs_R == R) ? c->obs_es.p : nullptr;
+  c->cur_obs_R = R;
+  c->null_exact_near_obs = c->cur_obs != nullptr;
   if (P == 0) return FGS_OK;
   FGS_TRY(flags_reset(c, P));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -646,6 +655,9 @@ int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scor
   auto body = [&]() -> int {
     FGS_TRY(c->es_null.ensure(std::max<size_t>((size_t)S * C, 1)));
     c->null_S = S; c->null_R = R; c->null_P = P;
+    c->cur_obs = (es_kind == FGS_ES_WEIGHTED_KS && c->obs_valid && c->obs_S == S && c->obs_R == R) ? c->obs_es.p : nullptr;
+    c->cur_obs_R = R;
+    c->null_exact_near_obs = c->cur_obs != nullptr;
     if (C == 0) return FGS_OK;
     FGS_TRY(flags_reset(c, C));
     FGS_CUDA(cudaEventRecord(c->ev[0], c->stream));
@@ -708,6 +720,7 @@ int fgs_set_null(fgs_ctx *c, const double *es_null, int n_sets, int n_response, 
   FGS_TRY(h2d(c, c->es_null.p, es_null, len));
   FGS_TRY(sync(c));
   c->null_S = n_sets; c->null_R = n_response; c->null_P = n_perm;
+  c->null_exact_near_obs = false;  // a null made elsewhere: values within rounding of the observed ES count as equal
   return FGS_OK;
 }
 
@@ -738,6 +751,9 @@ int fgs_observed_es(fgs_ctx *c, int es_kind, double p_exp, const double *scores,
       FGS_TRY(launch_sort(c, c->scores.p, G, R, 0, p_exp, c->rank16.p, c->sabs.p));
       FGS_TRY(launch_observed_wks(c, c->rank16.p, c->sabs.p, G, R, d_es.p, d_mea.p, d_lep.p, d_at.p,
                                   d_pos.p, d_neg.p, d_lf.p, d_lc.p));
+      FGS_TRY(c->obs_es.ensure(SR));
+      FGS_CUDA(cudaMemcpyAsync(c->obs_es.p, d_es.p, SR * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      c->obs_S = S; c->obs_R = R; c->obs_valid = true;
       c->last_cols = R; c->last_G = G;
       FGS_TRY(d2h(c, max_es_at, d_mea.p, SR)); FGS_TRY(d2h(c, le_prop, d_lep.p, SR));
       FGS_TRY(d2h(c, le_first, d_lf.p, SR)); FGS_TRY(d2h(c, le_count, d_lc.p, SR));

@@ -106,6 +106,14 @@ struct fgs_ctx {
   // "slow" = duplicated members or more than ES_MAX_SET members (order-free kernel)
   fgs::DevBuf<int4> set_info;
   fgs::DevBuf<double> set_invgm;   // [S] 1 / (G - m), processing order
+  // observed ES of the last fgs_observed_es (weighted KS): null units that land within
+  // rounding of it are recomputed in the reference's operation order (es_wks_tie_kernel)
+  fgs::DevBuf<double> obs_es;      // [S x R]
+  int obs_S = 0, obs_R = 0;
+  bool obs_valid = false;
+  const double *cur_obs = nullptr;   // set by rank_and_es for the ES launches of the current call
+  int cur_obs_R = 1;
+  bool null_exact_near_obs = false;  // the resident null was made with that treatment
   fgs::DevBuf<int2> tie_list;      // (column, set) units whose es_pos and -es_neg tied: redone exactly
   fgs::DevBuf<int> tie_ctr;
   int tie_cap = 0;

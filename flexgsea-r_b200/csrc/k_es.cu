@@ -151,6 +151,15 @@ __device__ __forceinline__ double warp_max_exact(double x) {
   return __hiloint2double((int)(mh ^ (inv | 0x80000000u)), (int)(ml ^ inv));
 }
 
+// a null ES within rounding of the set's observed ES (label-preserving permutations,
+// small universes): whether the two compare equal is the reference's rounding, so the
+// unit is redone exactly like a tied one
+__device__ __forceinline__ bool near_observed(const double *__restrict__ obs, int S, int R, long long col,
+                                              int set_id, double es) {
+  if (!obs) return false;
+  const double e = __ldg(obs + (size_t)(col % R) * S + set_id);
+  return fabs(es - e) <= 1e-9 * fabs(e);
+}
 constexpr double ES_TIE_REL = 1e-9;  // |es_pos + es_neg| below this fraction of their size: redo exactly
 __device__ __forceinline__ void tie_push(int2 *__restrict__ list, int *__restrict__ ctr, int cap, int col,
                                          int set_id) {
@@ -275,7 +284,8 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
 es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sabs, int G,
               long long C, const int4 *__restrict__ set_info, const uint16_t *__restrict__ idx16,
               const double *__restrict__ set_invgm, int S, double *__restrict__ es_out,
-              int2 *__restrict__ tie_list, int *__restrict__ tie_ctr, int tie_cap) {
+              int2 *__restrict__ tie_list, int *__restrict__ tie_ctr, int tie_cap,
+              const double *__restrict__ obs, int R) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const size_t Gp = pitch_of(G);
@@ -326,7 +336,7 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
         else es = wks_sets<8, 64, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie);  // 257 .. 512 members
         if (mine && ls == 0) {
           es_col[info.w] = es;
-          if (tie) tie_push(tie_list, tie_ctr, tie_cap, (int)col, info.w);
+          if (tie || near_observed(obs, S, R, col, info.w, es)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, info.w);
         }
       } else {  // a quad with a set of 513 .. ES_MAX_SET members: one set at a time on the whole warp
 #pragma unroll 1
@@ -342,7 +352,7 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
           else es = wks_sets<32, 64, W_SMEM>(s_rank, wsrc, idx16, zi, mi, G, igi, lane, tie);
           if (lane == 0) {
             es_col[wi] = es;
-            if (tie) tie_push(tie_list, tie_ctr, tie_cap, (int)col, wi);
+            if (tie || near_observed(obs, S, R, col, wi, es)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, wi);
           }
         }
       }
@@ -389,7 +399,8 @@ __global__ void __launch_bounds__(256)
 es_wks_generic_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sabs, int G,
                       long long C, const int *__restrict__ set_off, const int *__restrict__ set_idx,
                       const int *__restrict__ set_ids, int n_ids, int S, double *__restrict__ es_out,
-                      int2 *__restrict__ tie_list, int *__restrict__ tie_ctr, int tie_cap) {
+                      int2 *__restrict__ tie_list, int *__restrict__ tie_ctr, int tie_cap,
+                      const double *__restrict__ obs, int R) {
   const int lane = threadIdx.x & 31;
   const long long unit = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (unit >= (long long)n_ids * C) return;
@@ -431,7 +442,7 @@ es_wks_generic_kernel(const uint16_t *__restrict__ rank16, const double *__restr
     const bool degenerate = W == 0.0 || m == 0 || has_nan;
     if (degenerate) es = nan("");
     es_out[(size_t)col * S + s] = es;
-    if (!degenerate && fabs(mx + mn) <= ES_TIE_REL * fmax(fabs(mx), fabs(mn)))
+    if (!degenerate && (fabs(mx + mn) <= ES_TIE_REL * fmax(fabs(mx), fabs(mn)) || near_observed(obs, S, R, col, s, es)))
       tie_push(tie_list, tie_ctr, tie_cap, (int)col, s);
   }
 }
@@ -550,7 +561,7 @@ int launch_es_wks_generic(fgs_ctx *c, const uint16_t *d_rank16, const double *d_
   if (blocks > 0x7fffffffLL) { set_error("too many (set, column) units"); return FGS_ERR_ARG; }
   es_wks_generic_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(
       d_rank16, d_sabs, G, C, c->set_off.p, c->set_idx.p, d_set_ids, n_ids, c->S, d_es,
-      c->tie_list.p, c->tie_ctr.p, c->tie_cap);
+      c->tie_list.p, c->tie_ctr.p, c->tie_cap, c->cur_obs, c->cur_obs_R);
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   return FGS_OK;
@@ -646,13 +657,13 @@ static int launch_es_wks_inner(fgs_ctx *c, const uint16_t *d_rank16, const doubl
     FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx16.p,
                                              c->set_invgm.p, c->S, d_es, c->tie_list.p, c->tie_ctr.p,
-                                             c->tie_cap);
+                                             c->tie_cap, c->cur_obs, c->cur_obs_R);
   } else {
     auto k = es_wks_kernel<false>;
     FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx16.p,
                                              c->set_invgm.p, c->S, d_es, c->tie_list.p, c->tie_ctr.p,
-                                             c->tie_cap);
+                                             c->tie_cap, c->cur_obs, c->cur_obs_R);
   }
   c->launches++;
   FGS_CUDA(cudaGetLastError());

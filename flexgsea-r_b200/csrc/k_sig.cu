@@ -37,15 +37,17 @@ __device__ __forceinline__ double dd_div_n(dd a, double n) {
   return q + r / n;
 }
 
-// A null ES within rounding of the set's observed ES is taken as equal to it.  They
-// come from permutations that reproduce the observed labelling (common when there
-// are few samples); the reference computes both with the same code, so there they
-// are bit-identical and its `<=` / `>=` / `>` counts see a tie.  Here the observed ES
-// is made by the exact kernel and the null by the tensor-core / in-register path,
-// which agree to ~1e-13 only.
+// A null ES within rounding of the set's observed ES.  Such values come from
+// permutations that reproduce the observed labelling (common with few samples) or,
+// in small gene universes, from the few values the statistic can take; the reference
+// computes the observed and the null ES with the same code, so whether they compare
+// equal is decided by ITS rounding.  When the observed ES was known during the null
+// loop (fgs_observed_es was called first, as flexgsea() does), the ES kernels
+// recomputed every such unit in the reference's operation order and nothing is done
+// here (snap_rel = 0).  Otherwise the null value is taken as equal to the observed one.
 constexpr double SIG_SNAP_REL = 1e-11;
-__device__ __forceinline__ double snap_to_observed(double v, double e) {
-  return fabs(v - e) <= SIG_SNAP_REL * fabs(e) ? e : v;
+__device__ __forceinline__ double snap_to_observed(double v, double e, double snap_rel) {
+  return fabs(v - e) <= snap_rel * fabs(e) ? e : v;
 }
 
 constexpr int SIG_NF = 4;  // sums per set: pos hi, pos lo, neg hi, neg lo
@@ -55,7 +57,7 @@ constexpr int SIG_NC = 6;  // counts per set
 __global__ void __launch_bounds__(128)
 sig_partial_kernel(const double *__restrict__ null, int S, int R, int P, int resp,
                    const double *__restrict__ es, int split_p, int abs_flag, int chunk_len,
-                   double *__restrict__ psums /* [nchunk][S][4] */,
+                   double snap_rel, double *__restrict__ psums /* [nchunk][S][4] */,
                    long long *__restrict__ pcounts /* [nchunk][S][6] */) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
@@ -68,7 +70,7 @@ sig_partial_kernel(const double *__restrict__ null, int S, int R, int P, int res
   const double *base = null + (size_t)s + (size_t)S * resp;
   const size_t stride = (size_t)S * R;
   for (int p = p0; p < p1; p++) {
-    const double v = snap_to_observed(base[stride * p], e);
+    const double v = snap_to_observed(base[stride * p], e, snap_rel);
     if (v >= 0.0) { c0++; sp = dd_add_d(sp, v); }
     if (v < 0.0) { c1++; sn = dd_add_d(sn, v); }
     if (v <= 0.0) c2++;
@@ -119,7 +121,9 @@ int launch_sig_stage1(fgs_ctx *c, const double *d_null, int S, int R, int P, int
   FGS_TRY(c->sig_i.ensure((size_t)nchunk * S * SIG_NC));
   dim3 grid(ceil_div(S, 128), nchunk);
   sig_partial_kernel<<<grid, 128, 0, c->stream>>>(d_null, S, R, P, response, d_es, split_p,
-                                                  abs_flag, chunk_len, c->sig_d.p, c->sig_i.p);
+                                                  abs_flag, chunk_len,
+                                                  c->null_exact_near_obs ? 0.0 : SIG_SNAP_REL, c->sig_d.p,
+                                                  c->sig_i.p);
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   sig_combine_kernel<<<ceil_div(S, 128), 128, 0, c->stream>>>(c->sig_d.p, c->sig_i.p, S, nchunk,
@@ -285,7 +289,8 @@ fdr_count_kernel(const double *__restrict__ null, int S, int R, int P, int resp,
                  const double *__restrict__ es, const double *__restrict__ mpos,
                  const double *__restrict__ mneg,
                  const double *__restrict__ t1, int n1, const double *__restrict__ t2, int n2,
-                 const int *__restrict__ lut_g, int chunk_len, unsigned long long *__restrict__ hist1,
+                 const int *__restrict__ lut_g, int chunk_len, double snap_rel,
+                 unsigned long long *__restrict__ hist1,
                  unsigned long long *__restrict__ hist2, unsigned long long *__restrict__ glob) {
   extern __shared__ __align__(16) unsigned char smem[];
   double *st1 = (double *)smem;
@@ -317,7 +322,7 @@ fdr_count_kernel(const double *__restrict__ null, int S, int R, int P, int resp,
     for (int pb = p0; pb < p1; pb += U) {
       double v[U];
 #pragma unroll
-      for (int u = 0; u < U; u++) v[u] = (pb + u < p1) ? snap_to_observed(base[stride * (pb + u)], e) : nan("");
+      for (int u = 0; u < U; u++) v[u] = (pb + u < p1) ? snap_to_observed(base[stride * (pb + u)], e, snap_rel) : nan("");
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const double nv = abs_flag ? v[u] / mp : v[u] / (v[u] >= 0.0 ? mp : -mg);  // :608-610, :619-621
@@ -535,12 +540,14 @@ int launch_sig_stage2(fgs_ctx *c, const double *d_null, int S, int R, int P, int
       auto k = fdr_count_kernel<true>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
       k<<<grid, 256, smem_t, c->stream>>>(d_null, S, R, P, response, abs_flag, d_es, d_mpos, d_mneg, t1, n1,
-                                          t2, n2, c->sig_lut.p, chunk_len, h1, h2, (unsigned long long *)d_glob);
+                                          t2, n2, c->sig_lut.p, chunk_len, c->null_exact_near_obs ? 0.0 : SIG_SNAP_REL, h1, h2,
+                                          (unsigned long long *)d_glob);
     } else {
       auto k = fdr_count_kernel<false>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
       k<<<grid, 256, smem_h, c->stream>>>(d_null, S, R, P, response, abs_flag, d_es, d_mpos, d_mneg, t1, n1,
-                                          t2, n2, c->sig_lut.p, chunk_len, h1, h2, (unsigned long long *)d_glob);
+                                          t2, n2, c->sig_lut.p, chunk_len, c->null_exact_near_obs ? 0.0 : SIG_SNAP_REL, h1, h2,
+                                          (unsigned long long *)d_glob);
     }
     c->launches++;
     FGS_CUDA(cudaGetLastError());
