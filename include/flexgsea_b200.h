@@ -94,7 +94,13 @@ int fgs_score_observed(fgs_ctx *ctx, int score_kind, int abs_flag, double *score
  * ragged arrays sharing the CSR offsets, [nnz x R]: running_es_at (1-based gene
  * ids in rank order), running_es_pos, running_es_neg; le_first/le_count
  * [S x R]: the leading edge of set s is running_es_at[offsets[s] + le_first ..
- * + le_count). */
+ * + le_count).
+ * The weighted-KS observed ES stays in the context (until x, the gene sets or
+ * the response change): a later fgs_perm_null / fgs_es_from_scores recomputes
+ * every null unit that lands within rounding of it in the reference's own
+ * operation order, so the `<=` / `>=` comparisons of flexgsea_calc_sig see the
+ * ties the reference sees (label-preserving permutations, small universes).
+ * Call it before the null loop, as flexgsea() does (:266-305). */
 int fgs_observed_es(fgs_ctx *ctx, int es_kind, double p_exponent, const double *scores,
                     int n_gene, int n_response, double *es, double *max_es_at, double *le_prop,
                     int *running_es_at, double *running_es_pos, double *running_es_neg,
