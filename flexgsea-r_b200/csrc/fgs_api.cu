@@ -296,7 +296,7 @@ int fgs_destroy(fgs_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->x.release(); c->xc.release(); c->xtot.release(); c->cert_list.release(); c->cert_ctr.release();
-  c->cert_redo.release(); c->sort_redo.release(); c->sort_glist.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release(); c->set_idx16.release(); c->sig_lut.release(); c->set_slow.release(); c->tie_list.release(); c->tie_ctr.release(); c->obs_es.release();
+  c->cert_redo.release(); c->sort_redo.release(); c->sort_glist.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release(); c->set_idx16.release(); c->sig_lut.release(); c->set_slow.release(); c->tie_list.release(); c->tie_ctr.release(); c->obs_es.release(); c->ident.release(); c->obs_labels.release();
   for (auto &b : c->api_d) b.release();
   for (auto &b : c->api_i) b.release();
   c->api_l.release();
@@ -590,9 +590,16 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
   if (perm) FGS_TRY(h2d(c, c->perm.p, perm, (size_t)n * P));
   else FGS_TRY(launch_philox_perm(c, seed, perm_id0, n, P, c->perm.p));
   const int W = (n + 31) / 32;
+  c->cur_ident = nullptr;
   if (score_kind == FGS_SCORE_S2N) {
     FGS_TRY(c->labels.ensure((size_t)P * R * 2 * W));
     FGS_TRY(launch_labels(c, c->perm.p, c->ybin.p, n, R, P, c->labels.p));
+    if (c->cur_obs) {  // label-preserving permutations get the observed ES as it is
+      FGS_TRY(c->obs_labels.ensure((size_t)R * 2 * W));
+      FGS_TRY(c->ident.ensure((size_t)P));
+      FGS_TRY(launch_labels(c, nullptr, c->ybin.p, n, R, 1, c->obs_labels.p));
+      FGS_TRY(launch_label_identity(c, c->labels.p, c->obs_labels.p, R, W, P, c->ident.p));
+    }
   }
   c->last_launches[0] = c->launches - l0;
   float pro_ms = 0;
@@ -608,9 +615,14 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
                         c->labels.p + (size_t)p0 * R * 2 * W, Pb, p0));
     c->last_launches[1] += c->launches - l0;
     tm.mark();
+    c->cur_ident = (c->cur_obs && score_kind == FGS_SCORE_S2N) ? c->ident.p + p0 : nullptr;
     FGS_TRY(rank_and_es(c, es_kind, p_exp, abs_flag, (long long)Pb * R,
                         c->es_null.p + (size_t)p0 * R * S, tm));
+    if (c->cur_ident)
+      FGS_TRY(launch_copy_observed(c, c->cur_obs, c->cur_ident, R, (long long)Pb * R,
+                                   c->es_null.p + (size_t)p0 * R * S));
   }
+  c->cur_ident = nullptr;
   FGS_CUDA(cudaEventRecord(c->ev[1], c->stream));
   int rc = flags_check(c, P);
   if (c->profiling) {
@@ -657,6 +669,7 @@ int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scor
     c->null_S = S; c->null_R = R; c->null_P = P;
     c->cur_obs = (es_kind == FGS_ES_WEIGHTED_KS && c->obs_valid && c->obs_S == S && c->obs_R == R) ? c->obs_es.p : nullptr;
     c->cur_obs_R = R;
+    c->cur_ident = nullptr;
     c->null_exact_near_obs = c->cur_obs != nullptr;
     if (C == 0) return FGS_OK;
     FGS_TRY(flags_reset(c, C));

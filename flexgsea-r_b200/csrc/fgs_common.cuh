@@ -113,6 +113,9 @@ struct fgs_ctx {
   bool obs_valid = false;
   const double *cur_obs = nullptr;   // set by rank_and_es for the ES launches of the current call
   int cur_obs_R = 1;
+  const int *cur_ident = nullptr;    // [Pb] label-preserving permutations of the current block (or NULL)
+  fgs::DevBuf<int> ident;            // [P]
+  fgs::DevBuf<uint32_t> obs_labels;  // [R][2][W] class masks of the unpermuted response
   bool null_exact_near_obs = false;  // the resident null was made with that treatment
   fgs::DevBuf<int2> tie_list;      // (column, set) units whose es_pos and -es_neg tied: redone exactly
   fgs::DevBuf<int> tie_ctr;
@@ -204,6 +207,10 @@ int launch_s2n_exact_entries(fgs_ctx *c, const double *d_x, int n, int G, const 
 int launch_prep_sets(fgs_ctx *c, int S, int *h_status, unsigned char *h_slow);
 int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
                   double *d_es, bool defer_ties = false);
+int launch_copy_observed(fgs_ctx *c, const double *d_obs, const int *d_ident, int R, long long C,
+                         double *d_es);
+int launch_label_identity(fgs_ctx *c, const uint32_t *d_labels, const uint32_t *d_obs, int R, int W, int P,
+                          int *d_ident);
 int launch_es_wks_ties(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
                        double *d_es);
 int launch_tie_members(fgs_ctx *c, int2 *d_out, int *d_out_ctr, int out_cap, int *d_overflow);

@@ -154,9 +154,10 @@ __device__ __forceinline__ double warp_max_exact(double x) {
 // a null ES within rounding of the set's observed ES (label-preserving permutations,
 // small universes): whether the two compare equal is the reference's rounding, so the
 // unit is redone exactly like a tied one
-__device__ __forceinline__ bool near_observed(const double *__restrict__ obs, int S, int R, long long col,
-                                              int set_id, double es) {
+__device__ __forceinline__ bool near_observed(const double *__restrict__ obs, const int *__restrict__ ident,
+                                              int S, int R, long long col, int set_id, double es) {
   if (!obs) return false;
+  if (ident && __ldg(ident + col / R)) return false;  // label-preserving permutation: the column is copied
   const double e = __ldg(obs + (size_t)(col % R) * S + set_id);
   return fabs(es - e) <= 1e-9 * fabs(e);
 }
@@ -285,7 +286,7 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
               long long C, const int4 *__restrict__ set_info, const uint16_t *__restrict__ idx16,
               const double *__restrict__ set_invgm, int S, double *__restrict__ es_out,
               int2 *__restrict__ tie_list, int *__restrict__ tie_ctr, int tie_cap,
-              const double *__restrict__ obs, int R) {
+              const double *__restrict__ obs, const int *__restrict__ ident, int R) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const size_t Gp = pitch_of(G);
@@ -336,7 +337,7 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
         else es = wks_sets<8, 64, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie);  // 257 .. 512 members
         if (mine && ls == 0) {
           es_col[info.w] = es;
-          if (tie || near_observed(obs, S, R, col, info.w, es)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, info.w);
+          if (tie || near_observed(obs, ident, S, R, col, info.w, es)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, info.w);
         }
       } else {  // a quad with a set of 513 .. ES_MAX_SET members: one set at a time on the whole warp
 #pragma unroll 1
@@ -352,7 +353,7 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
           else es = wks_sets<32, 64, W_SMEM>(s_rank, wsrc, idx16, zi, mi, G, igi, lane, tie);
           if (lane == 0) {
             es_col[wi] = es;
-            if (tie || near_observed(obs, S, R, col, wi, es)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, wi);
+            if (tie || near_observed(obs, ident, S, R, col, wi, es)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, wi);
           }
         }
       }
@@ -400,7 +401,7 @@ es_wks_generic_kernel(const uint16_t *__restrict__ rank16, const double *__restr
                       long long C, const int *__restrict__ set_off, const int *__restrict__ set_idx,
                       const int *__restrict__ set_ids, int n_ids, int S, double *__restrict__ es_out,
                       int2 *__restrict__ tie_list, int *__restrict__ tie_ctr, int tie_cap,
-                      const double *__restrict__ obs, int R) {
+                      const double *__restrict__ obs, const int *__restrict__ ident, int R) {
   const int lane = threadIdx.x & 31;
   const long long unit = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (unit >= (long long)n_ids * C) return;
@@ -442,7 +443,7 @@ es_wks_generic_kernel(const uint16_t *__restrict__ rank16, const double *__restr
     const bool degenerate = W == 0.0 || m == 0 || has_nan;
     if (degenerate) es = nan("");
     es_out[(size_t)col * S + s] = es;
-    if (!degenerate && (fabs(mx + mn) <= ES_TIE_REL * fmax(fabs(mx), fabs(mn)) || near_observed(obs, S, R, col, s, es)))
+    if (!degenerate && (fabs(mx + mn) <= ES_TIE_REL * fmax(fabs(mx), fabs(mn)) || near_observed(obs, ident, S, R, col, s, es)))
       tie_push(tie_list, tie_ctr, tie_cap, (int)col, s);
   }
 }
@@ -561,7 +562,7 @@ int launch_es_wks_generic(fgs_ctx *c, const uint16_t *d_rank16, const double *d_
   if (blocks > 0x7fffffffLL) { set_error("too many (set, column) units"); return FGS_ERR_ARG; }
   es_wks_generic_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(
       d_rank16, d_sabs, G, C, c->set_off.p, c->set_idx.p, d_set_ids, n_ids, c->S, d_es,
-      c->tie_list.p, c->tie_ctr.p, c->tie_cap, c->cur_obs, c->cur_obs_R);
+      c->tie_list.p, c->tie_ctr.p, c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R);
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   return FGS_OK;
@@ -657,13 +658,13 @@ static int launch_es_wks_inner(fgs_ctx *c, const uint16_t *d_rank16, const doubl
     FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx16.p,
                                              c->set_invgm.p, c->S, d_es, c->tie_list.p, c->tie_ctr.p,
-                                             c->tie_cap, c->cur_obs, c->cur_obs_R);
+                                             c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R);
   } else {
     auto k = es_wks_kernel<false>;
     FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx16.p,
                                              c->set_invgm.p, c->S, d_es, c->tie_list.p, c->tie_ctr.p,
-                                             c->tie_cap, c->cur_obs, c->cur_obs_R);
+                                             c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R);
   }
   c->launches++;
   FGS_CUDA(cudaGetLastError());
@@ -730,6 +731,24 @@ int launch_tie_refresh_weights(fgs_ctx *c, const int2 *d_list, const int *d_ctr,
                                double p_exp) {
   tie_refresh_weights_kernel<<<c->num_sms * 2, 256, 0, c->stream>>>(d_list, d_ctr, cap, d_scores, d_rank16,
                                                                     d_sabs, G, p_exp);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
+}
+
+// es_null[, r, p] = observed ES[, r] for the label-preserving permutations of a block
+__global__ void copy_observed_kernel(const double *__restrict__ obs, const int *__restrict__ ident, int S,
+                                     int R, long long C, double *__restrict__ es_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * S) return;
+  const long long col = i / S;
+  if (ident[col / R]) es_out[i] = obs[(size_t)(col % R) * S + (i % S)];
+}
+int launch_copy_observed(fgs_ctx *c, const double *d_obs, const int *d_ident, int R, long long C,
+                         double *d_es) {
+  const long long tot = C * c->S;
+  if (tot <= 0) return FGS_OK;
+  copy_observed_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(d_obs, d_ident, c->S, R, C, d_es);
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   return FGS_OK;

@@ -84,6 +84,28 @@ __global__ void labels_kernel(const int *__restrict__ perm, const int *__restric
   }
 }
 
+// ident[p] = 1 when permutation p leaves the class labels of EVERY response as they are
+// (label-preserving permutation: one in twenty at 3 + 3 samples).  Its scores, ranks and
+// ES are the observed ones, which fgs_perm_null then copies instead of recomputing them
+// in the reference's arithmetic unit by unit.  obs = labels of the identity, [R][2][W].
+__global__ void label_identity_kernel(const uint32_t *__restrict__ labels, const uint32_t *__restrict__ obs,
+                                      int R, int W, int P, int *__restrict__ ident) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const uint32_t *lp = labels + (size_t)p * R * 2 * W;
+  int same = 1;
+  for (int i = 0; i < R * 2 * W; i++) same &= lp[i] == obs[i];
+  ident[p] = same;
+}
+int launch_label_identity(fgs_ctx *c, const uint32_t *d_labels, const uint32_t *d_obs, int R, int W, int P,
+                          int *d_ident) {
+  if (P <= 0) return FGS_OK;
+  label_identity_kernel<<<ceil_div(P, 128), 128, 0, c->stream>>>(d_labels, d_obs, R, W, P, d_ident);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
+}
+
 int launch_labels(fgs_ctx *c, const int *d_perm, const int *d_ybin, int n, int R, int P,
                   uint32_t *d_labels) {
   long long C = (long long)P * R;
