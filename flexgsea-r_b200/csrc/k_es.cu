@@ -773,7 +773,7 @@ int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, in
                   double *d_es, bool defer_ties) {
   if (C <= 0 || c->S <= 0) return FGS_OK;
   if (c->tie_cap == 0) {
-    c->tie_cap = 1 << 20;
+    c->tie_cap = 1 << 22;  // 32 MB of (column, set) pairs per block; beyond that every unit is redone
     FGS_TRY(c->tie_list.ensure((size_t)c->tie_cap));
     FGS_TRY(c->tie_ctr.ensure(4));
   }
