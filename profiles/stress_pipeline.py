@@ -34,16 +34,28 @@ def run(ncase, seed, ctx=None):
         perm = synth.perm_matrix(n, P, seed=int(rng.integers(1 << 30)))
         abs_flag = bool(rng.random() < 0.25)
         simple = bool(rng.random() < 0.3)
-        tag = dict(case=case, G=G, n=n, S=S, P=P, abs=abs_flag, simple=simple)
+        user = bool(rng.random() < 0.3)  # user-defined gene.score.fn: scores made on the host
+        if user:
+            usc = rng.normal(size=(G, 1, P + 1))
+            if rng.random() < 0.5:
+                usc = np.round(usc, 1)      # ties, exact zeros
+            dup = rng.integers(0, P + 1, size=max(1, P // 10))
+            usc[:, 0, dup[1:]] = usc[:, 0, [dup[0]]]   # identical score columns (incl. possibly the observed one)
+            abs_flag = False
+        tag = dict(case=case, G=G, n=n, S=S, P=P, abs=abs_flag, simple=simple, user=user)
         if os.environ.get("ONLY") and int(os.environ["ONLY"]) != case:
             continue
         why = []
         # ---- oracle
-        o_sc = oracle.s2n_post(oracle.s2n_C(x, y), abs_flag)
-        if not np.isfinite(o_sc).all():
-            continue  # the reference stops here (:251-253)
+        if user:
+            o_sc = np.asfortranarray(usc[:, :, 0])
+            rc, o_null = oracle.es_from_scores(oracle.ES_WKS, usc[:, :, 1:], off, idx)
+        else:
+            o_sc = oracle.s2n_post(oracle.s2n_C(x, y), abs_flag)
+            if not np.isfinite(o_sc).all():
+                continue  # the reference stops here (:251-253)
+            rc, o_null = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, oracle.ES_WKS, abs_flag=abs_flag)
         o_obs = [oracle.wks_column(o_sc[:, 0], oracle.rank_desc(o_sc[:, 0]), s_, extras=True) for s_ in sets]
-        rc, o_null = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, oracle.ES_WKS, abs_flag=abs_flag)
         if rc != 0:
             continue
         o_es = np.array([o["es"] for o in o_obs])
@@ -51,9 +63,12 @@ def run(ncase, seed, ctx=None):
         # ---- device
         try:
             ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
-            sc = ctx.score_observed(nat.SCORE_S2N, abs_flag=abs_flag)
+            sc = o_sc.copy() if user else ctx.score_observed(nat.SCORE_S2N, abs_flag=abs_flag)
             obs = ctx.observed_es(nat.ES_WEIGHTED_KS, sc, ragged=True)
-            ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm, abs_flag=abs_flag, want_host=False)
+            if user:
+                ctx.es_from_scores(nat.ES_WEIGHTED_KS, usc[:, :, 1:], want_host=False)
+            else:
+                ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm, abs_flag=abs_flag, want_host=False)
             sig = ctx.calc_sig(obs["es"][:, 0], 0, not simple, not simple, abs_flag)
         except nat.FlexgseaError as e:
             bad += 1; print("MISMATCH device error", e, tag); continue
@@ -87,7 +102,8 @@ def run(ncase, seed, ctx=None):
             bad += 1; print("MISMATCH", tag, why[:6])
             if os.environ.get("ONLY"):
                 d_null = np.zeros((len(sets), 1, P), order="F")
-                d_null = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm, abs_flag=abs_flag)
+                d_null = (ctx.es_from_scores(nat.ES_WEIGHTED_KS, usc[:, :, 1:]) if user else
+                          ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm, abs_flag=abs_flag))
                 for k_ in range(len(sets)):
                     if not simple and not np.array_equal(sig["fdr_counts"][k_], o_sig["fdr_counts"][k_]):
                         print("  fdr set", k_, sets[k_].tolist(), "nes dev/oracle", repr(sig["nes"][k_]), repr(o_sig["nes"][k_]), "counts", sig["fdr_counts"][k_], o_sig["fdr_counts"][k_])
