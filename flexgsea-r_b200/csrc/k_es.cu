@@ -151,6 +151,7 @@ __device__ __forceinline__ double warp_max_exact(double x) {
   return __hiloint2double((int)(mh ^ (inv | 0x80000000u)), (int)(ml ^ inv));
 }
 
+constexpr double ES_OBS_REL = 1e-9;  // |null - observed| below this fraction of the observed ES: redo exactly
 // a null ES within rounding of the set's observed ES (label-preserving permutations,
 // small universes): whether the two compare equal is the reference's rounding, so the
 // unit is redone exactly like a tied one
@@ -159,7 +160,7 @@ __device__ __forceinline__ bool near_observed(const double *__restrict__ obs, co
   if (!obs) return false;
   if (ident && __ldg(ident + col / R)) return false;  // label-preserving permutation: the column is copied
   const double e = __ldg(obs + (size_t)(col % R) * S + set_id);
-  return fabs(es - e) <= 1e-9 * fabs(e);
+  return fabs(es - e) <= ES_OBS_REL * fabs(e);
 }
 constexpr double ES_TIE_REL = 1e-9;  // |es_pos + es_neg| below this fraction of their size: redo exactly
 __device__ __forceinline__ void tie_push(int2 *__restrict__ list, int *__restrict__ ctr, int cap, int col,
@@ -315,6 +316,8 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
     if (tid == 0) s_rank[G] = (uint16_t)G;  // the pad gene's key (inside the staged row when G < Gp)
     __syncthreads();
     const double *wsrc = W_SMEM ? s_abs : sabs + (size_t)col * Gp;
+    // observed ES of this column's response; none for a label-preserving permutation (copied later)
+    const double *col_obs = (obs && !(ident && __ldg(ident + col / R))) ? obs + (size_t)(col % R) * S : nullptr;
     double *es_col = es_out + (size_t)col * S;
     // sets in descending size, four per warp (eight lanes each), quads round-robin
     // over the warps: similar work per warp and one size class per quad
@@ -323,6 +326,8 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
       int4 info = make_int4(0, (int)0x80000000, 0, 0);  // {-, m | slow << 31, member block offset, set id}
       double ig = 0.0;
       if (k < S) { info = __ldg(set_info + k); ig = __ldg(set_invgm + k); }  // ig = 1 / (G - m)
+      // the set's observed ES, fetched now so that the comparison at the end costs nothing
+      const double e_obs = (col_obs && k < S) ? __ldg(col_obs + info.w) : nan("");
       const bool mine = info.y >= 0;              // slow sets: es_wks_generic_kernel does these
       const int m = mine ? info.y : 0;
       int mmax = max(m, __shfl_xor_sync(0xffffffffu, m, 8));
@@ -337,14 +342,14 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
         else es = wks_sets<8, 64, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie);  // 257 .. 512 members
         if (mine && ls == 0) {
           es_col[info.w] = es;
-          if (tie || near_observed(obs, ident, S, R, col, info.w, es)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, info.w);
+          if (tie || fabs(es - e_obs) <= ES_OBS_REL * fabs(e_obs)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, info.w);
         }
       } else {  // a quad with a set of 513 .. ES_MAX_SET members: one set at a time on the whole warp
 #pragma unroll 1
         for (int i = 0; i < 4; i++) {
           const int mi = __shfl_sync(0xffffffffu, m, 8 * i);
           const int zi = __shfl_sync(0xffffffffu, info.z, 8 * i), wi = __shfl_sync(0xffffffffu, info.w, 8 * i);
-          const double igi = __shfl_sync(0xffffffffu, ig, 8 * i);
+          const double igi = __shfl_sync(0xffffffffu, ig, 8 * i), eoi = __shfl_sync(0xffffffffu, e_obs, 8 * i);
           const bool on = __shfl_sync(0xffffffffu, (int)mine, 8 * i) != 0;
           if (!on) continue;
           double es;
@@ -353,7 +358,7 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
           else es = wks_sets<32, 64, W_SMEM>(s_rank, wsrc, idx16, zi, mi, G, igi, lane, tie);
           if (lane == 0) {
             es_col[wi] = es;
-            if (tie || near_observed(obs, ident, S, R, col, wi, es)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, wi);
+            if (tie || fabs(es - eoi) <= ES_OBS_REL * fabs(eoi)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, wi);
           }
         }
       }
@@ -737,18 +742,23 @@ int launch_tie_refresh_weights(fgs_ctx *c, const int2 *d_list, const int *d_ctr,
 }
 
 // es_null[, r, p] = observed ES[, r] for the label-preserving permutations of a block
+// (a block row per permutation: the others leave at once)
 __global__ void copy_observed_kernel(const double *__restrict__ obs, const int *__restrict__ ident, int S,
-                                     int R, long long C, double *__restrict__ es_out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C * S) return;
-  const long long col = i / S;
-  if (ident[col / R]) es_out[i] = obs[(size_t)(col % R) * S + (i % S)];
+                                     int R, double *__restrict__ es_out) {
+  const int p = blockIdx.y;
+  if (!ident[p]) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (set, response) of the observed matrix
+  if (i < S * R) es_out[(size_t)p * R * S + i] = obs[i];
 }
 int launch_copy_observed(fgs_ctx *c, const double *d_obs, const int *d_ident, int R, long long C,
                          double *d_es) {
-  const long long tot = C * c->S;
-  if (tot <= 0) return FGS_OK;
-  copy_observed_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(d_obs, d_ident, c->S, R, C, d_es);
+  const long long Pb = C / R;
+  if (Pb <= 0 || c->S <= 0) return FGS_OK;
+  for (long long p0 = 0; p0 < Pb; p0 += 65535) {  // grid.y limit
+    const int np = (int)std::min<long long>(65535, Pb - p0);
+    dim3 grid(ceil_div((long long)c->S * R, 256), np);
+    copy_observed_kernel<<<grid, 256, 0, c->stream>>>(d_obs, d_ident + p0, c->S, R, d_es + (size_t)p0 * R * c->S);
+  }
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   return FGS_OK;
