@@ -183,6 +183,16 @@ static long long block_columns(fgs_ctx *c, long long C_total) {
   return cb < 1 ? 1 : cb;
 }
 
+// A problem small enough that computing EVERY weighted-KS unit in the reference's own
+// operation order (es_wks_tie_kernel, O(m^2 / 32) per unit) costs next to nothing.  Worth
+// doing because small problems are where it matters: with a dozen genes or four samples the
+// statistic takes a handful of values, NES of different sets tie up to rounding, and the
+// pooled-FDR counts then hang on the last bit of every null value, not only of those near
+// the observed ES.
+static bool small_wks_problem(const fgs_ctx *c, long long C) {
+  return c->opt_exact_small && c->sum_m2 * (double)C * (25.0 / 32.0) <= 5e8;
+}
+
 // rank + ES of the score columns currently in c->scores
 static int rank_and_es(fgs_ctx *c, int es_kind, double p_exp, int abs_flag, long long Cb,
                        double *d_es, StageTimer &tm) {
@@ -333,6 +343,7 @@ int fgs_set_option(fgs_ctx *c, const char *name, long long value) {
   else if (!strcmp(name, "force_generic_es")) c->opt_force_generic = (int)value;
   else if (!strcmp(name, "force_sort64")) c->opt_sort64 = (int)value;
   else if (!strcmp(name, "s2n_mode")) c->opt_s2n_mode = (int)value;
+  else if (!strcmp(name, "es_exact_small")) c->opt_exact_small = (int)value;
   else if (!strcmp(name, "cert_cap")) c->opt_cert_cap = value > 2 ? (int)value : 2;
   else { set_error("unknown option '%s'", name); return FGS_ERR_ARG; }
   return FGS_OK;
@@ -392,6 +403,8 @@ int fgs_set_gene_sets(fgs_ctx *c, const int *offsets, const int *index, int n_se
     blocks += (m + 7) / 8;
   }
   c->idx16_blocks = blocks;
+  c->sum_m2 = 0.0;
+  for (int s2 = 0; s2 < n_sets; s2++) { const double m = offsets[s2 + 1] - offsets[s2]; c->sum_m2 += m * m; }
   FGS_TRY(c->slow_ids.ensure(std::max<size_t>(slow_ids.size(), 1)));
   FGS_TRY(h2d(c, c->set_info.p, info.data(), (size_t)n_sets));
   FGS_TRY(h2d(c, c->slow_ids.p, slow_ids.data(), slow_ids.size()));
@@ -579,6 +592,8 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
   c->cur_obs = (es_kind == FGS_ES_WEIGHTED_KS && c->obs_valid && c->obs_S == S && c->obs_R == R) ? c->obs_es.p : nullptr;
   c->cur_obs_R = R;
   c->null_exact_near_obs = c->cur_obs != nullptr;
+  c->cur_exact_all = es_kind == FGS_ES_WEIGHTED_KS && score_kind == FGS_SCORE_S2N && small_wks_problem(c, (long long)R * P);
+  if (c->cur_exact_all) c->null_exact_near_obs = true;
   if (P == 0) return FGS_OK;
   FGS_TRY(flags_reset(c, P));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -612,7 +627,7 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
     tm.mark();
     l0 = c->launches;
     FGS_TRY(score_block(c, score_kind, c->perm.p + (size_t)p0 * n,
-                        c->labels.p + (size_t)p0 * R * 2 * W, Pb, p0));
+                        c->labels.p + (size_t)p0 * R * 2 * W, Pb, p0, /*force_exact=*/c->cur_exact_all));
     c->last_launches[1] += c->launches - l0;
     tm.mark();
     c->cur_ident = (c->cur_obs && score_kind == FGS_SCORE_S2N) ? c->ident.p + p0 : nullptr;
@@ -623,6 +638,7 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
                                    c->es_null.p + (size_t)p0 * R * S));
   }
   c->cur_ident = nullptr;
+  c->cur_exact_all = false;
   FGS_CUDA(cudaEventRecord(c->ev[1], c->stream));
   int rc = flags_check(c, P);
   if (c->profiling) {
@@ -671,6 +687,8 @@ int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scor
     c->cur_obs_R = R;
     c->cur_ident = nullptr;
     c->null_exact_near_obs = c->cur_obs != nullptr;
+    c->cur_exact_all = es_kind == FGS_ES_WEIGHTED_KS && small_wks_problem(c, C);
+    if (c->cur_exact_all) c->null_exact_near_obs = true;
     if (C == 0) return FGS_OK;
     FGS_TRY(flags_reset(c, C));
     FGS_CUDA(cudaEventRecord(c->ev[0], c->stream));
@@ -685,6 +703,7 @@ int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scor
       tm.mark();
       FGS_TRY(rank_and_es(c, es_kind, p_exp, 0, Cb, c->es_null.p + (size_t)c0 * S, tm));
     }
+    c->cur_exact_all = false;
     FGS_CUDA(cudaEventRecord(c->ev[1], c->stream));
     int r2 = flags_check(c, C);
     tm.finish(0.f);

@@ -76,6 +76,9 @@ struct fgs_ctx {
   // options
   int opt_perm_block = 0;      // 0 = auto
   int opt_force_generic = 0;
+  int opt_exact_small = 1;     // small problems: every ES unit in the reference's operation order
+  double sum_m2 = 0.0;         // sum of squared set sizes (cost of that path)
+  bool cur_exact_all = false;
   int opt_sort64 = 0;          // force the 64-bit global-memory sort (tests)
   int opt_s2n_mode = 1;        // 1 = tensor-core contraction + rank certification, 0 = bit-faithful kernel
   int opt_cert_cap = 4 << 20;  // entries per certification list (epilogue list, tie list)

@@ -776,6 +776,8 @@ int launch_es_wks_ties(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sab
   return FGS_OK;
 }
 
+__global__ void set_int_kernel(int *p, int v) { *p = v; }
+
 // Weighted KS of C score columns: the in-register kernel (or the order-free one),
 // then -- unless the caller first wants to refresh the tied units' weights
 // (defer_ties) -- the exact redo of the units whose two extremes tied.
@@ -788,6 +790,11 @@ int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, in
     FGS_TRY(c->tie_ctr.ensure(4));
   }
   FGS_CUDA(cudaMemsetAsync(c->tie_ctr.p, 0, 4 * sizeof(int), c->stream));
+  if (c->cur_exact_all) {  // a small problem: every unit by es_wks_tie_kernel (a count above the cap means "all")
+    set_int_kernel<<<1, 1, 0, c->stream>>>(c->tie_ctr.p, c->tie_cap + 1);
+    c->launches++;
+    return launch_es_wks_ties(c, d_rank16, d_sabs, G, C, d_es);
+  }
   FGS_TRY(launch_es_wks_inner(c, d_rank16, d_sabs, G, C, d_es));
   if (!defer_ties) FGS_TRY(launch_es_wks_ties(c, d_rank16, d_sabs, G, C, d_es));
   return FGS_OK;

@@ -202,7 +202,9 @@ int fgs_set_profiling(fgs_ctx *ctx, int enabled);
  * (route every set through the duplicate-safe O(m^2) kernel), "force_sort64"
  * (rank with the 64-bit global-memory sort), "s2n_mode" (1, default: s2n scores
  * of the null loop by the FP64 tensor-core contraction with rank certification;
- * 0: the bit-faithful three-pass kernel), "cert_cap" (certification list size) */
+ * 0: the bit-faithful three-pass kernel), "cert_cap" (certification list size),
+ * "es_exact_small" (1, default: problems that cost well under a millisecond that
+ * way compute every weighted-KS unit in the reference's operation order) */
 int fgs_set_option(fgs_ctx *ctx, const char *name, long long value);
 
 #ifdef __cplusplus

@@ -23,6 +23,9 @@ NA = np.iinfo(np.int32).min
 @pytest.fixture(scope="module")
 def ctx():
     c = fg.Context(0)
+    # the tests below are about the production kernels: keep small problems off the
+    # all-exact path they would otherwise take (test_random_small_pipelines turns it on)
+    c.set_option("es_exact_small", 0)
     yield c
     c.close()
 
@@ -156,6 +159,11 @@ def test_random_small_pipelines(ctx):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.run(1500, 5, ctx) == 0
+    ctx.set_option("es_exact_small", 1)      # the default: small problems entirely in the reference's arithmetic
+    try:
+        assert mod.run(1500, 5, ctx, fdr_strict_always=True) == 0
+    finally:
+        ctx.set_option("es_exact_small", 0)
 
 
 def test_tensor_scores_certified_ranks(ctx, oracle):
