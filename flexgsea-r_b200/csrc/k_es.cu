@@ -61,11 +61,7 @@ __device__ __forceinline__ uint32_t swap_halves(uint32_t v) { return __byte_perm
 // comparator between the two halves of one register: as 32-bit numbers, the
 // larger of (hi:lo) and (lo:hi) is the one with the larger key on top and the
 // smaller below -- one PRMT and one 32-bit max
-// (`flipped`: smaller key on top instead -- the form the next level's in-lane
-// mirror stage wants for the upper register of each pair, saving its two PRMTs)
-__device__ __forceinline__ uint32_t sort_halves(uint32_t v, bool flipped = false) {
-  return flipped ? min(v, swap_halves(v)) : max(v, swap_halves(v));
-}
+__device__ __forceinline__ uint32_t sort_halves(uint32_t v) { return max(v, swap_halves(v)); }
 // cross-lane comparator: `hi_mask` is 0 on the lane that keeps the minimum and
 // ~0 on the lane that keeps the maximum
 __device__ __forceinline__ uint32_t minmax2_side(uint32_t a, uint32_t o, uint32_t hi_mask) {
@@ -76,38 +72,42 @@ template <int LANES, int NB>
 __device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[NB / 2], int lane) {
   constexpr int N = LANES * NB;
   constexpr int NR = NB / 2;
-  static_assert(NB >= 2 && LANES <= 32, "packed pairs");
+  static_assert(NB >= 4 && LANES <= 32, "packed pairs, at least two registers");
+  // Slot s of a lane lives in register s % NR, half s / NR: the TOP slot bit selects the
+  // half.  A comparator stage on the half bit costs two instructions per register (PRMT +
+  // 32-bit max), one between registers a single VIMNMX; the top slot bit is the in-lane
+  // bit the network touches least often (log2(LANES) + 1 times, the lowest bit log2(N)).
 #pragma unroll
   for (int k = 2; k <= N; k <<= 1) {
     // mirror stage: e <-> e ^ (k - 1)
-    if (k == 2) {
-#pragma unroll
-      for (int q = 0; q < NR; q++) v[q] = sort_halves(v[q], 2 * k <= NB && (q & (k >> 1)));
-    } else if (k <= NB) {  // slot ^ (k - 1): register q ^ (k/2 - 1), halves swapped
-      // the upper register of each pair arrives with its halves already
-      // exchanged (see sort_halves) and stays so until this level's last stage
+    if (k <= NR) {  // only register bits flip: same half
 #pragma unroll
       for (int q = 0; q < NR; q++) {
-        const int qb = q ^ ((k >> 1) - 1);
+        const int qb = q ^ (k - 1);
         if (qb > q) {
           const uint32_t a = v[q], t = v[qb];
           v[q] = __vminu2(a, t);
           v[qb] = __vmaxu2(a, t);
         }
       }
+    } else if (k == NB) {  // every slot bit flips: (half 0, q) <-> (half 1, NR-1-q) and (1, q) <-> (0, NR-1-q)
+#pragma unroll
+      for (int q = 0; q < NR / 2; q++) {
+        const int qb = NR - 1 - q;
+        const uint32_t a = v[q], bs = swap_halves(v[qb]);
+        const uint32_t mn = __vminu2(a, bs), mx = __vmaxu2(a, bs);
+        v[q] = __byte_perm(mn, mx, 0x7610);   // low: min(a.lo, b.hi) stays below; high: max(a.hi, b.lo)
+        v[qb] = __byte_perm(mn, mx, 0x5432);  // low: min(a.hi, b.lo); high: max(a.lo, b.hi)
+      }
     } else {  // lane ^ (k / NB - 1), slots reversed: register NR-1-q, halves swapped
       const uint32_t hi_mask = 0u - ((lane / ((k / NB) >> 1)) & 1u);
-      if constexpr (NR == 1) {
-        v[0] = minmax2_side(v[0], swap_halves(__shfl_xor_sync(0xffffffffu, v[0], (k / NB) - 1)), hi_mask);
-      } else {
 #pragma unroll
-        for (int q = 0; q < NR / 2; q++) {  // registers q and NR-1-q exchange with each other's mirror
-          const uint32_t a = v[q], b = v[NR - 1 - q];
-          const uint32_t oa = swap_halves(__shfl_xor_sync(0xffffffffu, b, (k / NB) - 1));
-          const uint32_t ob = swap_halves(__shfl_xor_sync(0xffffffffu, a, (k / NB) - 1));
-          v[q] = minmax2_side(a, oa, hi_mask);
-          v[NR - 1 - q] = minmax2_side(b, ob, hi_mask);
-        }
+      for (int q = 0; q < NR / 2; q++) {  // registers q and NR-1-q exchange with each other's mirror
+        const uint32_t a = v[q], b = v[NR - 1 - q];
+        const uint32_t oa = swap_halves(__shfl_xor_sync(0xffffffffu, b, (k / NB) - 1));
+        const uint32_t ob = swap_halves(__shfl_xor_sync(0xffffffffu, a, (k / NB) - 1));
+        v[q] = minmax2_side(a, oa, hi_mask);
+        v[NR - 1 - q] = minmax2_side(b, ob, hi_mask);
       }
     }
 #pragma unroll
@@ -117,19 +117,19 @@ __device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[NB / 2], int la
 #pragma unroll
         for (int q = 0; q < NR; q++)
           v[q] = minmax2_side(v[q], __shfl_xor_sync(0xffffffffu, v[q], j / NB), hi_mask);
-      } else if (j >= 2) {  // partner register q ^ (j / 2), same half
+      } else if (j == NR) {  // the two halves of one register
+#pragma unroll
+        for (int q = 0; q < NR; q++) v[q] = sort_halves(v[q]);
+      } else {  // partner register q ^ j, same half
 #pragma unroll
         for (int q = 0; q < NR; q++) {
-          const int qb = q ^ (j >> 1);
+          const int qb = q ^ j;
           if (qb > q) {
             const uint32_t a = v[q], b2 = v[qb];
             v[q] = __vminu2(a, b2);
             v[qb] = __vmaxu2(a, b2);
           }
         }
-      } else {  // j == 1: the two halves of one register
-#pragma unroll
-        for (int q = 0; q < NR; q++) v[q] = sort_halves(v[q], 2 * k <= NB && (q & (k >> 1)));
       }
     }
   }
@@ -231,7 +231,7 @@ __device__ __forceinline__ double wks_sets(const uint16_t *__restrict__ s_rank,
   double cl = 0.0, mx = -INFINITY, mn = INFINITY;
 #pragma unroll
   for (int t = 0; t < SL; t++) {
-    const uint32_t r0 = (v[t >> 1] >> (16 * (t & 1))) & 0xffffu;
+    const uint32_t r0 = (v[t % NR] >> (16 * (t / NR))) & 0xffffu;  // slot t: register t % NR, half t / NR
     const double w = (W_SMEM || t < nvalid) ? wsrc[r0] : 0.0;
     cl += w;
     // d_miss = (r - k) / (G - m) with r = r0 + 1, k = k0 + t + 1 (R/flexgsea.R:825-826)
