@@ -723,7 +723,10 @@ int fgs_debug_last_scores(fgs_ctx *c, double *scores, int *rank, long long n_col
   if (n_col > c->last_cols || c->last_G <= 0) { set_error("debug tap: only %lld columns resident", c->last_cols); return FGS_ERR_STATE; }
   const int G = c->last_G;
   if (scores) FGS_TRY(d2h(c, scores, c->scores.p, (size_t)G * n_col));
-  if (rank) {
+  if (rank && c->rank16.n < pitch_of(G) * (size_t)n_col) {
+    // the last call did not rank (maxmean / mean need no ranks): nothing to report
+    std::fill(rank, rank + (size_t)G * n_col, 0);
+  } else if (rank) {
     const size_t Gp = pitch_of(G);
     std::vector<uint16_t> h(Gp * n_col);
     FGS_TRY(d2h(c, h.data(), c->rank16.p, Gp * n_col));
