@@ -192,6 +192,13 @@ static long long block_columns(fgs_ctx *c, long long C_total) {
 static bool small_wks_problem(const fgs_ctx *c, long long C) {
   return c->opt_exact_small && c->sum_m2 * (double)C * (25.0 / 32.0) <= 5e8;
 }
+// the same for maxmean / mean (launch_es_mean_exact: double-double sums, ~10 instructions per member)
+static bool small_mean_problem(const fgs_ctx *c, long long C) {
+  return c->opt_exact_small && (double)c->nnz * (double)C * (10.0 / 32.0) <= 5e8;
+}
+static bool small_problem(const fgs_ctx *c, int es_kind, long long C) {
+  return es_kind == FGS_ES_WEIGHTED_KS ? small_wks_problem(c, C) : small_mean_problem(c, C);
+}
 
 // rank + ES of the score columns currently in c->scores
 static int rank_and_es(fgs_ctx *c, int es_kind, double p_exp, int abs_flag, long long Cb,
@@ -244,6 +251,15 @@ static int rank_and_es(fgs_ctx *c, int es_kind, double p_exp, int abs_flag, long
     tm.mark();
     long long l0 = c->launches;
     FGS_TRY(launch_es_mean(c, c->scores.p, G, Cb, es_kind, abs_flag, d_es));
+    if (c->cur_cert && !c->cur_exact_all) {  // listed units: exact member scores first (tensor-core scores)
+      int2 *list = c->cert_list.p;
+      int *cnt = c->cert_ctr.p + 2;
+      FGS_TRY(launch_tie_members(c, list, cnt, c->opt_cert_cap, c->flags.p + (c->flags.n - 1)));
+      FGS_TRY(launch_s2n_exact_entries(c, c->x.p, c->n, G, c->cur_labels, c->n1n2.p, c->s2n_R, list, cnt,
+                                       c->opt_cert_cap, c->scores.p, c->flags.p + c->cur_flag0,
+                                       /*after_patch=*/true));
+    }
+    FGS_TRY(launch_es_mean_exact(c, c->scores.p, G, Cb, es_kind, abs_flag, d_es));
     c->last_launches[3] += c->launches - l0;
     tm.mark();
   } else {
@@ -589,10 +605,10 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
   c->null_S = S; c->null_R = R; c->null_P = P;
   // the observed ES of this problem, if fgs_observed_es made one: null units that come out
   // within rounding of it are redone in the reference's arithmetic (see es_wks_tie_kernel)
-  c->cur_obs = (es_kind == FGS_ES_WEIGHTED_KS && c->obs_valid && c->obs_S == S && c->obs_R == R) ? c->obs_es.p : nullptr;
+  c->cur_obs = (c->obs_valid && c->obs_kind == es_kind && c->obs_S == S && c->obs_R == R) ? c->obs_es.p : nullptr;
   c->cur_obs_R = R;
   c->null_exact_near_obs = c->cur_obs != nullptr;
-  c->cur_exact_all = es_kind == FGS_ES_WEIGHTED_KS && score_kind == FGS_SCORE_S2N && small_wks_problem(c, (long long)R * P);
+  c->cur_exact_all = score_kind == FGS_SCORE_S2N && small_problem(c, es_kind, (long long)R * P);
   if (c->cur_exact_all) c->null_exact_near_obs = true;
   if (P == 0) return FGS_OK;
   FGS_TRY(flags_reset(c, P));
@@ -683,11 +699,11 @@ int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scor
   auto body = [&]() -> int {
     FGS_TRY(c->es_null.ensure(std::max<size_t>((size_t)S * C, 1)));
     c->null_S = S; c->null_R = R; c->null_P = P;
-    c->cur_obs = (es_kind == FGS_ES_WEIGHTED_KS && c->obs_valid && c->obs_S == S && c->obs_R == R) ? c->obs_es.p : nullptr;
+    c->cur_obs = (c->obs_valid && c->obs_kind == es_kind && c->obs_S == S && c->obs_R == R) ? c->obs_es.p : nullptr;
     c->cur_obs_R = R;
     c->cur_ident = nullptr;
     c->null_exact_near_obs = c->cur_obs != nullptr;
-    c->cur_exact_all = es_kind == FGS_ES_WEIGHTED_KS && small_wks_problem(c, C);
+    c->cur_exact_all = small_problem(c, es_kind, C);
     if (c->cur_exact_all) c->null_exact_near_obs = true;
     if (C == 0) return FGS_OK;
     FGS_TRY(flags_reset(c, C));
@@ -788,7 +804,7 @@ int fgs_observed_es(fgs_ctx *c, int es_kind, double p_exp, const double *scores,
                                   d_pos.p, d_neg.p, d_lf.p, d_lc.p));
       FGS_TRY(c->obs_es.ensure(SR));
       FGS_CUDA(cudaMemcpyAsync(c->obs_es.p, d_es.p, SR * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-      c->obs_S = S; c->obs_R = R; c->obs_valid = true;
+      c->obs_S = S; c->obs_R = R; c->obs_valid = true; c->obs_kind = FGS_ES_WEIGHTED_KS;
       c->last_cols = R; c->last_G = G;
       FGS_TRY(d2h(c, max_es_at, d_mea.p, SR)); FGS_TRY(d2h(c, le_prop, d_lep.p, SR));
       FGS_TRY(d2h(c, le_first, d_lf.p, SR)); FGS_TRY(d2h(c, le_count, d_lc.p, SR));
@@ -796,7 +812,16 @@ int fgs_observed_es(fgs_ctx *c, int es_kind, double p_exp, const double *scores,
       FGS_TRY(d2h(c, running_es_pos, d_pos.p, (size_t)c->nnz * R));
       FGS_TRY(d2h(c, running_es_neg, d_neg.p, (size_t)c->nnz * R));
     } else if (es_kind == FGS_ES_MAXMEAN || es_kind == FGS_ES_MEAN) {
-      FGS_TRY(launch_es_mean(c, c->scores.p, G, R, es_kind, 0, d_es.p));
+      // the observed pass sums like the reference (double-double for R's long double): every unit
+      const bool saved = c->cur_exact_all;
+      c->cur_exact_all = true;
+      int r2 = launch_es_mean(c, c->scores.p, G, R, es_kind, 0, d_es.p);
+      c->cur_exact_all = saved;
+      FGS_TRY(r2);
+      FGS_TRY(launch_es_mean_exact(c, c->scores.p, G, R, es_kind, 0, d_es.p));
+      FGS_TRY(c->obs_es.ensure(SR));
+      FGS_CUDA(cudaMemcpyAsync(c->obs_es.p, d_es.p, SR * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      c->obs_S = S; c->obs_R = R; c->obs_valid = true; c->obs_kind = es_kind;
     } else { set_error("unknown es_kind %d", es_kind); return FGS_ERR_ARG; }
     FGS_TRY(d2h(c, es, d_es.p, SR));
     return flags_check(c, R);

@@ -112,7 +112,7 @@ struct fgs_ctx {
   // observed ES of the last fgs_observed_es (weighted KS): null units that land within
   // rounding of it are recomputed in the reference's operation order (es_wks_tie_kernel)
   fgs::DevBuf<double> obs_es;      // [S x R]
-  int obs_S = 0, obs_R = 0;
+  int obs_S = 0, obs_R = 0, obs_kind = -1;
   bool obs_valid = false;
   const double *cur_obs = nullptr;   // set by rank_and_es for the ES launches of the current call
   int cur_obs_R = 1;
@@ -214,6 +214,9 @@ int launch_copy_observed(fgs_ctx *c, const double *d_obs, const int *d_ident, in
                          double *d_es);
 int launch_label_identity(fgs_ctx *c, const uint32_t *d_labels, const uint32_t *d_obs, int R, int W, int P,
                           int *d_ident);
+int ensure_tie_list(fgs_ctx *c);
+int launch_es_mean_exact(fgs_ctx *c, const double *d_scores, int G, long long C, int es_kind,
+                         int abs_flag, double *d_es);
 int launch_es_wks_ties(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
                        double *d_es);
 int launch_tie_members(fgs_ctx *c, int2 *d_out, int *d_out_ctr, int out_cap, int *d_overflow);

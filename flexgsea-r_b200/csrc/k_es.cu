@@ -526,7 +526,9 @@ es_wks_tie_kernel(const uint16_t *__restrict__ rank16, const double *__restrict_
 __global__ void __launch_bounds__(256)
 es_mean_kernel(const double *__restrict__ scores, int G, long long C,
                const int *__restrict__ set_off, const int *__restrict__ set_idx, int S, int es_kind,
-               int abs_flag, double *__restrict__ es_out) {
+               int abs_flag, double *__restrict__ es_out, int2 *__restrict__ tie_list,
+               int *__restrict__ tie_ctr, int tie_cap, const double *__restrict__ obs,
+               const int *__restrict__ ident, int R) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const long long nunits = (long long)S * C;
@@ -540,23 +542,90 @@ es_mean_kernel(const double *__restrict__ scores, int G, long long C,
     for (int j = lane; j < m; j += 32) {
       double v = sc[set_idx[off + j]];
       if (abs_flag) v = fabs(v);
-      if (es_kind == FGS_ES_MEAN) sp += v;
+      if (es_kind == FGS_ES_MEAN) { sp += v; sn += fabs(v); }
       else { double a = fabs(v); sp += (v + a) / 2; sn += (-v + a) / 2; }  // :734-735
     }
     sp = warp_sum(sp);
     sn = warp_sum(sn);
     if (lane == 0) {
       double es;
-      if (es_kind == FGS_ES_MEAN) es = sp / m;                 // :763
+      bool shaky;  // a sum that cancelled (mean) or a tie between the two sides (maxmean): redo exactly
+      if (es_kind == FGS_ES_MEAN) { es = sp / m; shaky = fabs(sp) <= ES_OBS_REL * sn; }  // :763
       else {
         double ps = sp / m, ng = sn / m;
         es = fmax(ps, ng);                                     // :736
         if (isnan(ps) || isnan(ng)) es = nan("");
         else if (ng > ps) es = -es;                            // :737, strict
+        shaky = fabs(ps - ng) <= ES_OBS_REL * fmax(ps, ng);
+      }
+      es_out[(size_t)col * S + s] = es;
+      if (shaky || near_observed(obs, ident, S, R, col, s, es)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, s);
+    }
+  }
+}
+
+// mean / maxmean of listed (column, set) units -- or of every unit when the list
+// overflowed or the problem is small -- the way the reference gets them: R sums in long
+// double, so the sum is exact to the last bit of the result; here double-double partial
+// sums per lane, combined in double-double, one rounding at the division.  Matters where
+// ES values tie exactly in the reference (rounded data, small universes, permutations that
+// reproduce the observed labelling) and a plain parallel sum would break the tie at random.
+__device__ __forceinline__ dd2 dd2_add_dd(dd2 a, dd2 b) { return dd2_add(dd2_add(a, b.hi), b.lo); }
+__device__ __forceinline__ double dd2_div_n(dd2 a, double n) {
+  const double q = a.hi / n;
+  const double r = fma(-q, n, a.hi) + a.lo;
+  return q + r / n;
+}
+__global__ void __launch_bounds__(256)
+es_mean_exact_kernel(const double *__restrict__ scores, int G, long long C,
+                     const int *__restrict__ set_off, const int *__restrict__ set_idx, int S,
+                     int es_kind, int abs_flag, const int2 *__restrict__ list,
+                     const int *__restrict__ ctr, int cap, double *__restrict__ es_out) {
+  const int lane = threadIdx.x & 31;
+  const int listed = *ctr;
+  const bool all = listed > cap;
+  const long long nunit = all ? (long long)S * C : listed;
+  for (long long u = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < nunit;
+       u += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const long long col = all ? u / S : list[u].x;
+    const int s = all ? (int)(u % S) : list[u].y;
+    const double *sc = scores + (size_t)col * G;
+    const int off = set_off[s], m = set_off[s + 1] - off;
+    dd2 sp = {0.0, 0.0}, sn = {0.0, 0.0};
+    for (int j = lane; j < m; j += 32) {
+      double v = sc[set_idx[off + j]];
+      if (abs_flag) v = fabs(v);
+      if (es_kind == FGS_ES_MEAN) sp = dd2_add(sp, v);
+      else { const double a = fabs(v); sp = dd2_add(sp, (v + a) / 2); sn = dd2_add(sn, (-v + a) / 2); }  // :734-735
+    }
+    for (int o = 16; o; o >>= 1) {
+      dd2 t = {__shfl_xor_sync(0xffffffffu, sp.hi, o), __shfl_xor_sync(0xffffffffu, sp.lo, o)};
+      sp = dd2_add_dd(sp, t);
+      dd2 t2 = {__shfl_xor_sync(0xffffffffu, sn.hi, o), __shfl_xor_sync(0xffffffffu, sn.lo, o)};
+      sn = dd2_add_dd(sn, t2);
+    }
+    if (lane == 0) {
+      double es;
+      if (es_kind == FGS_ES_MEAN) es = dd2_div_n(sp, (double)m);  // :763
+      else {
+        const double ps = dd2_div_n(sp, (double)m), ng = dd2_div_n(sn, (double)m);
+        es = fmax(ps, ng);                                       // :736
+        if (isnan(ps) || isnan(ng)) es = nan("");
+        else if (ng > ps) es = -es;                              // :737, strict
       }
       es_out[(size_t)col * S + s] = es;
     }
   }
+}
+int launch_es_mean_exact(fgs_ctx *c, const double *d_scores, int G, long long C, int es_kind,
+                         int abs_flag, double *d_es) {
+  if (C <= 0 || c->S <= 0) return FGS_OK;
+  es_mean_exact_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(d_scores, G, C, c->set_off.p, c->set_idx.p, c->S,
+                                                           es_kind, abs_flag, c->tie_list.p, c->tie_ctr.p,
+                                                           c->tie_cap, d_es);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
 }
 
 int launch_es_wks_generic(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G,
@@ -784,12 +853,7 @@ __global__ void set_int_kernel(int *p, int v) { *p = v; }
 int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
                   double *d_es, bool defer_ties) {
   if (C <= 0 || c->S <= 0) return FGS_OK;
-  if (c->tie_cap == 0) {
-    c->tie_cap = 1 << 22;  // 32 MB of (column, set) pairs per block; beyond that every unit is redone
-    FGS_TRY(c->tie_list.ensure((size_t)c->tie_cap));
-    FGS_TRY(c->tie_ctr.ensure(4));
-  }
-  FGS_CUDA(cudaMemsetAsync(c->tie_ctr.p, 0, 4 * sizeof(int), c->stream));
+  FGS_TRY(ensure_tie_list(c));
   if (c->cur_exact_all) {  // a small problem: every unit by es_wks_tie_kernel (a count above the cap means "all")
     set_int_kernel<<<1, 1, 0, c->stream>>>(c->tie_ctr.p, c->tie_cap + 1);
     c->launches++;
@@ -813,7 +877,9 @@ template <bool MAXMEAN>
 __global__ void __launch_bounds__(ESM_THREADS, 1)
 es_mean_smem_kernel(const double *__restrict__ scores, int G, long long C,
                     const int4 *__restrict__ set_info, const uint16_t *__restrict__ idx16, int S,
-                    int abs_flag, double *__restrict__ es_out) {
+                    int abs_flag, double *__restrict__ es_out, int2 *__restrict__ tie_list,
+                    int *__restrict__ tie_ctr, int tie_cap, const double *__restrict__ obs,
+                    const int *__restrict__ ident, int R) {
   extern __shared__ __align__(16) unsigned char smem[];
   double *s_sc = (double *)smem;  // [G + 1]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -829,10 +895,13 @@ es_mean_smem_kernel(const double *__restrict__ scores, int G, long long C,
     }
     __syncthreads();
     double *es_col = es_out + (size_t)col * S;
+    // observed ES of this column's response; none for a label-preserving permutation (copied later)
+    const double *col_obs = (obs && !(ident && __ldg(ident + col / R))) ? obs + (size_t)(col % R) * S : nullptr;
     for (int q = warp; q < nquads; q += nwarps) {
       const int k = 4 * q + seg;
       int4 info = make_int4(0, 0, 0, 0);
       if (k < S) info = __ldg(set_info + k);
+      const double e_obs = (col_obs && k < S) ? __ldg(col_obs + info.w) : nan("");
       const int m = info.y & 0x7fffffff;  // duplicates are just members here
       const int nblk = (m + 7) >> 3;
       int nb = (nblk + 7) >> 3;           // 16-byte loads per lane, the same count for the whole warp
@@ -849,7 +918,7 @@ es_mean_smem_kernel(const double *__restrict__ scores, int G, long long C,
           for (int i = 0; i < 4; i++) {
             const double v0 = s_sc[ww[i] & 0xffffu], v1 = s_sc[ww[i] >> 16];
             sv0 += v0; sv1 += v1;
-            if (MAXMEAN) { sa0 += fabs(v0); sa1 += fabs(v1); }
+            sa0 += fabs(v0); sa1 += fabs(v1);  // (mean: only to notice a sum that cancelled)
           }
         }
       }
@@ -857,26 +926,48 @@ es_mean_smem_kernel(const double *__restrict__ scores, int G, long long C,
 #pragma unroll
       for (int o = 4; o; o >>= 1) {
         sv += __shfl_xor_sync(0xffffffffu, sv, o);
-        if (MAXMEAN) sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
       }
       if (ls == 0 && k < S) {
         double es;
-        if (!MAXMEAN) es = sv / m;
+        bool shaky;  // a sum that cancelled (mean) or a tie between the two sides (maxmean): redo exactly
+        if (!MAXMEAN) { es = sv / m; shaky = fabs(sv) <= ES_OBS_REL * sa; }
         else {
           const double ps = (sa + sv) / 2 / m, ng = (sa - sv) / 2 / m;
           es = fmax(ps, ng);
           if (isnan(ps) || isnan(ng)) es = nan("");
           else if (ng > ps) es = -es;
+          shaky = fabs(ps - ng) <= ES_OBS_REL * fmax(ps, ng);
         }
         es_col[info.w] = es;
+        if (shaky || fabs(es - e_obs) <= ES_OBS_REL * fabs(e_obs)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, info.w);
       }
     }
   }
 }
 
+int ensure_tie_list(fgs_ctx *c) {
+  if (c->tie_cap == 0) {
+    c->tie_cap = 1 << 22;  // 32 MB of (column, set) pairs per block; beyond that every unit is redone
+    FGS_TRY(c->tie_list.ensure((size_t)c->tie_cap));
+    FGS_TRY(c->tie_ctr.ensure(4));
+  }
+  FGS_CUDA(cudaMemsetAsync(c->tie_ctr.p, 0, 4 * sizeof(int), c->stream));
+  return FGS_OK;
+}
+
+// maxmean / mean of C score columns.  Units that land within rounding of the observed ES are
+// listed (the caller redoes them with launch_es_mean_exact); a small problem is done exactly
+// from the start.
 int launch_es_mean(fgs_ctx *c, const double *d_scores, int G, long long C, int es_kind,
                    int abs_flag, double *d_es) {
   if (C <= 0 || c->S <= 0) return FGS_OK;
+  FGS_TRY(ensure_tie_list(c));
+  if (c->cur_exact_all) {
+    set_int_kernel<<<1, 1, 0, c->stream>>>(c->tie_ctr.p, c->tie_cap + 1);
+    c->launches++;
+    return FGS_OK;  // launch_es_mean_exact (all units) follows
+  }
   const size_t smem = ((size_t)G + 2) * 8;
   if (smem <= (size_t)c->smem_optin && G <= 65534) {
     int grid = c->num_sms;
@@ -885,11 +976,13 @@ int launch_es_mean(fgs_ctx *c, const double *d_scores, int G, long long C, int e
     if (es_kind == FGS_ES_MAXMEAN) {
       auto k = es_mean_smem_kernel<true>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<grid, ESM_THREADS, smem, c->stream>>>(d_scores, G, C, c->set_info.p, c->set_idx16.p, c->S, abs_flag, d_es);
+      k<<<grid, ESM_THREADS, smem, c->stream>>>(d_scores, G, C, c->set_info.p, c->set_idx16.p, c->S, abs_flag, d_es,
+                                                c->tie_list.p, c->tie_ctr.p, c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R);
     } else {
       auto k = es_mean_smem_kernel<false>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<grid, ESM_THREADS, smem, c->stream>>>(d_scores, G, C, c->set_info.p, c->set_idx16.p, c->S, abs_flag, d_es);
+      k<<<grid, ESM_THREADS, smem, c->stream>>>(d_scores, G, C, c->set_info.p, c->set_idx16.p, c->S, abs_flag, d_es,
+                                                c->tie_list.p, c->tie_ctr.p, c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R);
     }
   } else {  // column does not fit on chip: gather through L1/L2
     long long units = (long long)c->S * C;
@@ -898,7 +991,8 @@ int launch_es_mean(fgs_ctx *c, const double *d_scores, int G, long long C, int e
     if (blocks > cap) blocks = cap;
     es_mean_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(d_scores, G, C, c->set_off.p,
                                                             c->set_idx.p, c->S, es_kind, abs_flag,
-                                                            d_es);
+                                                            d_es, c->tie_list.p, c->tie_ctr.p, c->tie_cap,
+                                                            c->cur_obs, c->cur_ident, c->cur_obs_R);
   }
   c->launches++;
   FGS_CUDA(cudaGetLastError());

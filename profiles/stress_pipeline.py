@@ -16,6 +16,8 @@ import pyoracle as oracle
 def run(ncase, seed, ctx=None, fdr_strict_always=False):
     rng = np.random.default_rng(seed)
     ctx = ctx or fg.Context(0)
+    if os.environ.get('EXACT_SMALL') is not None:
+        ctx.set_option('es_exact_small', int(os.environ['EXACT_SMALL']))
     oracle.use_all_cores()
     bad = 0
     for case in range(ncase):
@@ -42,40 +44,47 @@ def run(ncase, seed, ctx=None, fdr_strict_always=False):
             dup = rng.integers(0, P + 1, size=max(1, P // 10))
             usc[:, 0, dup[1:]] = usc[:, 0, [dup[0]]]   # identical score columns (incl. possibly the observed one)
             abs_flag = False
-        tag = dict(case=case, G=G, n=n, S=S, P=P, abs=abs_flag, simple=simple, user=user)
+        es_kind = int(rng.choice([nat.ES_WEIGHTED_KS, nat.ES_WEIGHTED_KS, nat.ES_WEIGHTED_KS, nat.ES_MAXMEAN, nat.ES_MEAN]))
+        okind = {nat.ES_WEIGHTED_KS: oracle.ES_WKS, nat.ES_MAXMEAN: oracle.ES_MAXMEAN, nat.ES_MEAN: oracle.ES_MEAN}[es_kind]
+        wks = es_kind == nat.ES_WEIGHTED_KS
+        tag = dict(case=case, G=G, n=n, S=S, P=P, abs=abs_flag, simple=simple, user=user, es=es_kind)
         if os.environ.get("ONLY") and int(os.environ["ONLY"]) != case:
             continue
         why = []
         # ---- oracle
         if user:
             o_sc = np.asfortranarray(usc[:, :, 0])
-            rc, o_null = oracle.es_from_scores(oracle.ES_WKS, usc[:, :, 1:], off, idx)
+            rc, o_null = oracle.es_from_scores(okind, usc[:, :, 1:], off, idx)
         else:
             o_sc = oracle.s2n_post(oracle.s2n_C(x, y), abs_flag)
             if not np.isfinite(o_sc).all():
                 continue  # the reference stops here (:251-253)
-            rc, o_null = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, oracle.ES_WKS, abs_flag=abs_flag)
-        o_obs = [oracle.wks_column(o_sc[:, 0], oracle.rank_desc(o_sc[:, 0]), s_, extras=True) for s_ in sets]
+            rc, o_null = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, okind, abs_flag=abs_flag)
         if rc != 0:
             continue
-        o_es = np.array([o["es"] for o in o_obs])
+        if wks:
+            o_obs = [oracle.wks_column(o_sc[:, 0], oracle.rank_desc(o_sc[:, 0]), s_, extras=True) for s_ in sets]
+            o_es = np.array([o["es"] for o in o_obs])
+        else:
+            o_obs = None
+            o_es = oracle.es_from_scores(okind, o_sc.reshape(G, 1, 1), off, idx)[1][:, 0, 0]
         o_sig = oracle.calc_sig(o_es, o_null[:, 0, :], not simple, not simple, abs_flag)
         # ---- device
         try:
             ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
             sc = o_sc.copy() if user else ctx.score_observed(nat.SCORE_S2N, abs_flag=abs_flag)
-            obs = ctx.observed_es(nat.ES_WEIGHTED_KS, sc, ragged=True)
+            obs = ctx.observed_es(es_kind, sc, ragged=True)
             if user:
-                ctx.es_from_scores(nat.ES_WEIGHTED_KS, usc[:, :, 1:], want_host=False)
+                ctx.es_from_scores(es_kind, usc[:, :, 1:], want_host=False)
             else:
-                ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm, abs_flag=abs_flag, want_host=False)
+                ctx.perm_null(nat.SCORE_S2N, es_kind, P, perm=perm, abs_flag=abs_flag, want_host=False)
             sig = ctx.calc_sig(obs["es"][:, 0], 0, not simple, not simple, abs_flag)
         except nat.FlexgseaError as e:
             bad += 1; print("MISMATCH device error", e, tag); continue
         if not np.array_equal(sc[:, 0], o_sc[:, 0]): why.append("observed scores")
         es = obs["es"][:, 0]
         if not np.array_equal(np.isnan(es), np.isnan(o_es)) or np.nanmax(np.abs(es - o_es), initial=0.0) > 1e-10: why.append("observed es")
-        for k_, s_ in enumerate(sets):
+        for k_, s_ in enumerate(sets if wks else []):
             o = o_obs[k_]
             if np.isnan(o["es"]):
                 continue
@@ -102,8 +111,8 @@ def run(ncase, seed, ctx=None, fdr_strict_always=False):
             bad += 1; print("MISMATCH", tag, why[:6])
             if os.environ.get("ONLY"):
                 d_null = np.zeros((len(sets), 1, P), order="F")
-                d_null = (ctx.es_from_scores(nat.ES_WEIGHTED_KS, usc[:, :, 1:]) if user else
-                          ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm, abs_flag=abs_flag))
+                d_null = (ctx.es_from_scores(es_kind, usc[:, :, 1:]) if user else
+                          ctx.perm_null(nat.SCORE_S2N, es_kind, P, perm=perm, abs_flag=abs_flag))
                 for k_ in range(len(sets)):
                     if not simple and not np.array_equal(sig["fdr_counts"][k_], o_sig["fdr_counts"][k_]):
                         print("  fdr set", k_, sets[k_].tolist(), "nes dev/oracle", repr(sig["nes"][k_]), repr(o_sig["nes"][k_]), "counts", sig["fdr_counts"][k_], o_sig["fdr_counts"][k_])

@@ -146,7 +146,8 @@ def test_random_small_shapes(ctx):
 
 
 def test_random_small_pipelines(ctx):
-    """1 500 random small flexgsea() pipelines (profiles/stress_pipeline.py): observed
+    """1 500 random small flexgsea() pipelines (profiles/stress_pipeline.py; weighted KS,
+    maxmean and mean; s2n and user-made score columns with ties): observed
     scores bit-exact, observed ES / max_es_at / le_prop / leading edge / running_es_at
     exact, and the p-value COUNTS identical to the oracle pipeline even with 4-8
     samples and a dozen genes, where the null takes a handful of values and equality
