@@ -509,6 +509,43 @@ def test_small_n_label_preserving_permutations(ctx, oracle):
     assert np.allclose(got["fdr"], want["fdr"], rtol=1e-10, atol=0)
 
 
+@pytest.mark.parametrize("exact_small", [0, 1])
+@pytest.mark.parametrize("es_kind", ["wks", "maxmean", "mean"])
+def test_two_responses_small_n_pipeline(ctx, oracle, es_kind, exact_small):
+    """two responses, six samples: the observed ES handed to the null loop is indexed by
+    (response, set); p / FDR / global counts of every response match the oracle pipeline,
+    on the production kernels (+ exact redo of the flagged units) and on the all-exact
+    small-problem path"""
+    G, n, S, P = 400, 6, 30, 300
+    off, idx = synth.gene_sets_csr(G, S, (5, 60), "uniform", seed=31)
+    x, y0 = synth.two_class(G, n, off, idx, seed=32)
+    y = np.column_stack([y0[:, 0], np.array([1, 0, 1, 0, 0, 1])]).astype(np.int32)
+    perm = synth.perm_matrix(n, P, seed=33)
+    k = {"wks": nat.ES_WEIGHTED_KS, "maxmean": nat.ES_MAXMEAN, "mean": nat.ES_MEAN}[es_kind]
+    ok = {"wks": oracle.ES_WKS, "maxmean": oracle.ES_MAXMEAN, "mean": oracle.ES_MEAN}[es_kind]
+    ctx.set_option("es_exact_small", exact_small)
+    try:
+        ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+        sc = ctx.score_observed(nat.SCORE_S2N)
+        obs = ctx.observed_es(k, sc, ragged=False)["es"]
+        ctx.perm_null(nat.SCORE_S2N, k, P, perm=perm, want_host=False)
+        o_sc = oracle.s2n_post(oracle.s2n_C(x, y))
+        assert np.array_equal(sc, o_sc)
+        rc, o_obs = oracle.es_from_scores(ok, o_sc.reshape(G, 2, 1), off, idx)
+        rc2, o_null = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, ok)
+        assert rc == 0 and rc2 == 0
+        assert np.abs(obs - o_obs[:, :, 0]).max() <= ES_TOL
+        for r in range(2):
+            got = ctx.calc_sig(obs[:, r], r, True, True, False)
+            want = oracle.calc_sig(o_obs[:, r, 0], o_null[:, r, :], True, True, False)
+            assert np.array_equal(got["p_counts"], want["p_counts"]), r
+            assert np.array_equal(got["fdr_counts"], want["fdr_counts"]), r
+            assert np.array_equal(got["glob_counts"], want["glob_counts"]), r
+            assert np.allclose(got["fdr"], want["fdr"], rtol=1e-10, atol=0, equal_nan=True)
+    finally:
+        ctx.set_option("es_exact_small", 0)
+
+
 def test_fdr_reference_properties_on_device(ctx):
     """tests/testthat/test_fdr.R:20-54 through the device path."""
     from test_oracle_golden import _fdr_inputs
