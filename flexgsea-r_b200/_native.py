@@ -22,7 +22,7 @@ ES_WEIGHTED_KS, ES_MAXMEAN, ES_MEAN = 0, 1, 2
 SYMBOLS = [
     "fgs_abi_version", "fgs_last_error", "fgs_device_count", "fgs_create", "fgs_destroy",
     "fgs_s2n", "fgs_set_x", "fgs_set_gene_sets", "fgs_set_response_s2n", "fgs_set_response_lm",
-    "fgs_n_response", "fgs_score_observed", "fgs_observed_es", "fgs_perm_null",
+    "fgs_n_response", "fgs_score_observed", "fgs_observed_es", "fgs_set_observed_es", "fgs_perm_null",
     "fgs_es_from_scores", "fgs_debug_last_scores", "fgs_null_device_ptr", "fgs_set_null",
     "fgs_calc_sig", "fgs_sig_stage1", "fgs_sig_stage2", "fgs_sig_finish", "fgs_launch_count",
     "fgs_last_timings", "fgs_set_profiling", "fgs_set_option",
@@ -208,6 +208,12 @@ class Context:
             self._check(self._lib.fgs_observed_es(self._h, es_kind, C.c_double(p), _p(sc, _dp), G, R,
                                                   _p(es, _dp), None, None, None, None, None, None, None))
         return res
+
+    def set_observed_es(self, es_kind, es):
+        """observed ES [S x R] computed elsewhere: handed to the null loop like
+        observed_es() does with its own result"""
+        e = _f(es if np.ndim(es) == 2 else np.asarray(es).reshape(-1, 1))
+        self._check(self._lib.fgs_set_observed_es(self._h, int(es_kind), _p(e, _dp), e.shape[0], e.shape[1]))
 
     # ---- null ------------------------------------------------------------
     def perm_null(self, score_kind, es_kind, n_perm, perm=None, seed=0, perm_id0=0, p=1.0,

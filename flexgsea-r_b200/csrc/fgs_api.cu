@@ -831,6 +831,18 @@ int fgs_observed_es(fgs_ctx *c, int es_kind, double p_exp, const double *scores,
   return rc;
 }
 
+int fgs_set_observed_es(fgs_ctx *c, int es_kind, const double *es, int n_sets, int n_response) {
+  if (!c || !es || n_sets <= 0 || n_response <= 0) { set_error("fgs_set_observed_es: bad argument"); return FGS_ERR_ARG; }
+  FGS_TRY(use_device(c));
+  if (c->S != n_sets) { set_error("fgs_set_observed_es: %d sets given, %d resident", n_sets, c->S); return FGS_ERR_ARG; }
+  const size_t SR = (size_t)n_sets * n_response;
+  FGS_TRY(c->obs_es.ensure(SR));
+  FGS_TRY(h2d(c, c->obs_es.p, es, SR));
+  FGS_TRY(sync(c));
+  c->obs_S = n_sets; c->obs_R = n_response; c->obs_kind = es_kind; c->obs_valid = true;
+  return FGS_OK;
+}
+
 // ---------------------------------------------------------------------------
 // significance
 static int sig_check(fgs_ctx *c, int response) {

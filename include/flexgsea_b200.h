@@ -105,6 +105,11 @@ int fgs_observed_es(fgs_ctx *ctx, int es_kind, double p_exponent, const double *
                     int n_gene, int n_response, double *es, double *max_es_at, double *le_prop,
                     int *running_es_at, double *running_es_pos, double *running_es_neg,
                     int *le_first, int *le_count);
+/* The same hand-over for an observed ES that was computed elsewhere (e.g. by the R
+ * closures of a caller that keeps the observed pass in R): es [S x R] for the
+ * ES kind the null loop will use. */
+int fgs_set_observed_es(fgs_ctx *ctx, int es_kind, const double *es, int n_sets, int n_response);
+
 
 /* ---- null loop: flexgsea_perm_sequential / _parallel (:356-472) -------- */
 /* Computes es_null [S, R, n_perm] for permutations perm_id0 .. perm_id0 +

@@ -528,6 +528,9 @@ def test_two_responses_small_n_pipeline(ctx, oracle, es_kind, exact_small):
         ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
         sc = ctx.score_observed(nat.SCORE_S2N)
         obs = ctx.observed_es(k, sc, ragged=False)["es"]
+        if exact_small == 0:  # same hand-over through the explicit entry point
+            ctx.set_gene_sets(off, idx)      # (forgets the observed ES)
+            ctx.set_observed_es(k, obs)
         ctx.perm_null(nat.SCORE_S2N, k, P, perm=perm, want_host=False)
         o_sc = oracle.s2n_post(oracle.s2n_C(x, y))
         assert np.array_equal(sc, o_sc)
