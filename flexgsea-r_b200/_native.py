@@ -25,7 +25,7 @@ SYMBOLS = [
     "fgs_n_response", "fgs_score_observed", "fgs_observed_es", "fgs_set_observed_es", "fgs_perm_null",
     "fgs_es_from_scores", "fgs_debug_last_scores", "fgs_null_device_ptr", "fgs_set_null",
     "fgs_calc_sig", "fgs_sig_stage1", "fgs_sig_stage2", "fgs_sig_finish", "fgs_launch_count",
-    "fgs_last_timings", "fgs_set_profiling", "fgs_set_option",
+    "fgs_last_timings", "fgs_set_profiling", "fgs_set_option", "fgs_set_progress",
     "fgs_gmt_parse", "fgs_gmt_read", "fgs_gmt_n_sets", "fgs_gmt_nnz", "fgs_gmt_offsets", "fgs_gmt_index",
     "fgs_gmt_set_name", "fgs_gmt_stats", "fgs_gmt_free",
 ]
@@ -319,6 +319,17 @@ class Context:
         self._check(self._lib.fgs_last_timings(self._h, ms, ln))
         keys = ("perm", "score", "rank", "es", "total")
         return {k: ms[i] for i, k in enumerate(keys)}, {k: ln[i] for i, k in enumerate(keys)}
+
+    def set_progress(self, fn):
+        """fn(columns_done, columns_total) -> truthy to stop the running null loop
+        (FlexgseaError with code 7); None removes the hook."""
+        if fn is None:
+            self._progress_cb = None
+            self._check(self._lib.fgs_set_progress(self._h, None, None))
+            return
+        proto = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_longlong, C.c_longlong)
+        self._progress_cb = proto(lambda _u, done, total: 1 if fn(int(done), int(total)) else 0)
+        self._check(self._lib.fgs_set_progress(self._h, self._progress_cb, None))
 
     def set_option(self, name, value):
         self._check(self._lib.fgs_set_option(self._h, name.encode(), C.c_longlong(int(value))))

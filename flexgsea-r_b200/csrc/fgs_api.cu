@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <climits>
+#include <thread>
 
 #include "fgs_common.cuh"
 
@@ -47,6 +48,59 @@ static int d2h(fgs_ctx *c, T *dst, const T *src, size_t n) {
 }
 static int sync(fgs_ctx *c) {
   FGS_CUDA(cudaStreamSynchronize(c->stream));
+  return FGS_OK;
+}
+
+// Host -> device upload of a large pageable array (user score columns).  A plain copy from
+// pageable memory runs at the pace of the driver's single staging thread (about 10 GB/s
+// measured); here `T` host threads each copy 8 MB pieces into their own two pinned staging
+// slots and queue the DMA of a piece as soon as it is staged, so the staging memcpy of one
+// thread overlaps the others' and the link.  Pieces land in any order; the caller records its
+// event on `st` after this returns (every DMA is queued by then).
+static const size_t STAGE_PIECE = 8u << 20;
+static int staged_upload(fgs_ctx *c, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+  int T = std::max(1, std::min(c->opt_h2d_threads, 8));
+  const unsigned hc = std::thread::hardware_concurrency();
+  if (hc && (unsigned)T > hc) T = (int)hc;
+  if (bytes < 4 * STAGE_PIECE || c->opt_h2d_threads <= 0) {
+    FGS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return FGS_OK;
+  }
+  const size_t need = (size_t)16 * STAGE_PIECE;
+  if (!c->stage) {
+    cudaError_t e = cudaHostAlloc((void **)&c->stage, need, cudaHostAllocDefault);
+    if (e != cudaSuccess) {  // no pinned memory to be had: the plain copy still works
+      cudaGetLastError();
+      c->stage = nullptr;
+      FGS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+      return FGS_OK;
+    }
+    c->stage_bytes = need;
+    for (int i = 0; i < 16; i++) FGS_CUDA(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+  }
+  const size_t n_piece = (bytes + STAGE_PIECE - 1) / STAGE_PIECE;
+  std::vector<int> status(T, 0);
+  auto worker = [&](int t) {
+    if (cudaSetDevice(c->device) != cudaSuccess) { status[t] = 1; return; }
+    int turn = 0;
+    for (size_t i = (size_t)t; i < n_piece; i += (size_t)T, turn ^= 1) {
+      const int slot = 2 * t + turn;
+      char *buf = c->stage + (size_t)slot * STAGE_PIECE;
+      const size_t o = i * STAGE_PIECE, len = std::min(STAGE_PIECE, bytes - o);
+      // the slot's previous piece (of this call or an earlier one) must have left; an event never
+      // recorded counts as complete
+      if (cudaEventSynchronize(c->stage_ev[slot]) != cudaSuccess) { status[t] = 1; return; }
+      memcpy(buf, (const char *)src + o, len);
+      if (cudaMemcpyAsync((char *)dst + o, buf, len, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+          cudaEventRecord(c->stage_ev[slot], st) != cudaSuccess) { status[t] = 1; return; }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; t++) th.emplace_back(worker, t);
+  worker(0);
+  for (auto &x : th) x.join();
+  for (int t = 0; t < T; t++)
+    if (status[t]) { cudaStreamSynchronize(st); set_error("staged upload failed: %s", cudaGetErrorString(cudaGetLastError())); return FGS_ERR_CUDA; }
   return FGS_OK;
 }
 
@@ -312,7 +366,12 @@ int fgs_create(int device, fgs_ctx **out) {
   c->num_sms = prop.multiProcessorCount;
   c->smem_optin = (int)prop.sharedMemPerBlockOptin;
   FGS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  FGS_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; i++) FGS_CUDA(cudaEventCreate(&c->ev[i]));
+  for (int i = 0; i < 2; i++) {
+    FGS_CUDA(cudaEventCreateWithFlags(&c->blk_copy[i], cudaEventDisableTiming));
+    FGS_CUDA(cudaEventCreateWithFlags(&c->blk_done[i], cudaEventDisableTiming));
+  }
   *out = c;
   return FGS_OK;
 }
@@ -328,12 +387,45 @@ int fgs_destroy(fgs_ctx *c) {
   c->api_l.release();
   c->set_info.release(); c->set_invgm.release(); c->slow_ids.release(); c->ybin.release();
   c->n1n2.release(); c->lm_H.release(); c->perm.release(); c->labels.release(); c->lm_B.release();
-  c->scores.release(); c->rank16.release(); c->sabs.release(); c->sort_keys.release();
+  c->scores.release(); c->scores2.release(); c->rank16.release(); c->sabs.release(); c->sort_keys.release();
   c->sort_idx.release(); c->flags.release(); c->counters.release(); c->es_null.release();
   c->sig_d.release(); c->sig_i.release();
   for (int i = 0; i < 2; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 2; i++) {
+    if (c->blk_copy[i]) cudaEventDestroy(c->blk_copy[i]);
+    if (c->blk_done[i]) cudaEventDestroy(c->blk_done[i]);
+  }
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->stage) {
+    cudaFreeHost(c->stage);
+    for (int i = 0; i < 16; i++) if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
+  }
   cudaStreamDestroy(c->stream);
   delete c;
+  return FGS_OK;
+}
+
+int fgs_set_progress(fgs_ctx *c, fgs_progress_fn cb, void *user) {
+  if (!c) return FGS_ERR_ARG;
+  c->progress = cb;
+  c->progress_user = user;
+  return FGS_OK;
+}
+
+// Block-loop hook: with a progress callback set, wait until the block two back is finished
+// (so at most two blocks are queued), report, and stop when asked to.  `k` = index of the block
+// just enqueued; its blk_done event is recorded here.
+static int block_progress(fgs_ctx *c, long long k, long long cols_per_block, long long total) {
+  if (!c->progress) return FGS_OK;
+  const int slot = (int)(k & 1);
+  if (k >= 2) FGS_CUDA(cudaEventSynchronize(c->blk_done[slot]));
+  FGS_CUDA(cudaEventRecord(c->blk_done[slot], c->stream));
+  const long long done = std::min(total, std::max<long long>(0, k - 1) * cols_per_block);
+  if (c->progress(c->progress_user, done, total) != 0) {
+    cudaStreamSynchronize(c->stream);
+    set_error("stopped by the progress callback after %lld of %lld score columns", done, total);
+    return FGS_ERR_CANCELLED;
+  }
   return FGS_OK;
 }
 
@@ -356,6 +448,7 @@ int fgs_last_timings(fgs_ctx *c, float *ms, long long *launches) {
 int fgs_set_option(fgs_ctx *c, const char *name, long long value) {
   if (!c || !name) return FGS_ERR_ARG;
   if (!strcmp(name, "perm_block")) c->opt_perm_block = (int)value;
+  else if (!strcmp(name, "h2d_threads")) c->opt_h2d_threads = (int)value;
   else if (!strcmp(name, "force_generic_es")) c->opt_force_generic = (int)value;
   else if (!strcmp(name, "force_sort64")) c->opt_sort64 = (int)value;
   else if (!strcmp(name, "s2n_mode")) c->opt_s2n_mode = (int)value;
@@ -652,6 +745,10 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
     if (c->cur_ident)
       FGS_TRY(launch_copy_observed(c, c->cur_obs, c->cur_ident, R, (long long)Pb * R,
                                    c->es_null.p + (size_t)p0 * R * S));
+    if (c->progress) {
+      const int prc = block_progress(c, p0 / Pb_max, (long long)Pb_max * R, (long long)P * R);
+      if (prc != FGS_OK) { c->cur_ident = nullptr; c->cur_exact_all = false; return prc; }
+    }
   }
   c->cur_ident = nullptr;
   c->cur_exact_all = false;
@@ -709,17 +806,49 @@ int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scor
     FGS_TRY(flags_reset(c, C));
     FGS_CUDA(cudaEventRecord(c->ev[0], c->stream));
     StageTimer tm(c);
+    // Blocks of score columns stream in: block k+1 is uploaded on copy_stream into the second
+    // score buffer while block k is checked, ranked and scored on the compute stream (the step a
+    // user-defined gene.score.fn feeds, R/flexgsea.R:393-394).  The compute work
+    // of a block is enqueued BEFORE the next upload is issued: an upload from pageable host memory
+    // keeps the calling thread busy, and the device must already have its work by then.
     const long long Cb_max = block_columns(c, C);
-    for (long long c0 = 0; c0 < C; c0 += Cb_max) {
-      const long long Cb = std::min(Cb_max, C - c0);
-      FGS_TRY(c->scores.ensure((size_t)n_gene * Cb));
+    const long long n_blk = (C + Cb_max - 1) / Cb_max;
+    const size_t blk_elems = (size_t)n_gene * std::min(Cb_max, C);
+    FGS_TRY(c->scores.ensure(blk_elems));
+    if (n_blk > 1) FGS_TRY(c->scores2.ensure(blk_elems));
+    auto upload = [&](long long k, double *dst) -> int {
+      const long long c0 = k * Cb_max, Cb = std::min(Cb_max, C - c0);
+      const int slot = (int)(k & 1);
+      if (k >= 2) FGS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->blk_done[slot], 0));
+      FGS_TRY(staged_upload(c, dst, scores + (size_t)c0 * n_gene, (size_t)n_gene * Cb * sizeof(double),
+                            c->copy_stream));
+      FGS_CUDA(cudaEventRecord(c->blk_copy[slot], c->copy_stream));
+      return FGS_OK;
+    };
+    // nothing queued earlier on the compute stream may still read the score buffers
+    FGS_CUDA(cudaEventRecord(c->blk_done[0], c->stream));
+    FGS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->blk_done[0], 0));
+    FGS_TRY(upload(0, c->scores.p));
+    int brc = FGS_OK;
+    for (long long k = 0; k < n_blk && brc == FGS_OK; k++) {
+      const long long c0 = k * Cb_max, Cb = std::min(Cb_max, C - c0);
+      const int slot = (int)(k & 1);
       tm.mark();
-      FGS_TRY(h2d(c, c->scores.p, scores + (size_t)c0 * n_gene, (size_t)n_gene * Cb));
+      FGS_CUDA(cudaStreamWaitEvent(c->stream, c->blk_copy[slot], 0));
       FGS_TRY(launch_check_finite(c, c->scores.p, (long long)n_gene * Cb, n_gene, c->flags.p + c0));
       tm.mark();
       FGS_TRY(rank_and_es(c, es_kind, p_exp, 0, Cb, c->es_null.p + (size_t)c0 * S, tm));
+      if (c->progress && k >= 2) FGS_CUDA(cudaEventSynchronize(c->blk_done[slot]));
+      FGS_CUDA(cudaEventRecord(c->blk_done[slot], c->stream));
+      if (k + 1 < n_blk) FGS_TRY(upload(k + 1, c->scores2.p));
+      if (c->progress && c->progress(c->progress_user, std::min(C, std::max<long long>(0, k - 1) * Cb_max), C) != 0) {
+        set_error("stopped by the progress callback");
+        brc = FGS_ERR_CANCELLED;
+      }
+      if (k + 1 < n_blk) std::swap(c->scores, c->scores2);
     }
     c->cur_exact_all = false;
+    if (brc != FGS_OK) { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream); return brc; }
     FGS_CUDA(cudaEventRecord(c->ev[1], c->stream));
     int r2 = flags_check(c, C);
     tm.finish(0.f);

@@ -72,6 +72,17 @@ struct fgs_ctx {
   float last_ms[5] = {0, 0, 0, 0, 0};
   long long last_launches[5] = {0, 0, 0, 0, 0};
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // user-score streaming (fgs_es_from_scores): upload of block k+1 on copy_stream while
+  // block k is ranked; blk_copy / blk_done order the two score buffers
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t blk_copy[2] = {nullptr, nullptr}, blk_done[2] = {nullptr, nullptr};
+  // pinned staging ring of the threaded host->device upload (fgs_api.cu: staged_upload)
+  char *stage = nullptr;
+  size_t stage_bytes = 0;
+  cudaEvent_t stage_ev[16] = {};
+  int opt_h2d_threads = 8;
+  int (*progress)(void *, long long, long long) = nullptr;
+  void *progress_user = nullptr;
 
   // options
   int opt_perm_block = 0;      // 0 = auto
@@ -151,6 +162,7 @@ struct fgs_ctx {
 
   // per-block scratch
   fgs::DevBuf<double> scores;     // [Cb][G]
+  fgs::DevBuf<double> scores2;    // second block of user scores being uploaded (fgs_es_from_scores)
   fgs::DevBuf<uint16_t> rank16;   // [Cb][G] 1-based descending rank
   fgs::DevBuf<double> sabs;       // [Cb][G] |score|^p in rank order
   fgs::DevBuf<unsigned long long> sort_keys;  // ping-pong scratch

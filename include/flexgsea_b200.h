@@ -38,6 +38,7 @@ extern "C" {
 #define FGS_ERR_OOM 4
 #define FGS_ERR_STATE 5
 #define FGS_ERR_UNSUPPORTED 6
+#define FGS_ERR_CANCELLED 7 /* the progress callback asked to stop */
 
 /* gene.score.fn built-ins: flexgsea_s2n (R/flexgsea.R:689-723),
  * flexgsea_lm (:647-676) */
@@ -203,6 +204,17 @@ int fgs_launch_count(fgs_ctx *ctx, long long *count);
 int fgs_last_timings(fgs_ctx *ctx, float *ms, long long *launches);
 /* enable per-stage event timing (adds stream synchronisation points) */
 int fgs_set_profiling(fgs_ctx *ctx, int enabled);
+/* Progress / interrupt hook for the block loops of fgs_perm_null and
+ * fgs_es_from_scores: called on the calling thread once per block of score columns
+ * with the number of columns whose work is finished and the total; a non-zero return
+ * stops the call with FGS_ERR_CANCELLED (the null is then incomplete).  With a hook
+ * set the loop keeps at most two blocks in flight, so the answer to an interrupt
+ * comes within tens of milliseconds.  This is where an R binding polls
+ * R_CheckUserInterrupt (through R_ToplevelExec, so nothing longjmps over CUDA
+ * state); the reference is interruptible between its interpreted steps
+ * (R/flexgsea.R:372-417).  cb == NULL removes the hook. */
+typedef int (*fgs_progress_fn)(void *user, long long columns_done, long long columns_total);
+int fgs_set_progress(fgs_ctx *ctx, fgs_progress_fn cb, void *user);
 /* tuning / test hooks: "perm_block" (permutations per block), "force_generic_es"
  * (route every set through the duplicate-safe O(m^2) kernel), "force_sort64"
  * (rank with the 64-bit global-memory sort), "s2n_mode" (1, default: s2n scores

@@ -22,6 +22,7 @@ static void check(int rc) {
   // never Rf_error across frames that own CUDA resources: everything device side
   // is behind the C ABI and already unwound when we get the code back
   if (rc == FGS_ERR_NONFINITE) stop("Gene scoring function returned NA or Inf.");  // R/flexgsea.R:401
+  if (rc == FGS_ERR_CANCELLED) { Rf_onintr(); return; }  // the user interrupt seen by progress_hook_, raised here
   stop("flexgsea_b200: %s", fgs_last_error());
 }
 
@@ -80,6 +81,19 @@ void fgs_response_lm_(SEXP ctx, NumericMatrix design, bool has_intercept) {
 
 // es.null <- perm.fun(...) (R/flexgsea.R:305): perm is matrix(sample.int(n) per column), made in R so the
 // null is the one the reference's sequential loop draws under set.seed(); returns [S, R, P] like :363-368
+// Interrupt polling between blocks of the null loop: R_CheckUserInterrupt longjmps, so it runs
+// inside R_ToplevelExec and the answer goes back to the library as "stop" (FGS_ERR_CANCELLED),
+// which unwinds normally and releases nothing it should keep.
+static void poll_interrupt_(void *) { R_CheckUserInterrupt(); }
+static int progress_hook_(void *, long long, long long) {
+  return R_ToplevelExec(poll_interrupt_, nullptr) == FALSE;
+}
+
+// [[Rcpp::export]]
+void fgs_interruptible_(SEXP ctx, bool on) {
+  check(fgs_set_progress(ctx_of(ctx), on ? progress_hook_ : nullptr, nullptr));
+}
+
 // [[Rcpp::export]]
 NumericVector fgs_perm_null_(SEXP ctx, int score_kind, int es_kind, bool abs, IntegerMatrix perm,
                              int n_sets, int n_response, bool want_null) {

@@ -740,3 +740,88 @@ def test_flexgsea_lm_structure(ctx):
                       gene_score_fn=fg.flexgsea_lm, return_values=["es_null", "running_es_pos"], seed=2)
     assert res["es_null"].shape == (1, 2, 100)
     assert isinstance(res["running_es_pos"], dict)
+
+
+@pytest.mark.gpu
+def test_user_scores_stream_in_blocks(ctx, oracle):
+    """user score columns arrive block by block (upload of block k+1 while block k is ranked,
+    two score buffers): every block count, incl. a ragged last block, gives the one-block result"""
+    rng = np.random.default_rng(41)
+    G, R, P = 700, 2, 23
+    sc = rng.normal(size=(G, R, P))
+    sc[:, 1, 5] = np.round(sc[:, 1, 5], 1)
+    off, idx = synth.gene_sets_csr(G, 30, (5, 90), "uniform", seed=9)
+    ctx.set_gene_sets(off, idx)
+    rc, want = oracle.es_from_scores(oracle.ES_WKS, sc, off, idx)
+    assert rc == 0
+    try:
+        for blk in (0, 1, 4, 5, 23, 64):      # score columns per block (0: default); 46 columns in all
+            ctx.set_option("perm_block", blk)
+            got = ctx.es_from_scores(nat.ES_WEIGHTED_KS, sc)
+            assert np.abs(got - want).max() <= ES_TOL, blk
+            _, rk = ctx.debug_last(1, G=G)     # the resident buffer is the last block's
+        ctx.set_option("perm_block", 3)
+        for kind, ok in ((nat.ES_MEAN, oracle.ES_MEAN), (nat.ES_MAXMEAN, oracle.ES_MAXMEAN)):
+            g2 = ctx.es_from_scores(kind, sc)
+            _, w2 = oracle.es_from_scores(ok, sc, off, idx)
+            assert np.abs(g2 - w2).max() <= ES_TOL
+        bad = sc.copy(); bad[3, 1, P - 1] = np.nan    # in the last block
+        with pytest.raises(fg.NonFiniteScoreError):
+            ctx.es_from_scores(nat.ES_WEIGHTED_KS, bad)
+    finally:
+        ctx.set_option("perm_block", 0)
+
+
+@pytest.mark.gpu
+def test_user_scores_threaded_upload(ctx, oracle):
+    """blocks of 32 MB and more go up through the pinned staging ring filled by several host
+    threads; same ES as the plain copy, and as the oracle"""
+    rng = np.random.default_rng(43)
+    G, P = 20000, 560
+    sc = np.asfortranarray(rng.normal(size=(G, 1, P)))
+    off, idx = synth.gene_sets_csr(G, 40, (15, 300), "loguniform", seed=2)
+    ctx.set_gene_sets(off, idx)
+    try:
+        ctx.set_option("perm_block", 250)          # 40 MB blocks, ragged last block of 9.6 MB
+        res = {}
+        for th in (0, 1, 3, 8):
+            ctx.set_option("h2d_threads", th)
+            res[th] = ctx.es_from_scores(nat.ES_WEIGHTED_KS, sc)
+        for th in (1, 3, 8):
+            assert np.array_equal(res[th], res[0]), th
+        cols = [0, 249, 250, 499, 500, 559]
+        rc, want = oracle.es_from_scores(oracle.ES_WKS, np.asfortranarray(sc[:, :, cols]), off, idx)
+        assert rc == 0 and np.abs(res[3][:, :, cols] - want).max() <= ES_TOL
+    finally:
+        ctx.set_option("perm_block", 0)
+        ctx.set_option("h2d_threads", 8)
+
+
+@pytest.mark.gpu
+def test_progress_hook_reports_and_cancels(ctx, oracle):
+    x, y = synth.two_class(300, 24, seed=3)
+    off, idx = synth.gene_sets_csr(300, 12, (5, 40), "uniform", seed=4)
+    perm = synth.perm_matrix(24, 40, seed=5)
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    want = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, 40, perm=perm)
+    seen = []
+    try:
+        ctx.set_option("perm_block", 8)
+        ctx.set_progress(lambda done, total: seen.append((done, total)) or False)
+        got = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, 40, perm=perm)
+        assert np.array_equal(got, want)
+        assert len(seen) == 5 and all(t == 40 for _, t in seen)
+        assert [d for d, _ in seen] == sorted(d for d, _ in seen) and seen[-1][0] <= 40
+        ctx.set_progress(lambda done, total: done >= 8)
+        with pytest.raises(fg.FlexgseaError) as ei:
+            ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, 40, perm=perm)
+        assert ei.value.code == 7
+        sc = np.random.default_rng(1).normal(size=(300, 1, 40))
+        with pytest.raises(fg.FlexgseaError) as ei:
+            ctx.es_from_scores(nat.ES_WEIGHTED_KS, sc)
+        assert ei.value.code == 7
+        ctx.set_progress(None)
+        assert np.array_equal(ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, 40, perm=perm), want)
+    finally:
+        ctx.set_progress(None)
+        ctx.set_option("perm_block", 0)
