@@ -58,25 +58,39 @@ static int sync(fgs_ctx *c) {
 // thread overlaps the others' and the link.  Pieces land in any order; the caller records its
 // event on `st` after this returns (every DMA is queued by then).
 static const size_t STAGE_PIECE = 8u << 20;
-static int staged_upload(fgs_ctx *c, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+static bool stage_ring(fgs_ctx *c) {
+  if (c->stage) return true;
+  const size_t need = (size_t)16 * STAGE_PIECE;
+  if (cudaHostAlloc((void **)&c->stage, need, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    c->stage = nullptr;
+    return false;
+  }
+  c->stage_bytes = need;
+  for (int i = 0; i < 16; i++)
+    if (cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      cudaFreeHost(c->stage);
+      c->stage = nullptr;
+      return false;
+    }
+  return true;
+}
+static int stage_threads(fgs_ctx *c) {
   int T = std::max(1, std::min(c->opt_h2d_threads, 8));
   const unsigned hc = std::thread::hardware_concurrency();
   if (hc && (unsigned)T > hc) T = (int)hc;
+  return T;
+}
+static int staged_upload(fgs_ctx *c, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+  const int T = stage_threads(c);
   if (bytes < 4 * STAGE_PIECE || c->opt_h2d_threads <= 0) {
     FGS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
     return FGS_OK;
   }
-  const size_t need = (size_t)16 * STAGE_PIECE;
-  if (!c->stage) {
-    cudaError_t e = cudaHostAlloc((void **)&c->stage, need, cudaHostAllocDefault);
-    if (e != cudaSuccess) {  // no pinned memory to be had: the plain copy still works
-      cudaGetLastError();
-      c->stage = nullptr;
-      FGS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
-      return FGS_OK;
-    }
-    c->stage_bytes = need;
-    for (int i = 0; i < 16; i++) FGS_CUDA(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+  if (!stage_ring(c)) {  // no pinned memory to be had: the plain copy still works
+    FGS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return FGS_OK;
   }
   const size_t n_piece = (bytes + STAGE_PIECE - 1) / STAGE_PIECE;
   std::vector<int> status(T, 0);
@@ -102,6 +116,56 @@ static int staged_upload(fgs_ctx *c, void *dst, const void *src, size_t bytes, c
   for (int t = 0; t < T; t++)
     if (status[t]) { cudaStreamSynchronize(st); set_error("staged upload failed: %s", cudaGetErrorString(cudaGetLastError())); return FGS_ERR_CUDA; }
   return FGS_OK;
+}
+
+// The way back (a block of es.null into the caller's pageable array): the mirror image.  Every
+// thread keeps two pieces in flight -- DMA into one pinned slot while it copies the other out --
+// and the call returns when the data is in `dst`.  `st` must already be ordered after the
+// kernels that produce `src`.
+static int staged_download(fgs_ctx *c, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0 || !dst) return FGS_OK;
+  const int T = stage_threads(c);
+  if (bytes < 4 * STAGE_PIECE || c->opt_h2d_threads <= 0 || !stage_ring(c)) {
+    FGS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    FGS_CUDA(cudaStreamSynchronize(st));
+    return FGS_OK;
+  }
+  const size_t n_piece = (bytes + STAGE_PIECE - 1) / STAGE_PIECE;
+  std::vector<int> status(T, 0);
+  auto worker = [&](int t) {
+    if (cudaSetDevice(c->device) != cudaSuccess) { status[t] = 1; return; }
+    size_t pend_o[2] = {0, 0}, pend_len[2] = {0, 0};
+    auto finish = [&](int turn) -> bool {  // wait for the slot's DMA, copy the piece out
+      const int slot = 2 * t + turn;
+      if (cudaEventSynchronize(c->stage_ev[slot]) != cudaSuccess) return false;
+      if (pend_len[turn]) memcpy((char *)dst + pend_o[turn], c->stage + (size_t)slot * STAGE_PIECE, pend_len[turn]);
+      pend_len[turn] = 0;
+      return true;
+    };
+    int turn = 0;
+    for (size_t i = (size_t)t; i < n_piece; i += (size_t)T, turn ^= 1) {
+      const int slot = 2 * t + turn;
+      if (!finish(turn)) { status[t] = 1; return; }
+      const size_t o = i * STAGE_PIECE, len = std::min(STAGE_PIECE, bytes - o);
+      if (cudaMemcpyAsync(c->stage + (size_t)slot * STAGE_PIECE, (const char *)src + o, len, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaEventRecord(c->stage_ev[slot], st) != cudaSuccess) { status[t] = 1; return; }
+      pend_o[turn] = o; pend_len[turn] = len;
+    }
+    if (!finish(turn) || !finish(turn ^ 1)) status[t] = 1;   // oldest first
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; t++) th.emplace_back(worker, t);
+  worker(0);
+  for (auto &x : th) x.join();
+  for (int t = 0; t < T; t++)
+    if (status[t]) { cudaStreamSynchronize(st); set_error("staged download failed: %s", cudaGetErrorString(cudaGetLastError())); return FGS_ERR_CUDA; }
+  return FGS_OK;
+}
+
+// es.null of block `k` (recorded as finished in blk_out[k & 1]) into the caller's array
+static int download_block(fgs_ctx *c, int slot, double *dst, const double *src, size_t n) {
+  FGS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->blk_out[slot], 0));
+  return staged_download(c, dst, src, n * sizeof(double), c->copy_stream);
 }
 
 // Householder QR of the [n x q] design (column-major), then H = R^-1 Q^T.
@@ -371,6 +435,7 @@ int fgs_create(int device, fgs_ctx **out) {
   for (int i = 0; i < 2; i++) {
     FGS_CUDA(cudaEventCreateWithFlags(&c->blk_copy[i], cudaEventDisableTiming));
     FGS_CUDA(cudaEventCreateWithFlags(&c->blk_done[i], cudaEventDisableTiming));
+    FGS_CUDA(cudaEventCreateWithFlags(&c->blk_out[i], cudaEventDisableTiming));
   }
   *out = c;
   return FGS_OK;
@@ -394,6 +459,7 @@ int fgs_destroy(fgs_ctx *c) {
   for (int i = 0; i < 2; i++) {
     if (c->blk_copy[i]) cudaEventDestroy(c->blk_copy[i]);
     if (c->blk_done[i]) cudaEventDestroy(c->blk_done[i]);
+    if (c->blk_out[i]) cudaEventDestroy(c->blk_out[i]);
   }
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->stage) {
@@ -749,6 +815,20 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
       const int prc = block_progress(c, p0 / Pb_max, (long long)Pb_max * R, (long long)P * R);
       if (prc != FGS_OK) { c->cur_ident = nullptr; c->cur_exact_all = false; return prc; }
     }
+    if (es_null_out) {
+      // es.null goes back block by block: block k-1 leaves (pinned staging ring, several host
+      // threads) while block k, already queued, is computed
+      const int k = p0 / Pb_max;
+      FGS_CUDA(cudaEventRecord(c->blk_out[k & 1], c->stream));
+      if (k > 0) {
+        const size_t o = (size_t)(p0 - Pb_max) * R * S;
+        FGS_TRY(download_block(c, (k - 1) & 1, es_null_out + o, c->es_null.p + o, (size_t)Pb_max * R * S));
+      }
+      if (p0 + Pb >= P) {
+        const size_t o = (size_t)p0 * R * S;
+        FGS_TRY(download_block(c, k & 1, es_null_out + o, c->es_null.p + o, (size_t)Pb * R * S));
+      }
+    }
   }
   c->cur_ident = nullptr;
   c->cur_exact_all = false;
@@ -772,11 +852,7 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
     return rc;
   }
   if (rc != FGS_OK) return rc;
-  if (es_null_out) {
-    FGS_TRY(d2h(c, es_null_out, c->es_null.p, (size_t)S * R * P));
-    FGS_TRY(sync(c));
-  }
-  return FGS_OK;
+  return FGS_OK;   // es_null_out was filled block by block inside the loop
 }
 
 int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scores, int n_gene,
@@ -840,7 +916,14 @@ int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scor
       FGS_TRY(rank_and_es(c, es_kind, p_exp, 0, Cb, c->es_null.p + (size_t)c0 * S, tm));
       if (c->progress && k >= 2) FGS_CUDA(cudaEventSynchronize(c->blk_done[slot]));
       FGS_CUDA(cudaEventRecord(c->blk_done[slot], c->stream));
+      if (es_out) FGS_CUDA(cudaEventRecord(c->blk_out[slot], c->stream));
       if (k + 1 < n_blk) FGS_TRY(upload(k + 1, c->scores2.p));
+      if (es_out && k > 0) {  // results of block k-1 go back while block k is computed
+        const size_t o = (size_t)(c0 - Cb_max) * S;
+        FGS_TRY(download_block(c, slot ^ 1, es_out + o, c->es_null.p + o, (size_t)Cb_max * S));
+      }
+      if (es_out && k + 1 == n_blk)
+        FGS_TRY(download_block(c, slot, es_out + (size_t)c0 * S, c->es_null.p + (size_t)c0 * S, (size_t)Cb * S));
       if (c->progress && c->progress(c->progress_user, std::min(C, std::max<long long>(0, k - 1) * Cb_max), C) != 0) {
         set_error("stopped by the progress callback");
         brc = FGS_ERR_CANCELLED;
@@ -854,8 +937,7 @@ int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scor
     tm.finish(0.f);
     if (cudaEventSynchronize(c->ev[1]) == cudaSuccess) cudaEventElapsedTime(&c->last_ms[4], c->ev[0], c->ev[1]);
     if (r2 != FGS_OK) return r2;
-    if (es_out) { FGS_TRY(d2h(c, es_out, c->es_null.p, (size_t)S * C)); FGS_TRY(sync(c)); }
-    return FGS_OK;
+    return FGS_OK;   // es_out was filled block by block inside the loop
   };
   rc = body();
   c->G = saveG;

@@ -75,7 +75,7 @@ struct fgs_ctx {
   // user-score streaming (fgs_es_from_scores): upload of block k+1 on copy_stream while
   // block k is ranked; blk_copy / blk_done order the two score buffers
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t blk_copy[2] = {nullptr, nullptr}, blk_done[2] = {nullptr, nullptr};
+  cudaEvent_t blk_copy[2] = {nullptr, nullptr}, blk_done[2] = {nullptr, nullptr}, blk_out[2] = {nullptr, nullptr};
   // pinned staging ring of the threaded host->device upload (fgs_api.cu: staged_upload)
   char *stage = nullptr;
   size_t stage_bytes = 0;

@@ -220,6 +220,9 @@ int fgs_set_progress(fgs_ctx *ctx, fgs_progress_fn cb, void *user);
  * (rank with the 64-bit global-memory sort), "s2n_mode" (1, default: s2n scores
  * of the null loop by the FP64 tensor-core contraction with rank certification;
  * 0: the bit-faithful three-pass kernel), "cert_cap" (certification list size),
+ * "h2d_threads" (8, default: host threads that stage large uploads of user score
+ * columns and the block-wise return of es.null through pinned memory; 0: plain
+ * copies),
  * "es_exact_small" (1, default: problems that cost well under a millisecond that
  * way compute every weighted-KS unit in the reference's operation order) */
 int fgs_set_option(fgs_ctx *ctx, const char *name, long long value);

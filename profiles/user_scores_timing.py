@@ -25,3 +25,16 @@ for th in (0, 2, 4, 8):
     ms, ln = ctx.last_timings()
     print("  rep %d: wall %.1f ms (%.2e ES/s, %.1f GB/s of host scores); device span %.1f ms"
             % (rep, wall * 1e3, S * P / wall, sc.nbytes / wall / 1e9, ms["total"]), flush=True)
+# es.null back to the host (640 MB): the permutation loop with and without the host copy
+ctx.set_x(x); ctx.set_response_s2n(y.astype("int32"))
+out = np.zeros((S, 1, c["P"]), order="F")
+for th in (0, 8):
+    ctx.set_option("h2d_threads", th)
+    for want in (False, True):
+        best = 1e9
+        for rep in range(3):
+            t0 = time.perf_counter()
+            ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, c["P"], seed=5, want_host=want)
+            best = min(best, time.perf_counter() - t0)
+        print("perm_null, staging threads %d, es.null to host %s: wall %.1f ms" % (th, want, best * 1e3), flush=True)
+

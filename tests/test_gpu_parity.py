@@ -798,6 +798,34 @@ def test_user_scores_threaded_upload(ctx, oracle):
 
 
 @pytest.mark.gpu
+def test_null_streams_back_in_blocks(ctx, oracle):
+    """es.null returns to the host block by block while the next block is computed; blocks of
+    32 MB and more through the pinned ring and several host threads.  Same array as the plain
+    copy, for the permutation loop and for user scores, and as the oracle on sampled columns."""
+    G, n, S, P = 300, 24, 2000, 9000
+    off, idx = synth.gene_sets_csr(G, S, (5, 40), "uniform", seed=4)
+    x, y = synth.two_class(G, n, seed=3)
+    perm = synth.perm_matrix(n, P, seed=5)
+    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    sc = np.asfortranarray(np.random.default_rng(8).normal(size=(G, 1, P)))
+    try:
+        res, res_u = {}, {}
+        for th in (0, 3, 8):
+            ctx.set_option("h2d_threads", th)
+            res[th] = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm)
+            res_u[th] = ctx.es_from_scores(nat.ES_WEIGHTED_KS, sc)
+        for th in (3, 8):
+            assert np.array_equal(res[th], res[0]) and np.array_equal(res_u[th], res_u[0]), th
+        cols = [0, 4143, 4144, 8287, 8288, 8999]          # block edges of the default 4 144
+        rc, want = oracle.es_from_scores(oracle.ES_WKS, np.asfortranarray(sc[:, :, cols]), off, idx)
+        assert rc == 0 and np.abs(res_u[8][:, :, cols] - want).max() <= ES_TOL
+        rc, want = oracle.perm_null(x, oracle.SCORE_S2N, y, False, np.asfortranarray(perm[:, cols]), off, idx, oracle.ES_WKS)
+        assert rc == 0 and np.abs(res[8][:, :, cols] - want).max() <= ES_TOL
+    finally:
+        ctx.set_option("h2d_threads", 8)
+
+
+@pytest.mark.gpu
 def test_progress_hook_reports_and_cancels(ctx, oracle):
     x, y = synth.two_class(300, 24, seed=3)
     off, idx = synth.gene_sets_csr(300, 12, (5, 40), "uniform", seed=4)
