@@ -15,6 +15,8 @@ def run(ncase, seed, ctx=None):
     rng = np.random.default_rng(seed)
     ctx = ctx or fg.Context(0)
     oracle.use_all_cores()
+    if os.environ.get('EXACT_SMALL'):   # 0: small problems too go through the production kernels
+        ctx.set_option('es_exact_small', int(os.environ['EXACT_SMALL']))
     bad = 0
     for case in range(ncase):
         G = int(rng.choice([7, 16, 33, 100, 257, 1000, 3000]))
