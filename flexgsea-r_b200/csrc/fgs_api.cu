@@ -445,7 +445,7 @@ int fgs_destroy(fgs_ctx *c) {
   if (!c) return FGS_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->x.release(); c->xc.release(); c->xtot.release(); c->cert_list.release(); c->cert_ctr.release();
+  c->set_groups.release(); c->x.release(); c->xc.release(); c->xtot.release(); c->cert_list.release(); c->cert_ctr.release();
   c->cert_redo.release(); c->sort_redo.release(); c->sort_glist.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release(); c->set_idx16.release(); c->sig_lut.release(); c->set_slow.release(); c->tie_list.release(); c->tie_ctr.release(); c->obs_es.release(); c->ident.release(); c->obs_labels.release();
   for (auto &b : c->api_d) b.release();
   for (auto &b : c->api_i) b.release();
@@ -578,6 +578,34 @@ int fgs_set_gene_sets(fgs_ctx *c, const int *offsets, const int *index, int n_se
     blocks += (m + 7) / 8;
   }
   c->idx16_blocks = blocks;
+  // Work list of the weighted-KS kernel.  A set of m members is sorted with SL = 4 .. 64 members per
+  // lane (the smallest with 8 * SL >= m) on L = ceil(m / SL) lanes; sets of the same (SL, L) sit back
+  // to back in one warp, floor(31 / L) of them (one lane stays idle as the all-pad partner) or four
+  // of eight lanes.  Sets above 512 members take a warp each.
+  std::vector<int2> groups;
+  {
+    int cur_sl = -1, cur_L = -1, cur_cap = 0;
+    for (int k = 0; k < n_sets; k++) {
+      const int m = info[k].y & 0x7fffffff;
+      int sl, L, cap;
+      if (m > 512) { sl = m <= 1024 ? 5 : 6; L = 32; cap = 1; }
+      else {
+        sl = 2;
+        while ((8 << sl) < m) sl++;
+        L = std::max(3, (m + (1 << sl) - 1) >> sl);
+        if (L >= 7) L = 8;            // seven lanes also make four sets per warp
+        cap = L == 8 ? 4 : 31 / L;
+      }
+      if (groups.empty() || sl != cur_sl || L != cur_L || (groups.back().y & 0xff) >= cur_cap) {
+        groups.push_back(make_int2(k, (L << 8) | (sl << 16)));
+        cur_sl = sl; cur_L = L; cur_cap = cap;
+      }
+      groups.back().y++;
+    }
+  }
+  c->n_groups = (int)groups.size();
+  FGS_TRY(c->set_groups.ensure(std::max<size_t>(groups.size(), 1)));
+  FGS_TRY(h2d(c, c->set_groups.p, groups.data(), groups.size()));
   c->sum_m2 = 0.0;
   for (int s2 = 0; s2 < n_sets; s2++) { const double m = offsets[s2 + 1] - offsets[s2]; c->sum_m2 += m * m; }
   FGS_TRY(c->slow_ids.ensure(std::max<size_t>(slow_ids.size(), 1)));

@@ -119,6 +119,10 @@ struct fgs_ctx {
   //   {member offset, m | slow << 31, offset in set_idx16 in blocks of 8, set id};
   // "slow" = duplicated members or more than ES_MAX_SET members (order-free kernel)
   fgs::DevBuf<int4> set_info;
+  // es_wks_kernel work list: {first set in processing order, count | lanes per set << 8 |
+  // log2(members per lane) << 16}: the sets one warp takes at once (fgs_set_gene_sets)
+  fgs::DevBuf<int2> set_groups;
+  int n_groups = 0;
   fgs::DevBuf<double> set_invgm;   // [S] 1 / (G - m), processing order
   // observed ES of the last fgs_observed_es (weighted KS): null units that land within
   // rounding of it are recomputed in the reference's operation order (es_wks_tie_kernel)

@@ -68,9 +68,22 @@ __device__ __forceinline__ uint32_t minmax2_side(uint32_t a, uint32_t o, uint32_
   return hi_mask ? __vmaxu2(a, o) : __vminu2(a, o);
 }
 
+//
+// A set need not fill its eight lanes: one of L < 8 lanes (m <= L * NB) is sorted by the same
+// 8-lane network with lanes L..7 imagined full of pads.  Every comparator sends the minimum
+// down, so one whose upper end is an imagined lane changes nothing; the lane on its lower end
+// reads an all-pad register from lane 31 instead (kept idle, and so all pads, whenever L < 8).
+// `base` = first lane of the set, `Lp` = L on the set's lanes and 0 on idle ones, which then
+// read lane 31 throughout and stay all pads.  Sets of L lanes sit back to back in the warp
+// (floor(31 / L) of them), which is where the gain is: 6 sets of 5 lanes instead of 4 of 8.
 template <int LANES, int NB>
-__device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[NB / 2], int lane) {
+__device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[NB / 2], int lane, int base = 0, int Lp = LANES) {
   constexpr int N = LANES * NB;
+  auto src_of = [&](int mask) -> int {
+    if constexpr (LANES == 32) return lane ^ mask;
+    const int pl = lane ^ mask;
+    return pl < Lp ? base + pl : 31;
+  };
   constexpr int NR = NB / 2;
   static_assert(NB >= 4 && LANES <= 32, "packed pairs, at least two registers");
   // Slot s of a lane lives in register s % NR, half s / NR: the TOP slot bit selects the
@@ -101,11 +114,12 @@ __device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[NB / 2], int la
       }
     } else {  // lane ^ (k / NB - 1), slots reversed: register NR-1-q, halves swapped
       const uint32_t hi_mask = 0u - ((lane / ((k / NB) >> 1)) & 1u);
+      const int src = src_of((k / NB) - 1);
 #pragma unroll
       for (int q = 0; q < NR / 2; q++) {  // registers q and NR-1-q exchange with each other's mirror
         const uint32_t a = v[q], b = v[NR - 1 - q];
-        const uint32_t oa = swap_halves(__shfl_xor_sync(0xffffffffu, b, (k / NB) - 1));
-        const uint32_t ob = swap_halves(__shfl_xor_sync(0xffffffffu, a, (k / NB) - 1));
+        const uint32_t oa = swap_halves(__shfl_sync(0xffffffffu, b, src));
+        const uint32_t ob = swap_halves(__shfl_sync(0xffffffffu, a, src));
         v[q] = minmax2_side(a, oa, hi_mask);
         v[NR - 1 - q] = minmax2_side(b, ob, hi_mask);
       }
@@ -114,9 +128,10 @@ __device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[NB / 2], int la
     for (int j = k >> 2; j > 0; j >>= 1) {
       if (j >= NB) {  // partner lane ^ (j / NB), same slot
         const uint32_t hi_mask = 0u - ((lane / (j / NB)) & 1u);
+        const int src = src_of(j / NB);
 #pragma unroll
         for (int q = 0; q < NR; q++)
-          v[q] = minmax2_side(v[q], __shfl_xor_sync(0xffffffffu, v[q], j / NB), hi_mask);
+          v[q] = minmax2_side(v[q], __shfl_sync(0xffffffffu, v[q], src), hi_mask);
       } else if (j == NR) {  // the two halves of one register
 #pragma unroll
         for (int q = 0; q < NR; q++) v[q] = sort_halves(v[q]);
@@ -194,7 +209,8 @@ template <int LANES, int SL, bool W_SMEM>
 __device__ __forceinline__ double wks_sets(const uint16_t *__restrict__ s_rank,
                                            const double *__restrict__ wsrc,
                                            const uint16_t *__restrict__ idx16, int zblk, int m, int G,
-                                           double invGm, int ls, bool &tie) {
+                                           double invGm, int ls, bool &tie, int base = 0, int L = LANES,
+                                           int Lp = LANES) {
   constexpr int NR = SL / 2;
   const uint32_t padpair = (uint32_t)G * 0x10001u;
   uint32_t v[NR];
@@ -207,7 +223,7 @@ __device__ __forceinline__ double wks_sets(const uint16_t *__restrict__ s_rank,
   } else {
 #pragma unroll
     for (int b = 0; b < SL / 8; b++) {  // eight members per 16-byte load
-      const int blk = b * LANES + ls;
+      const int blk = b * L + ls;
       uint4 w = make_uint4(padpair, padpair, padpair, padpair);
       if (blk * 8 < m) w = __ldg((const uint4 *)(idx16 + (size_t)zblk * 8) + blk);
       v[4 * b + 0] = gather2<W_SMEM>(s_rank, wsrc, G, w.x, w0, w1);
@@ -216,12 +232,21 @@ __device__ __forceinline__ double wks_sets(const uint16_t *__restrict__ s_rank,
       v[4 * b + 3] = gather2<W_SMEM>(s_rank, wsrc, G, w.w, w0, w1);
     }
   }
-  double W = w0 + w1;  // every lane of the set ends with the same bits (commutative butterfly)
+  double W = w0 + w1;  // every lane of the set ends with the same bits
+  if constexpr (LANES == 32) {
 #pragma unroll
-  for (int o = LANES / 2; o; o >>= 1) W += __shfl_xor_sync(0xffffffffu, W, o);
+    for (int o = LANES / 2; o; o >>= 1) W += __shfl_xor_sync(0xffffffffu, W, o);
+  } else {  // L <= 8 lanes from `base`: fold towards the first lane, then hand its total out
+#pragma unroll
+    for (int d = 1; d < LANES; d <<= 1) {
+      const double t = __shfl_down_sync(0xffffffffu, W, d);
+      if (ls + d < L) W += t;
+    }
+    W = __shfl_sync(0xffffffffu, W, base);
+  }
   const double invW = 1.0 / W;
 
-  bitonic_sort_ranks<LANES, SL>(v, ls);
+  bitonic_sort_ranks<LANES, SL>(v, ls, base, Lp);
 
   const int k0 = ls * SL;
   // (r - k) as a double without integer->double conversions: 2^52 + r0 has the
@@ -247,15 +272,23 @@ __device__ __forceinline__ double wks_sets(const uint16_t *__restrict__ s_rank,
   // weight of the lanes below: inclusive scan of the lane totals over the set's
   // lanes; the shuffle's own in-range predicate guards the add (no select)
   double incw = cl;
+  if constexpr (LANES == 32) {
 #pragma unroll
-  for (int d = 1; d < LANES; d <<= 1) {
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, tlo, thi;\n\t.reg .f64 t;\n\t"
-                 "mov.b64 {lo, hi}, %0;\n\t"
-                 "shfl.sync.up.b32 tlo|p, lo, %1, %2, 0xffffffff;\n\t"
-                 "shfl.sync.up.b32 thi|p, hi, %1, %2, 0xffffffff;\n\t"
-                 "mov.b64 t, {tlo, thi};\n\t"
-                 "@p add.f64 %0, %0, t;\n\t}"
-                 : "+d"(incw) : "r"(d), "n"((32 - LANES) << 8));
+    for (int d = 1; d < LANES; d <<= 1) {
+      asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, tlo, thi;\n\t.reg .f64 t;\n\t"
+                   "mov.b64 {lo, hi}, %0;\n\t"
+                   "shfl.sync.up.b32 tlo|p, lo, %1, %2, 0xffffffff;\n\t"
+                   "shfl.sync.up.b32 thi|p, hi, %1, %2, 0xffffffff;\n\t"
+                   "mov.b64 t, {tlo, thi};\n\t"
+                   "@p add.f64 %0, %0, t;\n\t}"
+                   : "+d"(incw) : "r"(d), "n"((32 - LANES) << 8));
+    }
+  } else {  // the set's lanes start at any lane: the lane's own position guards the add
+#pragma unroll
+    for (int d = 1; d < LANES; d <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, incw, d);
+      if (ls >= d) incw += t;
+    }
   }
   const double below = (incw - cl) * invW;  // one more rounding than a single running sum; ES tolerance is 1e-10
   mx += below;
@@ -263,12 +296,13 @@ __device__ __forceinline__ double wks_sets(const uint16_t *__restrict__ s_rank,
   if constexpr (LANES == 32) {
     mx = warp_max_exact(mx);
     mn = -warp_max_exact(-mn);
-  } else {
+  } else {  // folded towards the set's first lane, which is the one that reports
 #pragma unroll
-    for (int o = LANES / 2; o; o >>= 1) {
-      const double a = __shfl_xor_sync(0xffffffffu, mx, o), b = __shfl_xor_sync(0xffffffffu, mn, o);
-      mx = (a > mx) ? a : mx;
-      mn = (b < mn) ? b : mn;
+    for (int d = 1; d < LANES; d <<= 1) {
+      const double a = __shfl_down_sync(0xffffffffu, mx, d), b = __shfl_down_sync(0xffffffffu, mn, d);
+      const bool in = ls + d < L;
+      mx = (in && a > mx) ? a : mx;
+      mn = (in && b < mn) ? b : mn;
     }
   }
   double es = (mx > -mn) ? mx : mn;                      // strict, :833
@@ -287,15 +321,14 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
               long long C, const int4 *__restrict__ set_info, const uint16_t *__restrict__ idx16,
               const double *__restrict__ set_invgm, int S, double *__restrict__ es_out,
               int2 *__restrict__ tie_list, int *__restrict__ tie_ctr, int tie_cap,
-              const double *__restrict__ obs, const int *__restrict__ ident, int R) {
+              const double *__restrict__ obs, const int *__restrict__ ident, int R,
+              const int2 *__restrict__ groups, int n_groups) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const size_t Gp = pitch_of(G);
   uint16_t *s_rank = (uint16_t *)smem;                    // [Gp + 8]: 0-based ranks, pad gene at [G]
   double *s_abs = (double *)(smem + (Gp + 8) * 2);
   if (W_SMEM && tid < 8) s_abs[G + tid] = 0.0;  // zero slot(s) behind the weights: the pads' weight
-  const int seg = lane >> 3, ls = lane & 7;
-  const int nquads = (S + 3) >> 2;
 
   for (long long col = blockIdx.x; col < C; col += gridDim.x) {
     __syncthreads();
@@ -319,47 +352,46 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
     // observed ES of this column's response; none for a label-preserving permutation (copied later)
     const double *col_obs = (obs && !(ident && __ldg(ident + col / R))) ? obs + (size_t)(col % R) * S : nullptr;
     double *es_col = es_out + (size_t)col * S;
-    // sets in descending size, four per warp (eight lanes each), quads round-robin
-    // over the warps: similar work per warp and one size class per quad
-    for (int q = warp; q < nquads; q += nwarps) {
-      const int k = 4 * q + seg;
-      int4 info = make_int4(0, (int)0x80000000, 0, 0);  // {-, m | slow << 31, member block offset, set id}
-      double ig = 0.0;
-      if (k < S) { info = __ldg(set_info + k); ig = __ldg(set_invgm + k); }  // ig = 1 / (G - m)
-      // the set's observed ES, fetched now so that the comparison at the end costs nothing
-      const double e_obs = (col_obs && k < S) ? __ldg(col_obs + info.w) : nan("");
-      const bool mine = info.y >= 0;              // slow sets: es_wks_generic_kernel does these
-      const int m = mine ? info.y : 0;
-      int mmax = max(m, __shfl_xor_sync(0xffffffffu, m, 8));
-      mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, 16));
-      if (mmax <= 8 * 64) {
+    // sets in descending size; a group (make_set_groups) is the sets one warp takes at once:
+    // `cnt` sets of one size class on L lanes each, back to back.  Groups go round-robin over
+    // the warps.
+    for (int g = warp; g < n_groups; g += nwarps) {
+      const int2 ge = __ldg(groups + g);  // {first set (processing order), cnt | L << 8 | log2(SL) << 16}
+      const int cnt = ge.y & 0xff, L = (ge.y >> 8) & 0xff, sl = ge.y >> 16;
+      if (L < 32) {
+        const int seg = lane / L, ls = lane - seg * L;
+        const bool on = seg < cnt;
+        const int k = ge.x + seg, base = lane - ls, Lp = on ? L : 0;
+        int4 info = make_int4(0, (int)0x80000000, 0, 0);  // {-, m | slow << 31, member block offset, set id}
+        double ig = 0.0;
+        if (on) { info = __ldg(set_info + k); ig = __ldg(set_invgm + k); }  // ig = 1 / (G - m)
+        // the set's observed ES, fetched now so that the comparison at the end costs nothing
+        const double e_obs = (col_obs && on) ? __ldg(col_obs + info.w) : nan("");
+        const bool mine = info.y >= 0;              // slow sets: es_wks_generic_kernel does these
+        const int m = mine ? info.y : 0;
         double es;
         bool tie = false;
-        if (mmax <= 8 * 4) es = wks_sets<8, 4, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie);
-        else if (mmax <= 8 * 8) es = wks_sets<8, 8, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie);
-        else if (mmax <= 8 * 16) es = wks_sets<8, 16, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie);
-        else if (mmax <= 8 * 32) es = wks_sets<8, 32, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie);
-        else es = wks_sets<8, 64, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie);  // 257 .. 512 members
+        if (sl == 2) es = wks_sets<8, 4, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie, base, L, Lp);
+        else if (sl == 3) es = wks_sets<8, 8, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie, base, L, Lp);
+        else if (sl == 4) es = wks_sets<8, 16, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie, base, L, Lp);
+        else if (sl == 5) es = wks_sets<8, 32, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie, base, L, Lp);
+        else es = wks_sets<8, 64, W_SMEM>(s_rank, wsrc, idx16, info.z, m, G, ig, ls, tie, base, L, Lp);  // 257 .. 512 members
         if (mine && ls == 0) {
           es_col[info.w] = es;
           if (tie || fabs(es - e_obs) <= ES_OBS_REL * fabs(e_obs)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, info.w);
         }
-      } else {  // a quad with a set of 513 .. ES_MAX_SET members: one set at a time on the whole warp
-#pragma unroll 1
-        for (int i = 0; i < 4; i++) {
-          const int mi = __shfl_sync(0xffffffffu, m, 8 * i);
-          const int zi = __shfl_sync(0xffffffffu, info.z, 8 * i), wi = __shfl_sync(0xffffffffu, info.w, 8 * i);
-          const double igi = __shfl_sync(0xffffffffu, ig, 8 * i), eoi = __shfl_sync(0xffffffffu, e_obs, 8 * i);
-          const bool on = __shfl_sync(0xffffffffu, (int)mine, 8 * i) != 0;
-          if (!on) continue;
-          double es;
-          bool tie = false;
-          if (mi <= 32 * 32) es = wks_sets<32, 32, W_SMEM>(s_rank, wsrc, idx16, zi, mi, G, igi, lane, tie);
-          else es = wks_sets<32, 64, W_SMEM>(s_rank, wsrc, idx16, zi, mi, G, igi, lane, tie);
-          if (lane == 0) {
-            es_col[wi] = es;
-            if (tie || fabs(es - eoi) <= ES_OBS_REL * fabs(eoi)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, wi);
-          }
+      } else {  // a set of 513 .. ES_MAX_SET members on the whole warp
+        const int4 info = __ldg(set_info + ge.x);
+        if (info.y < 0) continue;
+        const double ig = __ldg(set_invgm + ge.x);
+        const double e_obs = col_obs ? __ldg(col_obs + info.w) : nan("");
+        double es;
+        bool tie = false;
+        if (sl == 5) es = wks_sets<32, 32, W_SMEM>(s_rank, wsrc, idx16, info.z, info.y, G, ig, lane, tie);
+        else es = wks_sets<32, 64, W_SMEM>(s_rank, wsrc, idx16, info.z, info.y, G, ig, lane, tie);
+        if (lane == 0) {
+          es_col[info.w] = es;
+          if (tie || fabs(es - e_obs) <= ES_OBS_REL * fabs(e_obs)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, info.w);
         }
       }
     }
@@ -732,13 +764,15 @@ static int launch_es_wks_inner(fgs_ctx *c, const uint16_t *d_rank16, const doubl
     FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx16.p,
                                              c->set_invgm.p, c->S, d_es, c->tie_list.p, c->tie_ctr.p,
-                                             c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R);
+                                             c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R,
+                                             c->set_groups.p, c->n_groups);
   } else {
     auto k = es_wks_kernel<false>;
     FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx16.p,
                                              c->set_invgm.p, c->S, d_es, c->tie_list.p, c->tie_ctr.p,
-                                             c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R);
+                                             c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R,
+                                             c->set_groups.p, c->n_groups);
   }
   c->launches++;
   FGS_CUDA(cudaGetLastError());
