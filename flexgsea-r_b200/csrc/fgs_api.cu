@@ -604,6 +604,8 @@ int fgs_set_gene_sets(fgs_ctx *c, const int *offsets, const int *index, int n_se
     }
   }
   c->n_groups = (int)groups.size();
+  c->n_wide_groups = 0;
+  while (c->n_wide_groups < c->n_groups && ((groups[c->n_wide_groups].y >> 8) & 0xff) == 32) c->n_wide_groups++;
   FGS_TRY(c->set_groups.ensure(std::max<size_t>(groups.size(), 1)));
   FGS_TRY(h2d(c, c->set_groups.p, groups.data(), groups.size()));
   c->sum_m2 = 0.0;

@@ -122,7 +122,7 @@ struct fgs_ctx {
   // es_wks_kernel work list: {first set in processing order, count | lanes per set << 8 |
   // log2(members per lane) << 16}: the sets one warp takes at once (fgs_set_gene_sets)
   fgs::DevBuf<int2> set_groups;
-  int n_groups = 0;
+  int n_groups = 0, n_wide_groups = 0;  // the wide ones (a set per warp) come first
   fgs::DevBuf<double> set_invgm;   // [S] 1 / (G - m), processing order
   // observed ES of the last fgs_observed_es (weighted KS): null units that land within
   // rounding of it are recomputed in the reference's operation order (es_wks_tie_kernel)

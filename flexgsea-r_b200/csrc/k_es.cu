@@ -314,9 +314,14 @@ __device__ __forceinline__ double wks_sets(const uint16_t *__restrict__ s_rank,
   return es;
 }
 
-constexpr int ES_THREADS = 1024;  // 32 warps at 64 registers: the few spills of the wide classes cost less than the lost occupancy at 768
-template <bool W_SMEM>
-__global__ void __launch_bounds__(ES_THREADS, 1)
+constexpr int ES_THREADS = 1024;  // 32 warps at 64 registers: better than 24 warps at 80 (measured)
+constexpr int ES_WIDE_THREADS = 512;  // sets on a whole warp keep up to 32 packed registers: 128 registers per thread
+// WIDE = false: the groups of sets up to 512 members (eight-lane network, L lanes per set);
+// WIDE = true: the groups that are one set of 513 .. ES_MAX_SET members on a whole warp.  Two
+// instantiations because the whole-warp classes need twice the registers; the second one is
+// launched only when such sets exist.
+template <bool W_SMEM, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? ES_WIDE_THREADS : ES_THREADS, 1)
 es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sabs, int G,
               long long C, const int4 *__restrict__ set_info, const uint16_t *__restrict__ idx16,
               const double *__restrict__ set_invgm, int S, double *__restrict__ es_out,
@@ -358,7 +363,7 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
     for (int g = warp; g < n_groups; g += nwarps) {
       const int2 ge = __ldg(groups + g);  // {first set (processing order), cnt | L << 8 | log2(SL) << 16}
       const int cnt = ge.y & 0xff, L = (ge.y >> 8) & 0xff, sl = ge.y >> 16;
-      if (L < 32) {
+      if constexpr (!WIDE) {
         const int seg = lane / L, ls = lane - seg * L;
         const bool on = seg < cnt;
         const int k = ge.x + seg, base = lane - ls, Lp = on ? L : 0;
@@ -381,6 +386,7 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
           if (tie || fabs(es - e_obs) <= ES_OBS_REL * fabs(e_obs)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, info.w);
         }
       } else {  // a set of 513 .. ES_MAX_SET members on the whole warp
+        (void)cnt; (void)L;
         const int4 info = __ldg(set_info + ge.x);
         if (info.y < 0) continue;
         const double ig = __ldg(set_invgm + ge.x);
@@ -759,23 +765,26 @@ static int launch_es_wks_inner(fgs_ctx *c, const uint16_t *d_rank16, const doubl
   const bool w_smem = Gp * 10 + 16 + 64 <= budget;
   const size_t smem = w_smem ? Gp * 10 + 16 + 64 : Gp * 2 + 16;
   FGS_TRY(ensure_set_blocks(c, G));
+  // groups [0, n_wide) are single sets on a whole warp, the rest packed sets of up to 512 members
+  auto go = [&](auto kern, int threads, const int2 *groups, int n) -> int {
+    if (n <= 0) return FGS_OK;
+    FGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx16.p,
+                                             c->set_invgm.p, c->S, d_es, c->tie_list.p, c->tie_ctr.p,
+                                             c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R, groups, n);
+    c->launches++;
+    FGS_CUDA(cudaGetLastError());
+    return FGS_OK;
+  };
+  const int2 *gw = c->set_groups.p, *gp = c->set_groups.p + c->n_wide_groups;
+  const int n_packed = c->n_groups - c->n_wide_groups;
   if (w_smem) {
-    auto k = es_wks_kernel<true>;
-    FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx16.p,
-                                             c->set_invgm.p, c->S, d_es, c->tie_list.p, c->tie_ctr.p,
-                                             c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R,
-                                             c->set_groups.p, c->n_groups);
+    FGS_TRY(go(es_wks_kernel<true, false>, ES_THREADS, gp, n_packed));
+    FGS_TRY(go(es_wks_kernel<true, true>, ES_WIDE_THREADS, gw, c->n_wide_groups));
   } else {
-    auto k = es_wks_kernel<false>;
-    FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, ES_THREADS, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx16.p,
-                                             c->set_invgm.p, c->S, d_es, c->tie_list.p, c->tie_ctr.p,
-                                             c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R,
-                                             c->set_groups.p, c->n_groups);
+    FGS_TRY(go(es_wks_kernel<false, false>, ES_THREADS, gp, n_packed));
+    FGS_TRY(go(es_wks_kernel<false, true>, ES_WIDE_THREADS, gw, c->n_wide_groups));
   }
-  c->launches++;
-  FGS_CUDA(cudaGetLastError());
   if (c->n_slow > 0)
     FGS_TRY(launch_es_wks_generic(c, d_rank16, d_sabs, G, C, c->slow_ids.p, c->n_slow, d_es));
   return FGS_OK;
