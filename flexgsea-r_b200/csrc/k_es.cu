@@ -76,34 +76,62 @@ __device__ __forceinline__ uint32_t minmax2_side(uint32_t a, uint32_t o, uint32_
 // `base` = first lane of the set, `Lp` = L on the set's lanes and 0 on idle ones, which then
 // read lane 31 throughout and stay all pads.  Sets of L lanes sit back to back in the warp
 // (floor(31 / L) of them), which is where the gain is: 6 sets of 5 lanes instead of 4 of 8.
-template <int LANES, int NB>
-__device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[NB / 2], int lane, int base = 0, int Lp = LANES) {
-  constexpr int N = LANES * NB;
-  auto src_of = [&](int mask) -> int {
-    if constexpr (LANES == 32) return lane ^ mask;
-    const int pl = lane ^ mask;
-    return pl < Lp ? base + pl : 31;
-  };
+// source lane of a cross-lane comparator (see above)
+template <int LANES>
+__device__ __forceinline__ int bitonic_src(int lane, int mask, int base, int Lp) {
+  if constexpr (LANES == 32) return lane ^ mask;
+  const int pl = lane ^ mask;
+  return pl < Lp ? base + pl : 31;
+}
+
+// one e <-> e ^ J stage; the stages of a level follow each other by template recursion
+// (J, J/2, .. 1) so that the whole network is straight-line code whatever its size -- a
+// `#pragma unroll` over the levels gives up at 2 048 keys and leaves the keys in local memory
+template <int LANES, int NB, int J>
+__device__ __forceinline__ void bitonic_xor_stages(uint32_t (&v)[NB / 2], int lane, int base, int Lp) {
   constexpr int NR = NB / 2;
-  static_assert(NB >= 4 && LANES <= 32, "packed pairs, at least two registers");
-  // Slot s of a lane lives in register s % NR, half s / NR: the TOP slot bit selects the
-  // half.  A comparator stage on the half bit costs two instructions per register (PRMT +
-  // 32-bit max), one between registers a single VIMNMX; the top slot bit is the in-lane
-  // bit the network touches least often (log2(LANES) + 1 times, the lowest bit log2(N)).
+  if constexpr (J > 0) {
+    if constexpr (J >= NB) {  // partner lane ^ (J / NB), same slot
+      const uint32_t hi_mask = 0u - ((lane / (J / NB)) & 1u);
+      const int src = bitonic_src<LANES>(lane, J / NB, base, Lp);
 #pragma unroll
-  for (int k = 2; k <= N; k <<= 1) {
-    // mirror stage: e <-> e ^ (k - 1)
-    if (k <= NR) {  // only register bits flip: same half
+      for (int q = 0; q < NR; q++)
+        v[q] = minmax2_side(v[q], __shfl_sync(0xffffffffu, v[q], src), hi_mask);
+    } else if constexpr (J == NR) {  // the two halves of one register
+#pragma unroll
+      for (int q = 0; q < NR; q++) v[q] = sort_halves(v[q]);
+    } else {  // partner register q ^ J, same half
 #pragma unroll
       for (int q = 0; q < NR; q++) {
-        const int qb = q ^ (k - 1);
+        const int qb = q ^ J;
+        if (qb > q) {
+          const uint32_t a = v[q], b2 = v[qb];
+          v[q] = __vminu2(a, b2);
+          v[qb] = __vmaxu2(a, b2);
+        }
+      }
+    }
+    bitonic_xor_stages<LANES, NB, J / 2>(v, lane, base, Lp);
+  }
+}
+
+// level K: the mirror stage e <-> e ^ (K - 1), the stages K/4 .. 1, then level 2K
+template <int LANES, int NB, int K>
+__device__ __forceinline__ void bitonic_levels(uint32_t (&v)[NB / 2], int lane, int base, int Lp) {
+  constexpr int N = LANES * NB;
+  constexpr int NR = NB / 2;
+  if constexpr (K <= N) {
+    if constexpr (K <= NR) {  // only register bits flip: same half
+#pragma unroll
+      for (int q = 0; q < NR; q++) {
+        const int qb = q ^ (K - 1);
         if (qb > q) {
           const uint32_t a = v[q], t = v[qb];
           v[q] = __vminu2(a, t);
           v[qb] = __vmaxu2(a, t);
         }
       }
-    } else if (k == NB) {  // every slot bit flips: (half 0, q) <-> (half 1, NR-1-q) and (1, q) <-> (0, NR-1-q)
+    } else if constexpr (K == NB) {  // every slot bit flips: (half 0, q) <-> (half 1, NR-1-q) and (1, q) <-> (0, NR-1-q)
 #pragma unroll
       for (int q = 0; q < NR / 2; q++) {
         const int qb = NR - 1 - q;
@@ -112,9 +140,9 @@ __device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[NB / 2], int la
         v[q] = __byte_perm(mn, mx, 0x7610);   // low: min(a.lo, b.hi) stays below; high: max(a.hi, b.lo)
         v[qb] = __byte_perm(mn, mx, 0x5432);  // low: min(a.hi, b.lo); high: max(a.lo, b.hi)
       }
-    } else {  // lane ^ (k / NB - 1), slots reversed: register NR-1-q, halves swapped
-      const uint32_t hi_mask = 0u - ((lane / ((k / NB) >> 1)) & 1u);
-      const int src = src_of((k / NB) - 1);
+    } else {  // lane ^ (K / NB - 1), slots reversed: register NR-1-q, halves swapped
+      const uint32_t hi_mask = 0u - ((lane / ((K / NB) >> 1)) & 1u);
+      const int src = bitonic_src<LANES>(lane, (K / NB) - 1, base, Lp);
 #pragma unroll
       for (int q = 0; q < NR / 2; q++) {  // registers q and NR-1-q exchange with each other's mirror
         const uint32_t a = v[q], b = v[NR - 1 - q];
@@ -124,30 +152,19 @@ __device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[NB / 2], int la
         v[NR - 1 - q] = minmax2_side(b, ob, hi_mask);
       }
     }
-#pragma unroll
-    for (int j = k >> 2; j > 0; j >>= 1) {
-      if (j >= NB) {  // partner lane ^ (j / NB), same slot
-        const uint32_t hi_mask = 0u - ((lane / (j / NB)) & 1u);
-        const int src = src_of(j / NB);
-#pragma unroll
-        for (int q = 0; q < NR; q++)
-          v[q] = minmax2_side(v[q], __shfl_sync(0xffffffffu, v[q], src), hi_mask);
-      } else if (j == NR) {  // the two halves of one register
-#pragma unroll
-        for (int q = 0; q < NR; q++) v[q] = sort_halves(v[q]);
-      } else {  // partner register q ^ j, same half
-#pragma unroll
-        for (int q = 0; q < NR; q++) {
-          const int qb = q ^ j;
-          if (qb > q) {
-            const uint32_t a = v[q], b2 = v[qb];
-            v[q] = __vminu2(a, b2);
-            v[qb] = __vmaxu2(a, b2);
-          }
-        }
-      }
-    }
+    bitonic_xor_stages<LANES, NB, K / 4>(v, lane, base, Lp);
+    bitonic_levels<LANES, NB, K * 2>(v, lane, base, Lp);
   }
+}
+
+// Slot s of a lane lives in register s % NR, half s / NR: the TOP slot bit selects the
+// half.  A comparator stage on the half bit costs two instructions per register (PRMT +
+// 32-bit max), one between registers a single VIMNMX; the top slot bit is the in-lane
+// bit the network touches least often (log2(LANES) + 1 times, the lowest bit log2(N)).
+template <int LANES, int NB>
+__device__ __forceinline__ void bitonic_sort_ranks(uint32_t (&v)[NB / 2], int lane, int base = 0, int Lp = LANES) {
+  static_assert(NB >= 4 && LANES <= 32, "packed pairs, at least two registers");
+  bitonic_levels<LANES, NB, 2>(v, lane, base, Lp);
 }
 
 // Exact warp maximum of a double through two integer warp reductions (REDUX) on
