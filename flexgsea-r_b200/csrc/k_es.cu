@@ -332,13 +332,14 @@ __device__ __forceinline__ double wks_sets(const uint16_t *__restrict__ s_rank,
 }
 
 constexpr int ES_THREADS = 1024;  // 32 warps at 64 registers: better than 24 warps at 80 (measured)
+constexpr int ES_LONG_THREADS = 768;  // columns too long for on-chip weights: gathers through L1 / L2, 80 registers
 constexpr int ES_WIDE_THREADS = 512;  // sets on a whole warp keep up to 32 packed registers: 128 registers per thread
 // WIDE = false: the groups of sets up to 512 members (eight-lane network, L lanes per set);
 // WIDE = true: the groups that are one set of 513 .. ES_MAX_SET members on a whole warp.  Two
 // instantiations because the whole-warp classes need twice the registers; the second one is
 // launched only when such sets exist.
 template <bool W_SMEM, bool WIDE>
-__global__ void __launch_bounds__(WIDE ? ES_WIDE_THREADS : ES_THREADS, 1)
+__global__ void __launch_bounds__(WIDE ? ES_WIDE_THREADS : (W_SMEM ? ES_THREADS : ES_LONG_THREADS), 1)
 es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sabs, int G,
               long long C, const int4 *__restrict__ set_info, const uint16_t *__restrict__ idx16,
               const double *__restrict__ set_invgm, int S, double *__restrict__ es_out,
@@ -799,7 +800,7 @@ static int launch_es_wks_inner(fgs_ctx *c, const uint16_t *d_rank16, const doubl
     FGS_TRY(go(es_wks_kernel<true, false>, ES_THREADS, gp, n_packed));
     FGS_TRY(go(es_wks_kernel<true, true>, ES_WIDE_THREADS, gw, c->n_wide_groups));
   } else {
-    FGS_TRY(go(es_wks_kernel<false, false>, ES_THREADS, gp, n_packed));
+    FGS_TRY(go(es_wks_kernel<false, false>, ES_LONG_THREADS, gp, n_packed));
     FGS_TRY(go(es_wks_kernel<false, true>, ES_WIDE_THREADS, gw, c->n_wide_groups));
   }
   if (c->n_slow > 0)
