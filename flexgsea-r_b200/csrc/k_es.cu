@@ -347,10 +347,11 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
               const double *__restrict__ obs, const int *__restrict__ ident, int R,
               const int2 *__restrict__ groups, int n_groups) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const size_t Gp = pitch_of(G);
   uint16_t *s_rank = (uint16_t *)smem;                    // [Gp + 8]: 0-based ranks, pad gene at [G]
   double *s_abs = (double *)(smem + (Gp + 8) * 2);
+  __shared__ int s_next;  // next group of the column (see below)
   if (W_SMEM && tid < 8) s_abs[G + tid] = 0.0;  // zero slot(s) behind the weights: the pads' weight
 
   for (long long col = blockIdx.x; col < C; col += gridDim.x) {
@@ -369,16 +370,22 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
       }
     }
     __syncthreads();
-    if (tid == 0) s_rank[G] = (uint16_t)G;  // the pad gene's key (inside the staged row when G < Gp)
+    if (tid == 0) { s_rank[G] = (uint16_t)G; s_next = 0; }  // the pad gene's key (inside the staged row when G < Gp)
     __syncthreads();
     const double *wsrc = W_SMEM ? s_abs : sabs + (size_t)col * Gp;
     // observed ES of this column's response; none for a label-preserving permutation (copied later)
     const double *col_obs = (obs && !(ident && __ldg(ident + col / R))) ? obs + (size_t)(col % R) * S : nullptr;
     double *es_col = es_out + (size_t)col * S;
-    // sets in descending size; a group (make_set_groups) is the sets one warp takes at once:
-    // `cnt` sets of one size class on L lanes each, back to back.  Groups go round-robin over
-    // the warps.
-    for (int g = warp; g < n_groups; g += nwarps) {
+    // sets in descending size; a group (fgs_set_gene_sets) is the sets one warp takes at once:
+    // `cnt` sets of one size class on L lanes each, back to back.  A warp fetches its next group
+    // from a counter in shared memory: largest first, whoever is free -- the groups of a column
+    // differ 16-fold in cost, and a fixed round-robin leaves the first warps with more work than
+    // the last in every round.
+    for (;;) {
+      int g = 0;
+      if (lane == 0) g = atomicAdd(&s_next, 1);
+      g = __shfl_sync(0xffffffffu, g, 0);
+      if (g >= n_groups) break;
       const int2 ge = __ldg(groups + g);  // {first set (processing order), cnt | L << 8 | log2(SL) << 16}
       const int cnt = ge.y & 0xff, L = (ge.y >> 8) & 0xff, sl = ge.y >> 16;
       if constexpr (!WIDE) {
@@ -773,14 +780,14 @@ static int launch_es_wks_inner(fgs_ctx *c, const uint16_t *d_rank16, const doubl
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
   const size_t Gp = pitch_of(G);
   const size_t budget = (size_t)c->smem_optin;
-  if (Gp * 2 + 16 > budget)  // the rank array does not fit on chip: the order-free kernel does everything
+  if (Gp * 2 + 16 + 16 > budget)  // the rank array does not fit on chip: the order-free kernel does everything
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
   if (G > 65534)  // the pad key G must fit a uint16 next to the ranks
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
   int grid = c->num_sms;
   if (grid > C) grid = (int)C;
   // rank (2 B) + weight (8 B) per gene on chip, + pad gene, + zero weight slots
-  const bool w_smem = Gp * 10 + 16 + 64 <= budget;
+  const bool w_smem = Gp * 10 + 16 + 64 + 16 <= budget;  // 16: the kernel's static shared memory
   const size_t smem = w_smem ? Gp * 10 + 16 + 64 : Gp * 2 + 16;
   FGS_TRY(ensure_set_blocks(c, G));
   // groups [0, n_wide) are single sets on a whole warp, the rest packed sets of up to 512 members
