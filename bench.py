@@ -1,24 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- the headline metric of BASELINE.json on synthetic data.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config C2]
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+                    [--config C1|C2|C3|C4-maxmean|C4-mean|C5]
 
-metric: gene-set x permutation ES/sec of the sample-permutation null loop
-(permute -> gene score -> rank -> ES), config C2 by default: flexgsea_s2n +
-flexgsea_weighted_ks (p=1), 20,000 genes x 200 samples two-class, 8,000 gene
-sets of 15-500 genes, nperm=10,000.  One "step" = the whole null loop over the
-10,000 permutations.
+metric: gene-set x permutation ES/sec of the sample-permutation path (permute ->
+gene score -> rank -> ES -> NES / p / FDR), config C2 by default: flexgsea_s2n +
+flexgsea_weighted_ks (p=1), 20,000 genes x 200 samples two-class, 8,000 gene sets
+of 15-500 genes, nperm=10,000.  One "step" = the null loop over the config's
+permutations plus flexgsea_calc_sig of every response.
 
-  value : S*R*P*N / device time (CUDA events on the library's stream, inputs
+  value : S*R*P / device time (CUDA events on the library's stream from the
+          first kernel of the null loop to the last of the significance, inputs
           resident in HBM, permutations drawn on the device), max over ranks.
   e2e   : the same metric through the public C-ABI calls a flexgsea() call
           makes, host buffers in pinned memory, H2D/D2H inside the timed
           region, wall clock.
   roofline / cpu_baseline / clocks / stages: see DESIGN.md "Measurement".
 
-N > 1 (torchrun): permutations are independent units, every rank runs its own
-10,000 (weak scaling, no data-path collective); the significance step's small
-NCCL exchanges are exercised once after the timed loop.
+N > 1 (torchrun): STRONG scaling -- the config's nperm is sharded, rank r takes
+permutations [r*P/N, (r+1)*P/N) (Philox keyed by the global permutation id, so
+the null does not depend on N); the significance exchange (NCCL, inside the
+library: fgs_calc_sig_sharded) is in the timed region and its time is reported
+as collective_ms_per_step.
 --impl reference: the reference's CPU path.  R is not installable here (no R,
 no network), so this arm times the oracle restatement of the reference's loop
 (oracle/oracle.c, OpenMP over permutations, all host cores) on a bounded
@@ -40,8 +44,20 @@ sys.path.insert(0, ROOT)
 WORKLOAD_TEXT = {
     "C1": "C1: s2n + weighted KS (p=1), 1,000 genes x 20 samples two-class, 50 gene sets (10-50), nperm=1,000",
     "C2": "C2: s2n + weighted KS (p=1), 20,000 genes x 200 samples two-class, 8,000 gene sets (15-500), nperm=10,000",
-    "C4": "C4: s2n + maxmean ES, 20,000 genes x 200 samples two-class, 20,000 gene sets (15-300), nperm=50,000",
+    "C3": "C3: flexgsea_lm (response + 3 covariates, 4 score columns) + weighted KS, 20,000 genes x 500 samples, "
+          "8,000 gene sets (15-500), nperm=10,000",
+    "C4-maxmean": "C4: s2n + maxmean ES with NES-based FDR, 20,000 genes x 200 samples two-class, 20,000 gene sets "
+                  "(15-300), nperm=50,000",
+    "C4-mean": "C4: s2n + mean ES with NES-based FDR, 20,000 genes x 200 samples two-class, 20,000 gene sets "
+               "(15-300), nperm=50,000",
+    "C5": "C5: s2n + weighted KS, 60,000 transcripts x 1,000 samples two-class, 20,000 gene sets (15-500), "
+          "nperm=100,000",
 }
+WORKLOAD_TEXT["C4"] = WORKLOAD_TEXT["C4-maxmean"]
+# config -> (synthetic shape in synth.CONFIGS, gene score, ES)
+KINDS = {"C1": ("C1", "s2n", "wks"), "C2": ("C2", "s2n", "wks"), "C3": ("C3", "lm", "wks"),
+         "C4": ("C4", "s2n", "maxmean"), "C4-maxmean": ("C4", "s2n", "maxmean"), "C4-mean": ("C4", "s2n", "mean"),
+         "C5": ("C5", "s2n", "wks")}
 
 
 def peaks():
@@ -102,12 +118,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload(name, seed=1):
+def workload(config, seed=1):
+    """(shape dict, x, response, has_intercept, offsets, index) of a BASELINE config;
+    response = y_bin [n x 1] int32 (s2n) or the model matrix [n x 5] (lm: intercept,
+    response, three covariates -> R = 4 score columns)."""
     from flexgsea_r_b200 import synth
-    c = dict(synth.CONFIGS[name])
+    shape, score, _ = KINDS[config]
+    c = dict(synth.CONFIGS[shape])
     off, idx = synth.gene_sets_csr(c["G"], c["S"], c["sizes"], c["size_dist"], seed=seed)
     x, y = synth.two_class(c["G"], c["n"], off, idx, seed=seed + 1)
-    return c, x, y, off, idx
+    if score == "lm":
+        return c, x, synth.continuous_response(c["n"], k=3, seed=seed + 2), True, off, idx
+    return c, x, y.astype(np.int32), False, off, idx
 
 
 def pinned(a):
@@ -118,6 +140,18 @@ def pinned(a):
     return t.numpy().reshape(a.shape, order="F"), t
 
 
+def oracle_kinds(orc, config):
+    _, score, es = KINDS[config]
+    return (orc.SCORE_LM if score == "lm" else orc.SCORE_S2N,
+            {"wks": orc.ES_WKS, "maxmean": orc.ES_MAXMEAN, "mean": orc.ES_MEAN}[es])
+
+
+def cpu_sample_perms(config, cores):
+    """permutations per CPU step: about 10-30 s of work on the box's cores"""
+    base = {"C1": 1000, "C2": 8, "C3": 2, "C4": 8, "C4-maxmean": 8, "C4-mean": 8, "C5": 1}[config]
+    return max(base * cores, 16)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -126,27 +160,28 @@ def run_reference(args):
     import pyoracle as orc
     from flexgsea_r_b200 import synth
     orc.build()
-    c, x, y, off, idx = workload(args.config)
-    es_kind = orc.ES_MAXMEAN if args.config == "C4" else orc.ES_WKS
+    c, x, resp, icpt, off, idx = workload(args.config)
+    sk, ek = oracle_kinds(orc, args.config)
+    R = resp.shape[1] - 1 if sk == orc.SCORE_LM else resp.shape[1]
     cores = orc.use_all_cores()
-    P_s = args.ref_perms if args.ref_perms else max(cores * 8, 64)
+    P_s = args.ref_perms if args.ref_perms else cpu_sample_perms(args.config, cores)
     perm = synth.perm_matrix(c["n"], P_s, seed=4)
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        rc, _ = orc.perm_null(x, orc.SCORE_S2N, y, False, perm, off, idx, es_kind)
+        rc, _ = orc.perm_null(x, sk, resp, icpt, perm, off, idx, ek)
         dt = time.perf_counter() - t0
         assert rc == 0
         if it >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
-    val = c["S"] * P_s / (ms / 1e3)
+    val = c["S"] * R * P_s / (ms / 1e3)
     sample = ("%d of the %d permutations per step, all gene sets; C restatement of the reference loop "
               "(oracle/oracle.c), OpenMP over permutations" % (P_s, c["P"]))
     print(json.dumps({
         "impl": "reference", "metric": "gene-set x permutation ES/sec (null loop)", "value": val, "unit": "ES/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD_TEXT[args.config], "step": "bounded sample: " + sample},
         "cpu_baseline": {"value": val, "unit": "ES/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "ES/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -159,7 +194,7 @@ def run_reference(args):
 def run_gpu(args):
     import torch
     import flexgsea_r_b200 as fg
-    from flexgsea_r_b200 import _native as nat, synth, api
+    from flexgsea_r_b200 import _native as nat, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -169,21 +204,50 @@ def run_gpu(args):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    c, x, y, off, idx = workload(args.config)
+    c, x, resp, icpt, off, idx = workload(args.config)
     G, n, S, P = c["G"], c["n"], c["S"], c["P"]
     if args.perms:
         P = args.perms
-    R = 1
-    es_kind = nat.ES_MAXMEAN if args.config == "C4" else nat.ES_WEIGHTED_KS
+    _, score_name, es_name = KINDS[args.config]
+    score_kind = nat.SCORE_LM if score_name == "lm" else nat.SCORE_S2N
+    es_kind = {"wks": nat.ES_WEIGHTED_KS, "maxmean": nat.ES_MAXMEAN, "mean": nat.ES_MEAN}[es_name]
     nnz = int(off[-1])
     ctx = fg.Context(local)
-    ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+    if world > 1:
+        # the library's own NCCL communicator (include/flexgsea_b200.h): rank 0 makes the id, torch carries it
+        idt = torch.zeros(nat.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(nat.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.comm_init(bytes(idt.cpu().numpy().tobytes()), world, rank)
+
+    def upload(xh, rh, oh, ih):
+        ctx.set_x(xh); ctx.set_gene_sets(oh, ih)
+        if score_kind == nat.SCORE_LM:
+            ctx.set_response_lm(rh, icpt)
+        else:
+            ctx.set_response_s2n(rh)
+
+    upload(x, resp, off, idx)
+    ctx.set_option("nperm_total", P)
+    R = ctx.n_response(score_kind)
     ctx.set_profiling(True)
     seed = 20261019
+    lo, hi = nat.shard_span(P, world, rank)      # strong scaling: the config's nperm is sharded
+    sc_obs = ctx.score_observed(score_kind)
+    es_obs = ctx.observed_es(es_kind, sc_obs, ragged=False)["es"]
 
     def step():
-        ctx.perm_null(nat.SCORE_S2N, es_kind, P, perm=None, seed=seed, perm_id0=rank * P, want_host=False)
-        return ctx.last_timings()
+        """one pass of the hot path: this rank's span of the null loop, then the significance of
+        every response over the sharded null (NCCL exchange inside the library when N > 1)"""
+        ctx.perm_null(score_kind, es_kind, hi - lo, perm=None, seed=seed, perm_id0=lo, want_host=False)
+        ms, ln = ctx.last_timings()
+        coll = 0.0
+        for r in range(R):
+            sig = ctx.calc_sig_sharded(es_obs[:, r], P, r, True, True, False, exchange=args.exchange)
+            coll += ctx.last_sig_timings()["collectives"]
+        t = ctx.last_sig_timings()
+        return ms, ln, t["step"], coll, sig
 
     def barrier():
         if dist is not None:
@@ -197,11 +261,14 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count()
-    dev_ms, stage_ms, stage_launch = 0.0, {"perm": 0.0, "score": 0.0, "rank": 0.0, "es": 0.0}, None
+    dev_ms, null_ms, coll_ms = 0.0, 0.0, 0.0
+    stage_ms, stage_launch = {"perm": 0.0, "score": 0.0, "rank": 0.0, "es": 0.0}, None
     w0 = time.perf_counter()
     for _ in range(args.steps):
-        ms, ln = step()
-        dev_ms += ms["total"]
+        ms, ln, step_ms, coll, sig = step()
+        dev_ms += step_ms
+        null_ms += ms["total"]
+        coll_ms += coll
         for k in stage_ms:
             stage_ms[k] += ms[k]
         stage_launch = ln
@@ -209,51 +276,53 @@ def run_gpu(args):
     wall_ms = 1e3 * (time.perf_counter() - w0)
     launches = ctx.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, wall_ms, null_ms, coll_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms = float(t[0]), float(t[1])
-    units = float(S) * R * P * world * args.steps
+    dev_ms, wall_ms, null_ms, coll_ms = (float(v) for v in t)
+    lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(lt)
+    launches = int(lt[0])
+    units = float(S) * R * P * args.steps
     value = units / (dev_ms / 1e3)
+    assert np.isfinite(sig["fdr"]).all() and (sig["p"] > 0).all()
 
     # ---- end to end through the public C-ABI calls of one flexgsea() run --------
-    perm_h = synth.perm_matrix(n, P, seed=4 + rank)
-    xp, _k1 = pinned(x); yp, _k2 = pinned(y.astype(np.int32)); pp, _k3 = pinned(perm_h)
+    perm_h = synth.perm_matrix(n, P, seed=4) if P * n <= 4e7 else None   # C5: drawn on the device
+    xp, _k1 = pinned(x); rp, _k2 = pinned(resp)
+    pp = None
+    if perm_h is not None:
+        pp, _k3 = pinned(np.asfortranarray(perm_h[:, lo:hi]))
     offp, _k4 = pinned(off); idxp, _k5 = pinned(idx)
 
     def e2e_step():
-        ctx.set_x(xp); ctx.set_gene_sets(offp, idxp); ctx.set_response_s2n(yp)
-        sc = ctx.score_observed(nat.SCORE_S2N)
+        upload(xp, rp, offp, idxp)
+        sc = ctx.score_observed(score_kind)
         obs = ctx.observed_es(es_kind, sc, ragged=False)  # default flexgsea(): return_values = character()
-        ctx.perm_null(nat.SCORE_S2N, es_kind, P, perm=pp, want_host=False)
-        sig = ctx.calc_sig(obs["es"][:, 0], 0, True, True, False)
-        return sig
+        ctx.perm_null(score_kind, es_kind, hi - lo, perm=pp, seed=seed, perm_id0=lo, want_host=False)
+        return [ctx.calc_sig_sharded(obs["es"][:, r], P, r, True, True, False, exchange=args.exchange)
+                for r in range(R)]
 
     e2e_step()
     barrier()
     e0 = time.perf_counter()
     e_steps = max(1, min(args.steps, 3))
     for _ in range(e_steps):
-        sig = e2e_step()
+        e2e_step()
     barrier()
     e2e_s = (time.perf_counter() - e0) / e_steps
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te[0])
-    h2d = x.nbytes + 4 * n + perm_h.nbytes + 4 * (S + 1 + nnz) + 8 * G * R + 8 * S
-    d2h = 8 * G * R + S * R * (8 * 3 + 4 * 2) + S * (6 * 8 + 4 * 8) + 32
-
-    # ---- multi-GPU: the significance exchange (all-gather sums, all-reduce counts)
-    if dist is not None:
-        sc = ctx.score_observed(nat.SCORE_S2N)
-        es_obs = ctx.observed_es(es_kind, sc, ragged=False)["es"][:, 0]
-        shard = api._Shard(None)
-        r = api.sharded_sig(ctx, shard, fg.flexgsea_calc_sig, es_obs, 0, False, P * world)
-        assert np.isfinite(r["fdr"]).all()
+    # bytes over PCIe per step, all ranks: uploads are replicated, the permutation matrix is sharded
+    h2d = world * (x.nbytes + resp.nbytes + 4 * (S + 1 + nnz) + 8 * G * R + 8 * S * R) + (4 * n * P if pp is not None else 0)
+    d2h = world * (8 * G * R + S * R * (8 * 3 + 4 * 2) + R * (S * (6 * 8 + 4 * 8) + 32))
 
     if rank != 0:
         if dist is not None:
+            ctx.comm_destroy()
             dist.destroy_process_group()
         return
 
@@ -261,12 +330,13 @@ def run_gpu(args):
     peak, peak_src = peaks()
     Gp = (G + 7) & ~7
     dom = max(("score", "rank", "es"), key=lambda k: stage_ms[k])
+    wks = es_kind == nat.ES_WEIGHTED_KS
     alg_bytes_col = {  # algorithmic HBM bytes per score column (DESIGN.md "Kernels")
         "score": 8 * G,                 # score write (x is L2 resident, 8*n*G once)
         "rank": 8 * G + 10 * Gp,        # score read + rank (u16) and rank-ordered weight (f64) write
-        "es": (10 * Gp if es_kind == nat.ES_WEIGHTED_KS else 8 * G) + 8 * S,
+        "es": (10 * Gp if wks else 8 * G) + 8 * S,
     }
-    cols = P * R
+    cols = (hi - lo) * R   # rank 0's columns (the stage times are rank 0's)
     roof = {}
     for k in ("score", "rank", "es"):
         nl = max(1, stage_launch[k])
@@ -278,8 +348,10 @@ def run_gpu(args):
     dl = roof[dom]
     per_launch_bytes = dl["alg_bytes_per_step"] / dl["launches_per_step"]
     per_launch_ms = dl["ms_per_step"] / dl["launches_per_step"]
-    roofline = {"bound": "hbm", "kernel": {"score": "s2n_mma_kernel", "rank": "sort_rank32_kernel",
-                                            "es": "es_wks_kernel" if es_kind == nat.ES_WEIGHTED_KS else "es_mean_smem_kernel"}[dom],
+    kname = {"score": "lm_gemm_kernel" if score_kind == nat.SCORE_LM else "s2n_mma_kernel",
+             "rank": "sort_rank32_kernel" if G <= 29696 else "sort_rank_big_kernel",
+             "es": "es_wks_kernel" if wks else "es_mean_smem_kernel"}[dom]
+    roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": dl["achieved_gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": dl["achieved_gbs"] / peak, "traffic": None,
                 "alg_bytes_per_launch": per_launch_bytes, "launch_ms": per_launch_ms,
@@ -288,7 +360,7 @@ def run_gpu(args):
     if os.path.exists(tr):
         try:  # DRAM bytes per launch from the committed ncu --set full capture (per column x columns per launch)
             t = json.load(open(tr)).get(roofline["kernel"])
-            if t:
+            if t and t.get("config", "C2") == KINDS[args.config][0]:
                 roofline["traffic"] = t["dram_bytes_per_column"] * cols / dl["launches_per_step"]
                 roofline["traffic_source"] = t["source"]
                 if t.get("pipes"):  # what actually binds the kernel (ncu, same capture): not DRAM
@@ -302,14 +374,14 @@ def run_gpu(args):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import pyoracle as orc
         cores = orc.use_all_cores()
-        P_s = max(cores * 8, 64)
+        sk, ek = oracle_kinds(orc, args.config)
+        P_s = cpu_sample_perms(args.config, cores)
         ps = synth.perm_matrix(n, P_s, seed=4)
-        ok = orc.ES_MAXMEAN if args.config == "C4" else orc.ES_WKS
-        orc.perm_null(x, orc.SCORE_S2N, y, False, ps[:, :cores], off, idx, ok)
+        orc.perm_null(x, sk, resp, icpt, ps[:, :max(1, min(cores, P_s))], off, idx, ek)
         t0 = time.perf_counter()
         reps = 0
         while time.perf_counter() - t0 < 10.0 or reps < 1:
-            rc, _ = orc.perm_null(x, orc.SCORE_S2N, y, False, ps, off, idx, ok)
+            rc, _ = orc.perm_null(x, sk, resp, icpt, ps, off, idx, ek)
             reps += 1
         dt = (time.perf_counter() - t0) / reps
         cpu = {"value": S * R * P_s / dt, "unit": "ES/s", "cores": cores, "kind": "port",
@@ -317,20 +389,34 @@ def run_gpu(args):
                          "OpenMP over permutations" % (P_s, P, S)}
 
     out = {
-        "metric": "gene-set x permutation ES/sec (null loop)", "value": value, "unit": "ES/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_TEXT[args.config], "nperm_per_gpu": P, "genes": G, "samples": n,
-                   "gene_sets": S, "nnz": nnz, "responses": R, "seeds": {"sets": 1, "x": 2, "philox": seed},
-                   "permutations": "device Philox4x32-10 (value); host int32 matrix uploaded (e2e)",
+        "metric": "gene-set x permutation ES/sec (null loop + significance)", "value": value, "unit": "ES/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_TEXT[args.config], "nperm": P, "nperm_per_gpu": hi - lo, "genes": G,
+                   "samples": n, "gene_sets": S, "nnz": nnz, "responses": R,
+                   "seeds": {"sets": 1, "x": 2, "philox": seed},
+                   "permutations": "device Philox4x32-10 keyed by the global permutation id (value); host int32 "
+                                   "matrix uploaded (e2e)" + ("" if pp is not None else " -- drawn on the device for this size"),
+                   "sharding": "rank r takes permutations [r*P/N, (r+1)*P/N) of the config's nperm (strong scaling); "
+                               "significance exchange: " + ("all-gather of the null shards" if args.exchange else
+                               "all-gather of per-set double-double sums + int64 all-reduce of the counts")
+                               + " over NCCL inside the library",
                    "l2": "inputs larger than L2: each block streams %d MB of scores/ranks/weights (L2 is 126 MB)"
-                         % int(min(P, 2048) * (18 * G) / 1e6),
-                   "score_mode": "FP64 tensor-core contraction + rank certification (near-tied / cancelled entries recomputed in the reference operation order)"},
+                         % int(min((hi - lo) * R, 4096) * (18 * G) / 1e6),
+                   "score_mode": ("FP64 tensor-core GEMM against the permuted pseudo-inverse rows" if score_kind == nat.SCORE_LM else
+                                  "FP64 tensor-core contraction + rank certification (near-tied / cancelled entries "
+                                  "recomputed in the reference operation order)")},
+        "timed_region": "null loop of the rank's span + flexgsea_calc_sig of every response over the sharded null; "
+                        "device time from the first kernel of the null loop to the last of the significance "
+                        "(CUDA events on the library's stream), max over ranks",
+        "null_loop_ms_per_step": null_ms / args.steps,
+        "collective_ms_per_step": coll_ms / args.steps,
         "wall_ms_per_step": wall_ms / args.steps,
-        "e2e": {"value": float(S) * R * P * world / e2e_s, "unit": "ES/s", "h2d_bytes_per_step": int(h2d),
+        "e2e": {"value": float(S) * R * P / e2e_s, "unit": "ES/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
                 "what": "set_x + set_gene_sets + set_response + observed scores/ES(+extras) + null loop "
-                        "(host permutation matrix) + calc_sig; pinned host buffers; result table read back"},
+                        "(host permutation matrix) + calc_sig (sharded: NCCL exchange); pinned host buffers; "
+                        "result table read back on every rank"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "stages": roof,
@@ -339,6 +425,7 @@ def run_gpu(args):
     }
     print(json.dumps(out))
     if dist is not None:
+        ctx.comm_destroy()
         dist.destroy_process_group()
 
 
@@ -349,9 +436,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="C2", choices=list(WORKLOAD_TEXT))
-    ap.add_argument("--perms", type=int, default=0, help="override nperm per GPU (debug)")
+    ap.add_argument("--perms", type=int, default=0, help="override the config's nperm (debug)")
     ap.add_argument("--ref-perms", type=int, default=0, help="permutations per reference step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", type=int, default=0, choices=[0, 1],
+                    help="significance exchange at N > 1: 0 = counts (default), 1 = all-gather of the null")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3

@@ -14,7 +14,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libflexgsea_b200.so")
 
-OK, ERR_ARG, ERR_CUDA, ERR_NONFINITE, ERR_OOM, ERR_STATE, ERR_UNSUPPORTED = range(7)
+OK, ERR_ARG, ERR_CUDA, ERR_NONFINITE, ERR_OOM, ERR_STATE, ERR_UNSUPPORTED, ERR_CANCELLED, ERR_COMM = range(9)
+COMM_ID_BYTES = 128
 SCORE_S2N, SCORE_LM = 0, 1
 ES_WEIGHTED_KS, ES_MAXMEAN, ES_MEAN = 0, 1, 2
 
@@ -28,6 +29,12 @@ SYMBOLS = [
     "fgs_last_timings", "fgs_set_profiling", "fgs_set_option", "fgs_set_progress",
     "fgs_gmt_parse", "fgs_gmt_read", "fgs_gmt_n_sets", "fgs_gmt_nnz", "fgs_gmt_offsets", "fgs_gmt_index",
     "fgs_gmt_set_name", "fgs_gmt_stats", "fgs_gmt_free",
+    "fgs_comm_unique_id", "fgs_comm_init", "fgs_comm_destroy", "fgs_comm_info", "fgs_shard_span",
+    "fgs_calc_sig_sharded", "fgs_comm_allgather_null", "fgs_last_sig_timings",
+    "fgs_group_create", "fgs_group_destroy", "fgs_group_size", "fgs_group_ctx", "fgs_group_set_x",
+    "fgs_group_set_gene_sets", "fgs_group_set_response_s2n", "fgs_group_set_response_lm",
+    "fgs_group_set_option", "fgs_group_score_observed", "fgs_group_observed_es", "fgs_group_perm_null",
+    "fgs_group_es_from_scores", "fgs_group_calc_sig", "fgs_group_last_timings",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -55,6 +62,7 @@ def load():
                 "(there is no CPU fallback)" % LIB_PATH)
         _lib = C.CDLL(LIB_PATH)
         _lib.fgs_last_error.restype = C.c_char_p
+        _lib.fgs_group_ctx.restype = C.c_void_p
     return _lib
 
 
@@ -111,13 +119,37 @@ def device_count():
     return n.value
 
 
+def comm_unique_id():
+    """NCCL unique id (bytes) made by the library; rank 0 makes it, the host
+    program carries it to the other ranks (fgs_comm_unique_id)."""
+    L = load()
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = L.fgs_comm_unique_id(buf)
+    if rc != OK:
+        raise FlexgseaError(rc, L.fgs_last_error().decode())
+    return buf.raw
+
+
+def shard_span(n_perm, n_ranks, rank):
+    """[lo, hi) of the permutations rank `rank` of `n_ranks` takes (fgs_shard_span)."""
+    lo, hi = C.c_longlong(), C.c_longlong()
+    rc = load().fgs_shard_span(C.c_longlong(n_perm), int(n_ranks), int(rank), C.byref(lo), C.byref(hi))
+    if rc != OK:
+        raise FlexgseaError(rc, "fgs_shard_span: bad argument")
+    return lo.value, hi.value
+
+
 class Context:
     """One per GPU; owns the device-resident problem and null distribution."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, _handle=None):
         self._lib = load()
-        self._h = C.c_void_p()
-        self._check(self._lib.fgs_create(int(device), C.byref(self._h)))
+        self._owned = _handle is None
+        if _handle is None:
+            self._h = C.c_void_p()
+            self._check(self._lib.fgs_create(int(device), C.byref(self._h)))
+        else:  # a context that belongs to a Group
+            self._h = C.c_void_p(_handle)
         self.device = device
 
     def _check(self, rc):
@@ -128,9 +160,9 @@ class Context:
             raise FlexgseaError(rc, "flexgsea_b200 error %d: %s" % (rc, msg))
 
     def close(self):
-        if self._h:
+        if self._h and self._owned:
             self._lib.fgs_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -305,6 +337,48 @@ class Context:
                                              _p(fdr, _dp), _p(fc, _lp), _p(gc, _lp)))
         return dict(fdr=fdr, fdr_counts=fc, glob_counts=gc)
 
+    # ---- permutations sharded over GPUs (one process per GPU) ---------------
+    def comm_init(self, unique_id, n_ranks, rank):
+        assert len(unique_id) == COMM_ID_BYTES
+        self._check(self._lib.fgs_comm_init(self._h, unique_id, int(n_ranks), int(rank)))
+
+    def comm_destroy(self):
+        self._check(self._lib.fgs_comm_destroy(self._h))
+
+    def comm_info(self):
+        n, r = C.c_int(), C.c_int()
+        self._check(self._lib.fgs_comm_info(self._h, C.byref(n), C.byref(r)))
+        return n.value, r.value
+
+    def calc_sig_sharded(self, es, n_perm_total, response=0, split_p=True, calc_nes=True, abs_flag=False,
+                         exchange=0):
+        """flexgsea_calc_sig over the null sharded over the ranks of the attached
+        communicator (NCCL inside the library); same result dict as calc_sig."""
+        es = np.ascontiguousarray(es, dtype=np.float64)
+        S = es.size
+        res = {k: np.full(S, np.nan) for k in ("p", "p_high", "p_low", "nes", "fdr", "fwer")}
+        pc = np.zeros((S, 2), dtype=np.int64); fc = np.zeros((S, 2), dtype=np.int64)
+        gc = np.zeros(4, dtype=np.int64)
+        self._check(self._lib.fgs_calc_sig_sharded(
+            self._h, _p(es, _dp), int(response), int(split_p), int(calc_nes), int(abs_flag),
+            C.c_longlong(n_perm_total), int(exchange), _p(res["p"], _dp), _p(res["p_high"], _dp),
+            _p(res["p_low"], _dp), _p(res["nes"], _dp), _p(res["fdr"], _dp), _p(res["fwer"], _dp), _p(pc, _lp),
+            _p(fc, _lp), _p(gc, _lp)))
+        res.update(p_counts=pc, fdr_counts=fc, glob_counts=gc)
+        return res
+
+    def allgather_null(self, n_perm_total, want_host=True):
+        """every rank's resident null becomes the full [S, R, n_perm_total]"""
+        _, S, R, _ = self.null_device_ptr()
+        out = np.zeros((S, R, n_perm_total), order="F") if want_host else None
+        self._check(self._lib.fgs_comm_allgather_null(self._h, C.c_longlong(n_perm_total), _p(out, _dp)))
+        return out
+
+    def last_sig_timings(self):
+        ms = (C.c_float * 4)()
+        self._check(self._lib.fgs_last_sig_timings(self._h, ms))
+        return {"sig": ms[0], "collectives": ms[1], "step": ms[2], "n_collectives": int(ms[3])}
+
     # ---- instrumentation -------------------------------------------------
     def launch_count(self):
         n = C.c_longlong(0)
@@ -333,3 +407,139 @@ class Context:
 
     def set_option(self, name, value):
         self._check(self._lib.fgs_set_option(self._h, name.encode(), C.c_longlong(int(value))))
+
+
+class Group:
+    """One process, several GPUs: what flexgsea(parallel = N) binds from R
+    (fgs_group_*).  Uploads are replicated, the null loop takes the whole
+    permutation range and shards it, significance exchanges over NCCL."""
+
+    def __init__(self, n_gpu, devices=None):
+        self._lib = load()
+        self._h = C.c_void_p()
+        dv = None
+        if devices is not None:
+            dv = (C.c_int * n_gpu)(*[int(d) for d in devices])
+        rc = self._lib.fgs_group_create(int(n_gpu), dv, C.byref(self._h))
+        self._check(rc)
+        self.size = self._lib.fgs_group_size(self._h)
+        self.ctx = [Context(i, _handle=self._lib.fgs_group_ctx(self._h, i)) for i in range(self.size)]
+
+    def _check(self, rc):
+        if rc != OK:
+            msg = self._lib.fgs_last_error().decode()
+            if rc == ERR_NONFINITE:
+                raise NonFiniteScoreError(rc, msg)
+            raise FlexgseaError(rc, "flexgsea_b200 error %d: %s" % (rc, msg))
+
+    def close(self):
+        if self._h:
+            for c in self.ctx:
+                c._h = C.c_void_p()
+            self._lib.fgs_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_x(self, x):
+        x = _f(x)
+        self.n, self.G = x.shape
+        self._check(self._lib.fgs_group_set_x(self._h, _p(x, _dp), self.n, self.G))
+        for c in self.ctx:
+            c.n, c.G = self.n, self.G
+
+    def set_gene_sets(self, offsets, index):
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        index = np.ascontiguousarray(index, dtype=np.int32)
+        self.S, self.nnz, self.offsets = offsets.size - 1, int(offsets[-1]), offsets
+        self._check(self._lib.fgs_group_set_gene_sets(self._h, _p(offsets, _ip), _p(index, _ip), self.S))
+        for c in self.ctx:
+            c.S, c.nnz, c.offsets = self.S, self.nnz, offsets
+
+    def set_response_s2n(self, y_bin):
+        y = _i(y_bin)
+        if y.ndim == 1:
+            y = y.reshape(-1, 1, order="F")
+        self._check(self._lib.fgs_group_set_response_s2n(self._h, _p(y, _ip), y.shape[0], y.shape[1]))
+
+    def set_response_lm(self, design, has_intercept):
+        d = _f(design)
+        self._check(self._lib.fgs_group_set_response_lm(self._h, _p(d, _dp), d.shape[0], d.shape[1],
+                                                        int(bool(has_intercept))))
+
+    def set_option(self, name, value):
+        self._check(self._lib.fgs_group_set_option(self._h, name.encode(), C.c_longlong(int(value))))
+
+    def n_response(self, score_kind):
+        return self.ctx[0].n_response(score_kind)
+
+    def score_observed(self, score_kind, abs_flag=False):
+        R = self.n_response(score_kind)
+        out = np.zeros((self.G, R), order="F")
+        self._check(self._lib.fgs_group_score_observed(self._h, score_kind, int(abs_flag), _p(out, _dp)))
+        return out
+
+    def observed_es(self, es_kind, scores, p=1.0, ragged=True):
+        sc = _f(scores)
+        G, R = sc.shape
+        S, nnz = self.S, self.nnz
+        es = np.zeros((S, R), order="F")
+        res = {"es": es}
+        mea = lep = at = rp = rn = lf = lc = None
+        if es_kind == ES_WEIGHTED_KS:
+            mea = np.zeros((S, R), order="F"); lep = np.zeros((S, R), order="F")
+            if ragged:
+                at = np.zeros((max(nnz, 1), R), dtype=np.int32, order="F")
+                rp = np.zeros((max(nnz, 1), R), order="F"); rn = np.zeros((max(nnz, 1), R), order="F")
+            lf = np.zeros((S, R), dtype=np.int32, order="F"); lc = np.zeros((S, R), dtype=np.int32, order="F")
+        self._check(self._lib.fgs_group_observed_es(self._h, es_kind, C.c_double(p), _p(sc, _dp), G, R,
+                                                    _p(es, _dp), _p(mea, _dp), _p(lep, _dp), _p(at, _ip),
+                                                    _p(rp, _dp), _p(rn, _dp), _p(lf, _ip), _p(lc, _ip)))
+        if es_kind == ES_WEIGHTED_KS:
+            res.update(max_es_at=mea, le_prop=lep, running_es_at=at, running_es_pos=rp, running_es_neg=rn,
+                       le_first=lf, le_count=lc)
+        return res
+
+    def perm_null(self, score_kind, es_kind, n_perm, perm=None, seed=0, p=1.0, abs_flag=False,
+                  want_host=True):
+        R = self.n_response(score_kind)
+        pp = None
+        if perm is not None:
+            pm = _i(perm)
+            assert pm.shape == (self.n, n_perm), (pm.shape, (self.n, n_perm))
+            pp = _p(pm, _ip)
+        out = np.zeros((self.S, R, n_perm), order="F") if want_host else None
+        self._check(self._lib.fgs_group_perm_null(self._h, score_kind, es_kind, C.c_double(p), int(abs_flag),
+                                                  pp, C.c_ulonglong(seed), int(n_perm), _p(out, _dp)))
+        return out
+
+    def es_from_scores(self, es_kind, scores, p=1.0, want_host=True):
+        sc = _f(scores)
+        G, R, P = sc.shape
+        out = np.zeros((self.S, R, P), order="F") if want_host else None
+        self._check(self._lib.fgs_group_es_from_scores(self._h, es_kind, C.c_double(p), _p(sc, _dp), G, R, P,
+                                                       _p(out, _dp)))
+        return out
+
+    def calc_sig(self, es, response=0, split_p=True, calc_nes=True, abs_flag=False, exchange=0):
+        es = np.ascontiguousarray(es, dtype=np.float64)
+        S = es.size
+        res = {k: np.full(S, np.nan) for k in ("p", "p_high", "p_low", "nes", "fdr", "fwer")}
+        pc = np.zeros((S, 2), dtype=np.int64); fc = np.zeros((S, 2), dtype=np.int64)
+        gc = np.zeros(4, dtype=np.int64)
+        self._check(self._lib.fgs_group_calc_sig(self._h, _p(es, _dp), int(response), int(split_p),
+                                                 int(calc_nes), int(abs_flag), int(exchange), _p(res["p"], _dp),
+                                                 _p(res["p_high"], _dp), _p(res["p_low"], _dp),
+                                                 _p(res["nes"], _dp), _p(res["fdr"], _dp), _p(res["fwer"], _dp),
+                                                 _p(pc, _lp), _p(fc, _lp), _p(gc, _lp)))
+        res.update(p_counts=pc, fdr_counts=fc, glob_counts=gc)
+        return res
+
+    def last_timings(self):
+        ms = (C.c_float * 4)()
+        self._check(self._lib.fgs_group_last_timings(self._h, ms))
+        return {"null": ms[0], "sig": ms[1], "collectives": ms[2], "step": ms[3]}

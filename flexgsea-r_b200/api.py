@@ -29,6 +29,7 @@ except Exception:  # pragma: no cover
 NA_LOGICAL = np.iinfo(np.int32).min
 
 _contexts = {}
+_groups = {}
 
 
 def get_context(device=None):
@@ -40,6 +41,14 @@ def get_context(device=None):
     if device not in _contexts:
         _contexts[device] = nat.Context(device)
     return _contexts[device]
+
+
+def get_group(n_gpu):
+    """Process-wide group of the first `n_gpu` GPUs (flexgsea(parallel = N) from a
+    single process: one context and one host thread per GPU, NCCL inside the library)."""
+    if n_gpu not in _groups:
+        _groups[n_gpu] = nat.Group(n_gpu)
+    return _groups[n_gpu]
 
 
 # --------------------------------------------------------------------------
@@ -344,6 +353,40 @@ class _Shard:
         hi = (nperm * (self.rank + 1)) // self.world
         return lo, hi
 
+    def broadcast_bytes(self, b, n):
+        """`n` bytes from rank 0 to every rank (the NCCL unique id of the library's communicator)"""
+        if self.dist is None:
+            return b
+        import torch
+        t = torch.zeros(n, dtype=torch.uint8)
+        if self.rank == 0:
+            t.copy_(torch.frombuffer(bytearray(b), dtype=torch.uint8))
+        if self.dist.get_backend() == "nccl":
+            t = t.cuda()
+        self.dist.broadcast(t, 0)
+        return t.cpu().numpy().tobytes()
+
+    def attach(self, ctx):
+        """Give `ctx` the library's own NCCL communicator over these ranks (once), so that the
+        significance exchange runs device to device inside the C ABI (fgs_calc_sig_sharded)."""
+        if self.dist is None:
+            return False
+        if ctx.comm_info() == (self.world, self.rank):
+            return True
+        uid = nat.comm_unique_id() if self.rank == 0 else b""
+        ctx.comm_init(self.broadcast_bytes(uid, nat.COMM_ID_BYTES), self.world, self.rank)
+        return True
+
+    def random_seed(self):
+        """a fresh seed, the same on every rank (R draws from the session RNG when none is set)"""
+        sd = np.frombuffer(os.urandom(8), dtype=np.int64) & np.int64(0x7fffffffffffffff)
+        if self.dist is None:
+            return int(sd[0])
+        import torch
+        t = self._tensor(sd.copy())
+        self.dist.broadcast(t, 0)
+        return int(t.cpu().numpy()[0])
+
     def _tensor(self, a):
         import torch
         t = torch.from_numpy(np.ascontiguousarray(a))
@@ -374,7 +417,11 @@ def sharded_sig(ctx, shard, sig_fun, es, response, abs, nperm_total):
     all-gather of the per-set double-double null sums (combined in rank order),
     all-reduce of the integer counts, then the pooled-FDR exceedance counts
     all-reduced as int64 -- the exact equivalent of all-gathering the null NES
-    (SURVEY.md section 8e)."""
+    (SURVEY.md section 8e).  With the library's communicator attached
+    (_Shard.attach) the whole exchange is one C-ABI call, device to device; the
+    staged form below goes through the host's torch.distributed instead."""
+    if shard.dist is not None and ctx.comm_info() == (shard.world, shard.rank):
+        return ctx.calc_sig_sharded(es, nperm_total, response, sig_fun.split_p, sig_fun.calc_nes, abs)
     sums, counts = ctx.sig_stage1(es, response, sig_fun.split_p, abs)
     parts = shard.all_gather(sums)
     total = shard.all_reduce_sum(counts)
@@ -397,9 +444,11 @@ def flexgsea(x, y, gene_sets, gene_score_fn=flexgsea_s2n, es_fn=flexgsea_weighte
     the null is the one the reference would compute; ``seed`` + ``rng`` --
     ``rng='R'`` replays R's set.seed(seed); sample.int() stream on the host,
     ``rng='philox'`` draws on the device.  ``block_size`` is accepted for
-    compatibility; the device path sizes its own blocks.  ``parallel`` maps to
-    "shard permutations over the GPUs of torch.distributed", never to forked
-    workers.
+    compatibility; the device path sizes its own blocks.  ``parallel`` never
+    means forked workers: under torch.distributed (one process per GPU) the
+    permutations are sharded over its ranks; in a single process ``parallel=N``
+    (an integer > 1) shards them over N GPUs through the library's group of
+    contexts, which is what the R binding does.
     """
     # ---- prepare and check input (:152-239) -----------------------------
     xv, xnames = _x_values(x)
@@ -448,7 +497,15 @@ def flexgsea(x, y, gene_sets, gene_score_fn=flexgsea_s2n, es_fn=flexgsea_weighte
         offsets, index = gene_sets_to_csr(gene_sets, gene_names)
 
     shard = _Shard(parallel)
-    ctx = get_context(device)
+    n_group = parallel if (isinstance(parallel, int) and not isinstance(parallel, bool)) else 0
+    if shard.world == 1 and n_group > 1:
+        ctx = get_group(n_group)     # same calls; every one fans out over the group's GPUs
+    else:
+        ctx = get_context(device)
+        if shard.world > 1 and shard.dist.get_backend() == "nccl":
+            shard.attach(ctx)
+    grouped = isinstance(ctx, nat.Group)
+    ctx.set_option("nperm_total", nperm)
     ctx.set_x(xv)
     ctx.set_gene_sets(offsets, index)
     builtin_score = isinstance(gene_score_fn, ScoreFn)
@@ -498,18 +555,24 @@ def flexgsea(x, y, gene_sets, gene_score_fn=flexgsea_s2n, es_fn=flexgsea_weighte
         if pm.shape != (n_samples, nperm):
             raise ValueError("perm must be [n_samples x nperm], 1-based")
         pm_local = np.asfortranarray(pm[:, lo:hi])
-    elif rng == "R" or not builtin_score:
-        gen = RRNG(0 if seed is None else seed)
-        pm_local = np.asfortranarray(gen.perm_matrix(n_samples, nperm).T[:, lo:hi])
     else:
-        pm_local = None
-    if seed is None:
-        seed = int.from_bytes(os.urandom(8), "little") if (pm_local is None and shard.world == 1) else 0
+        if seed is None:   # every run its own permutations, the same on every rank
+            seed = shard.random_seed()
+        if rng == "R" or not (builtin_score and builtin_es):
+            # the host loop below needs the permutations themselves
+            gen = RRNG(seed % (2 ** 31))
+            pm_local = np.asfortranarray(gen.perm_matrix(n_samples, nperm).T[:, lo:hi])
+        else:
+            pm_local = None
     want_null_host = ("es_null" in return_values) or not builtin_sig or not builtin_es
     if builtin_score and builtin_es:
         try:
-            null_local = ctx.perm_null(gene_score_fn.kind, es_fn.kind, local, perm=pm_local, seed=seed,
-                                       perm_id0=lo, abs_flag=abs, want_host=want_null_host)
+            if grouped:
+                null_local = ctx.perm_null(gene_score_fn.kind, es_fn.kind, nperm, perm=pm_local, seed=seed or 0,
+                                           abs_flag=abs, want_host=want_null_host)
+            else:
+                null_local = ctx.perm_null(gene_score_fn.kind, es_fn.kind, local, perm=pm_local, seed=seed or 0,
+                                           perm_id0=lo, abs_flag=abs, want_host=want_null_host)
         except nat.NonFiniteScoreError:
             raise ValueError("Gene scoring function returned NA or Inf.")  # :401
     else:
@@ -535,7 +598,7 @@ def flexgsea(x, y, gene_sets, gene_score_fn=flexgsea_s2n, es_fn=flexgsea_weighte
     sig = []
     for r in range(R):
         if builtin_sig and builtin_es:
-            if shard.world == 1:
+            if shard.world == 1:   # (a group exchanges over NCCL inside this call)
                 res = ctx.calc_sig(es[:, r], r, sig_fun.split_p, sig_fun.calc_nes, abs)
             else:
                 res = sharded_sig(ctx, shard, sig_fun, es[:, r], r, abs, nperm)

@@ -445,6 +445,7 @@ int fgs_destroy(fgs_ctx *c) {
   if (!c) return FGS_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  fgs_comm_destroy(c);
   c->set_groups.release(); c->x.release(); c->xc.release(); c->xtot.release(); c->cert_list.release(); c->cert_ctr.release();
   c->cert_redo.release(); c->sort_redo.release(); c->sort_glist.release(); c->gene_sd.release(); c->set_off.release(); c->set_idx.release(); c->set_idx16.release(); c->sig_lut.release(); c->set_slow.release(); c->tie_list.release(); c->tie_ctr.release(); c->obs_es.release(); c->ident.release(); c->obs_labels.release();
   for (auto &b : c->api_d) b.release();
@@ -466,6 +467,8 @@ int fgs_destroy(fgs_ctx *c) {
     cudaFreeHost(c->stage);
     for (int i = 0; i < 16; i++) if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
   }
+  for (int i = 0; i < 8; i++) if (c->sig_ev[i]) cudaEventDestroy(c->sig_ev[i]);
+  c->null_full.release();
   cudaStreamDestroy(c->stream);
   delete c;
   return FGS_OK;
@@ -519,6 +522,8 @@ int fgs_set_option(fgs_ctx *c, const char *name, long long value) {
   else if (!strcmp(name, "force_sort64")) c->opt_sort64 = (int)value;
   else if (!strcmp(name, "s2n_mode")) c->opt_s2n_mode = (int)value;
   else if (!strcmp(name, "es_exact_small")) c->opt_exact_small = (int)value;
+  else if (!strcmp(name, "tail_split")) c->opt_tail_split = (int)value;
+  else if (!strcmp(name, "nperm_total")) c->opt_nperm_total = value > 0 ? value : 0;
   else if (!strcmp(name, "cert_cap")) c->opt_cert_cap = value > 2 ? (int)value : 2;
   else { set_error("unknown option '%s'", name); return FGS_ERR_ARG; }
   return FGS_OK;
@@ -797,7 +802,10 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
   c->cur_obs = (c->obs_valid && c->obs_kind == es_kind && c->obs_S == S && c->obs_R == R) ? c->obs_es.p : nullptr;
   c->cur_obs_R = R;
   c->null_exact_near_obs = c->cur_obs != nullptr;
-  c->cur_exact_all = score_kind == FGS_SCORE_S2N && small_problem(c, es_kind, (long long)R * P);
+  // (routing by the TOTAL permutation count when the caller shards: the same units take the same
+  // path on one GPU and on eight)
+  c->cur_exact_all = score_kind == FGS_SCORE_S2N &&
+                     small_problem(c, es_kind, (long long)R * std::max<long long>(P, c->opt_nperm_total));
   if (c->cur_exact_all) c->null_exact_near_obs = true;
   if (P == 0) return FGS_OK;
   FGS_TRY(flags_reset(c, P));
@@ -906,7 +914,7 @@ int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scor
     c->cur_obs_R = R;
     c->cur_ident = nullptr;
     c->null_exact_near_obs = c->cur_obs != nullptr;
-    c->cur_exact_all = small_problem(c, es_kind, C);
+    c->cur_exact_all = small_problem(c, es_kind, std::max<long long>(C, (long long)R * c->opt_nperm_total));
     if (c->cur_exact_all) c->null_exact_near_obs = true;
     if (C == 0) return FGS_OK;
     FGS_TRY(flags_reset(c, C));
@@ -1167,32 +1175,56 @@ int fgs_sig_finish(fgs_ctx *c, const double *nes, const long long *null_counts,
   return rc;
 }
 
-int fgs_calc_sig(fgs_ctx *c, const double *es, int response, int split_p, int calc_nes, int abs_flag,
-                 double *p, double *p_high, double *p_low, double *nes, double *fdr, double *fwer,
-                 long long *p_counts, long long *fdr_counts, long long *glob_counts) {
-  if (!c || !es) return FGS_ERR_ARG;
-  FGS_TRY(use_device(c));
-  FGS_TRY(sig_check(c, response));
+}  // extern "C" (reopened below)
+
+namespace fgs {
+// flexgsea_calc_sig on the resident null of this context.  With a communicator (sharded = true)
+// the null holds this rank's span of the permutations and the three small exchanges of
+// include/flexgsea_b200.h happen here, on the context's stream, between the kernels: nothing
+// goes through the host.
+int calc_sig_core(fgs_ctx *c, const double *es, int response, int split_p, int calc_nes, int abs_flag,
+                  long long P_total, bool sharded, double *p, double *p_high, double *p_low, double *nes,
+                  double *fdr, double *fwer, long long *p_counts, long long *fdr_counts,
+                  long long *glob_counts) {
   const int S = c->null_S, P = c->null_P;
-  if (P == 0) return FGS_OK;  // R/flexgsea.R:575-577
+  const int nparts = sharded ? c->comm_size : 1, part = sharded ? c->comm_rank : 0;
+  for (int i = 0; i < 8; i++)
+    if (!c->sig_ev[i]) FGS_CUDA(cudaEventCreate(&c->sig_ev[i]));
   DevBuf<double> &d = c->api_d[0]; DevBuf<long long> &di = c->api_l;
+  int n_coll = 0;
+  auto coll_begin = [&]() { if (sharded && n_coll < 3) cudaEventRecord(c->sig_ev[2 + 2 * n_coll], c->stream); };
+  auto coll_end = [&]() { if (sharded && n_coll < 3) cudaEventRecord(c->sig_ev[3 + 2 * n_coll], c->stream); n_coll++; };
   auto body = [&]() -> int {
-    // doubles: es sums[4S] p ph pl mpos mneg nes fwer fdr
-    FGS_TRY(d.ensure((size_t)S * 13)); FGS_TRY(di.ensure((size_t)S * 9 + 8));
-    double *d_es = d.p, *d_sums = d_es + S, *d_p = d_sums + (size_t)S * 4, *d_ph = d_p + S, *d_pl = d_ph + S,
+    // doubles: es parts[nparts*4S] p ph pl mpos mneg nes fwer fdr
+    FGS_TRY(d.ensure((size_t)S * (9 + 4 * (size_t)nparts))); FGS_TRY(di.ensure((size_t)S * 9 + 8));
+    double *d_es = d.p, *d_parts = d_es + S, *d_p = d_parts + (size_t)nparts * S * 4, *d_ph = d_p + S, *d_pl = d_ph + S,
            *d_mp = d_pl + S, *d_mn = d_mp + S, *d_nes = d_mn + S, *d_fw = d_nes + S, *d_fdr = d_fw + S;
     long long *d_cnt = di.p, *d_nc = d_cnt + (size_t)S * 6, *d_gl = d_nc + S, *d_fc = d_gl + 2, *d_gc = d_fc + (size_t)S * 2;
+    FGS_CUDA(cudaEventRecord(c->sig_ev[0], c->stream));
     FGS_TRY(h2d(c, d_es, es, S));
+    double *d_sums = d_parts + (size_t)part * S * 4;  // this rank's slot: the all-gather is in place
     FGS_TRY(launch_sig_stage1(c, c->es_null.p, S, c->null_R, P, response, d_es, split_p, abs_flag, d_sums, d_cnt));
-    FGS_TRY(launch_sig_means(c, d_sums, 1, d_cnt, d_es, S, P, split_p, calc_nes, abs_flag, d_p, d_ph,
+    if (sharded) {
+      coll_begin();
+      if (calc_nes) FGS_TRY(comm_allgather_f64(c, d_sums, d_parts, (size_t)S * 4));
+      FGS_TRY(comm_allreduce_i64(c, d_cnt, (size_t)S * 6));
+      coll_end();
+    }
+    FGS_TRY(launch_sig_means(c, d_parts, nparts, d_cnt, d_es, S, P_total, split_p, calc_nes, abs_flag, d_p, d_ph,
                              d_pl, d_mp, d_mn, d_nes, d_fw));
     if (calc_nes) {
       FGS_TRY(launch_sig_stage2(c, c->es_null.p, S, c->null_R, P, response, d_es, abs_flag, d_mp, d_mn,
                                 d_nes, d_nc, d_gl));
+      if (sharded) {  // [S] exceedance counts + the two global counts sit back to back
+        coll_begin();
+        FGS_TRY(comm_allreduce_i64(c, d_nc, (size_t)S + 2));
+        coll_end();
+      }
       FGS_TRY(launch_sig_finish(c, d_nes, d_nc, d_gl, S, abs_flag, d_fdr, d_fc, d_gc));
     } else {
       FGS_TRY(launch_bh(c, d_p, S, d_fdr));
     }
+    FGS_CUDA(cudaEventRecord(c->sig_ev[1], c->stream));
     FGS_TRY(d2h(c, p, d_p, S)); FGS_TRY(d2h(c, p_high, d_ph, S)); FGS_TRY(d2h(c, p_low, d_pl, S));
     FGS_TRY(d2h(c, nes, d_nes, S)); FGS_TRY(d2h(c, fdr, d_fdr, S)); FGS_TRY(d2h(c, fwer, d_fw, S));
     if (p_counts) {  // (numerator-1, denominator-1) of p, or (high, low) counts
@@ -1210,8 +1242,39 @@ int fgs_calc_sig(fgs_ctx *c, const double *es, int response, int split_p, int ca
     if (calc_nes) { FGS_TRY(d2h(c, fdr_counts, d_fc, (size_t)S * 2)); FGS_TRY(d2h(c, glob_counts, d_gc, 4)); }
     return sync(c);
   };
-  int rc = body();
+  const int rc = body();
+  if (rc == FGS_OK) {
+    float t = 0.f;
+    c->last_sig_ms[1] = 0.f;
+    cudaEventElapsedTime(&c->last_sig_ms[0], c->sig_ev[0], c->sig_ev[1]);
+    for (int k = 0; k < std::min(n_coll, 3); k++)
+      if (cudaEventElapsedTime(&t, c->sig_ev[2 + 2 * k], c->sig_ev[3 + 2 * k]) == cudaSuccess) c->last_sig_ms[1] += t;
+    // one step on the device timeline: start of the most recent null loop -> end of this call
+    if (cudaEventElapsedTime(&t, c->ev[0], c->sig_ev[1]) == cudaSuccess) c->last_sig_ms[2] = t;
+    else { cudaGetLastError(); c->last_sig_ms[2] = 0.f; }
+    c->last_sig_ms[3] = (float)n_coll;
+  }
   return rc;
+}
+}  // namespace fgs
+
+extern "C" {
+
+int fgs_calc_sig(fgs_ctx *c, const double *es, int response, int split_p, int calc_nes, int abs_flag,
+                 double *p, double *p_high, double *p_low, double *nes, double *fdr, double *fwer,
+                 long long *p_counts, long long *fdr_counts, long long *glob_counts) {
+  if (!c || !es) return FGS_ERR_ARG;
+  FGS_TRY(use_device(c));
+  FGS_TRY(sig_check(c, response));
+  if (c->null_P == 0) return FGS_OK;  // R/flexgsea.R:575-577
+  return calc_sig_core(c, es, response, split_p, calc_nes, abs_flag, c->null_P, false, p, p_high, p_low, nes,
+                       fdr, fwer, p_counts, fdr_counts, glob_counts);
+}
+
+int fgs_last_sig_timings(fgs_ctx *c, float *ms) {
+  if (!c || !ms) return FGS_ERR_ARG;
+  for (int i = 0; i < 4; i++) ms[i] = c->last_sig_ms[i];
+  return FGS_OK;
 }
 
 }  // extern "C"

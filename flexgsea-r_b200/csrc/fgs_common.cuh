@@ -94,6 +94,8 @@ struct fgs_ctx {
   int opt_s2n_mode = 1;        // 1 = tensor-core contraction + rank certification, 0 = bit-faithful kernel
   int opt_cert_cap = 4 << 20;  // entries per certification list (epilogue list, tie list)
   int opt_score_ppt = 0;
+  long long opt_nperm_total = 0;  // permutations over ALL ranks when the caller shards them (0: this call's)
+  int opt_tail_split = 1;      // split the columns of a partial last round over the idle SMs (ES kernels)
 
   // expression matrix x [n x G] (gene's samples contiguous)
   int n = 0, G = 0;
@@ -187,6 +189,14 @@ struct fgs_ctx {
   fgs::DevBuf<int> api_i[3];
   fgs::DevBuf<long long> api_l;
   fgs::DevBuf<int> sig_lut;        // coarse cell index over the sorted NES thresholds (pooled FDR)
+
+  // permutations sharded over GPUs (fgs_multi.cu): NCCL communicator of this rank
+  void *comm = nullptr;            // ncclComm_t
+  int comm_rank = 0, comm_size = 1;
+  bool comm_owned = true;          // false: the communicator belongs to a fgs_group
+  fgs::DevBuf<double> null_full;   // all-gathered null (fgs_comm_allgather_null), swapped with es_null
+  cudaEvent_t sig_ev[8] = {};      // [0],[1] significance call; [2..7] around its collectives
+  float last_sig_ms[4] = {0, 0, 0, 0};
 };
 
 namespace fgs {
@@ -256,6 +266,10 @@ int launch_sig_stage2(fgs_ctx *c, const double *d_null, int S, int R, int P, int
 int launch_sig_finish(fgs_ctx *c, const double *d_nes, const long long *d_null_counts,
                       const long long *d_glob, int S, int abs_flag, double *d_fdr,
                       long long *d_fdr_counts, long long *d_glob_counts);
+
+// collectives of the significance exchange on c->stream (fgs_multi.cu); no-ops without a communicator
+int comm_allgather_f64(fgs_ctx *c, const double *send, double *recv, size_t count);
+int comm_allreduce_i64(fgs_ctx *c, long long *buf, size_t count);
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 // row pitch (elements) of the per-column rank16 / sabs arrays: 16-byte aligned rows

@@ -20,6 +20,8 @@
 // O(m^2 / 32) warp kernel that needs no ordering at all: max/min over the
 // members of pos/neg is order independent once each member knows its ordinal
 // and prefix weight, which it gets by comparing against every other member.
+#include <algorithm>
+
 #include "fgs_common.cuh"
 
 namespace fgs {
@@ -345,7 +347,7 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
               const double *__restrict__ set_invgm, int S, double *__restrict__ es_out,
               int2 *__restrict__ tie_list, int *__restrict__ tie_ctr, int tie_cap,
               const double *__restrict__ obs, const int *__restrict__ ident, int R,
-              const int2 *__restrict__ groups, int n_groups) {
+              const int2 *__restrict__ groups, int n_groups, int tail_split) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31;
   const size_t Gp = pitch_of(G);
@@ -354,7 +356,22 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
   __shared__ int s_next;  // next group of the column (see below)
   if (W_SMEM && tid < 8) s_abs[G + tid] = 0.0;  // zero slot(s) behind the weights: the pads' weight
 
-  for (long long col = blockIdx.x; col < C; col += gridDim.x) {
+  // Whole rounds of one column per CTA, then the tail round: the C % gridDim.x columns left over
+  // are split `tail_split` ways (every CTA stages the column, the groups go round by `part`), so
+  // that the last round keeps the SMs busy for 1 / tail_split of a column instead of idling most
+  // of them for a whole one -- what a rank's share of a sharded null (1 250 columns = 8.45 rounds
+  // at C2 over eight GPUs) would otherwise pay.
+  // (a launch holds one block of columns: int arithmetic; part / nparts live in shared memory so
+  // that the group loop keeps its registers)
+  const int C_full = ((int)C / (int)gridDim.x) * (int)gridDim.x;
+  __shared__ int s_part[2];
+  for (int w = blockIdx.x;; w += gridDim.x) {
+    int col = w;
+    if (w >= C_full) {
+      const int t = w - C_full;
+      if (t >= ((int)C - C_full) * tail_split) break;
+      col = C_full + t / tail_split;
+    }
     __syncthreads();
     {  // stage the column: 16-byte vector copies (rows are 16-byte aligned), ranks made 0-based
       const uint4 *src = (const uint4 *)(rank16 + (size_t)col * Gp);
@@ -370,7 +387,12 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
       }
     }
     __syncthreads();
-    if (tid == 0) { s_rank[G] = (uint16_t)G; s_next = 0; }  // the pad gene's key (inside the staged row when G < Gp)
+    if (tid == 0) {
+      s_rank[G] = (uint16_t)G; s_next = 0;  // the pad gene's key (inside the staged row when G < Gp)
+      const bool in_tail = w >= C_full;
+      s_part[0] = in_tail ? (w - C_full) % tail_split : 0;
+      s_part[1] = in_tail ? tail_split : 1;
+    }
     __syncthreads();
     const double *wsrc = W_SMEM ? s_abs : sabs + (size_t)col * Gp;
     // observed ES of this column's response; none for a label-preserving permutation (copied later)
@@ -384,7 +406,7 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
     for (;;) {
       int g = 0;
       if (lane == 0) g = atomicAdd(&s_next, 1);
-      g = __shfl_sync(0xffffffffu, g, 0);
+      g = s_part[0] + s_part[1] * __shfl_sync(0xffffffffu, g, 0);
       if (g >= n_groups) break;
       const int2 ge = __ldg(groups + g);  // {first set (processing order), cnt | L << 8 | log2(SL) << 16}
       const int cnt = ge.y & 0xff, L = (ge.y >> 8) & 0xff, sl = ge.y >> 16;
@@ -426,6 +448,7 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
         }
       }
     }
+    if (w >= C_full) break;  // the tail round is the last
   }
 }
 
@@ -784,8 +807,9 @@ static int launch_es_wks_inner(fgs_ctx *c, const uint16_t *d_rank16, const doubl
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
   if (G > 65534)  // the pad key G must fit a uint16 next to the ranks
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
-  int grid = c->num_sms;
-  if (grid > C) grid = (int)C;
+  const int grid = c->num_sms;
+  const int tail = (int)(C % grid);
+  const int tail_split = (tail && c->opt_tail_split) ? std::max(1, std::min(8, grid / tail)) : 1;
   // rank (2 B) + weight (8 B) per gene on chip, + pad gene, + zero weight slots
   const bool w_smem = Gp * 10 + 16 + 64 + 16 <= budget;  // 16: the kernel's static shared memory
   const size_t smem = w_smem ? Gp * 10 + 16 + 64 : Gp * 2 + 16;
@@ -796,7 +820,8 @@ static int launch_es_wks_inner(fgs_ctx *c, const uint16_t *d_rank16, const doubl
     FGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, threads, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx16.p,
                                              c->set_invgm.p, c->S, d_es, c->tie_list.p, c->tie_ctr.p,
-                                             c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R, groups, n);
+                                             c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R, groups, n,
+                                             tail_split);
     c->launches++;
     FGS_CUDA(cudaGetLastError());
     return FGS_OK;
@@ -947,14 +972,22 @@ es_mean_smem_kernel(const double *__restrict__ scores, int G, long long C,
                     const int4 *__restrict__ set_info, const uint16_t *__restrict__ idx16, int S,
                     int abs_flag, double *__restrict__ es_out, int2 *__restrict__ tie_list,
                     int *__restrict__ tie_ctr, int tie_cap, const double *__restrict__ obs,
-                    const int *__restrict__ ident, int R) {
+                    const int *__restrict__ ident, int R, int tail_split) {
   extern __shared__ __align__(16) unsigned char smem[];
   double *s_sc = (double *)smem;  // [G + 1]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int seg = lane >> 3, ls = lane & 7;
   const int nquads = (S + 3) >> 2;
   if (tid == 0) s_sc[G] = 0.0;  // the pad gene
-  for (long long col = blockIdx.x; col < C; col += gridDim.x) {
+  const long long C_full = (C / gridDim.x) * gridDim.x;  // then the tail round, split (see es_wks_kernel)
+  for (long long w = blockIdx.x;; w += gridDim.x) {
+    long long col = w;
+    int part = 0, nparts = 1;
+    if (w >= C_full) {
+      const long long t = w - C_full;
+      if (t >= (C - C_full) * tail_split) break;
+      col = C_full + t / tail_split; part = (int)(t % tail_split); nparts = tail_split;
+    }
     __syncthreads();
     const double *sc = scores + (size_t)col * G;
     for (int i = tid; i < G; i += blockDim.x) {
@@ -965,7 +998,7 @@ es_mean_smem_kernel(const double *__restrict__ scores, int G, long long C,
     double *es_col = es_out + (size_t)col * S;
     // observed ES of this column's response; none for a label-preserving permutation (copied later)
     const double *col_obs = (obs && !(ident && __ldg(ident + col / R))) ? obs + (size_t)(col % R) * S : nullptr;
-    for (int q = warp; q < nquads; q += nwarps) {
+    for (int q = warp * nparts + part; q < nquads; q += nwarps * nparts) {
       const int k = 4 * q + seg;
       int4 info = make_int4(0, 0, 0, 0);
       if (k < S) info = __ldg(set_info + k);
@@ -1011,6 +1044,7 @@ es_mean_smem_kernel(const double *__restrict__ scores, int G, long long C,
         if (shaky || fabs(es - e_obs) <= ES_OBS_REL * fabs(e_obs)) tie_push(tie_list, tie_ctr, tie_cap, (int)col, info.w);
       }
     }
+    if (w >= C_full) break;
   }
 }
 
@@ -1038,19 +1072,20 @@ int launch_es_mean(fgs_ctx *c, const double *d_scores, int G, long long C, int e
   }
   const size_t smem = ((size_t)G + 2) * 8;
   if (smem <= (size_t)c->smem_optin && G <= 65534) {
-    int grid = c->num_sms;
-    if (grid > C) grid = (int)C;
+    const int grid = c->num_sms;
+    const int tail = (int)(C % grid);
+    const int tail_split = (tail && c->opt_tail_split) ? std::max(1, std::min(8, grid / tail)) : 1;
     FGS_TRY(ensure_set_blocks(c, G));
     if (es_kind == FGS_ES_MAXMEAN) {
       auto k = es_mean_smem_kernel<true>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k<<<grid, ESM_THREADS, smem, c->stream>>>(d_scores, G, C, c->set_info.p, c->set_idx16.p, c->S, abs_flag, d_es,
-                                                c->tie_list.p, c->tie_ctr.p, c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R);
+                                                c->tie_list.p, c->tie_ctr.p, c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R, tail_split);
     } else {
       auto k = es_mean_smem_kernel<false>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k<<<grid, ESM_THREADS, smem, c->stream>>>(d_scores, G, C, c->set_info.p, c->set_idx16.p, c->S, abs_flag, d_es,
-                                                c->tie_list.p, c->tie_ctr.p, c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R);
+                                                c->tie_list.p, c->tie_ctr.p, c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R, tail_split);
     }
   } else {  // column does not fit on chip: gather through L1/L2
     long long units = (long long)c->S * C;

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define FGS_ABI_VERSION 1
+#define FGS_ABI_VERSION 2
 
 #define FGS_OK 0
 #define FGS_ERR_ARG 1
@@ -39,6 +39,7 @@ extern "C" {
 #define FGS_ERR_STATE 5
 #define FGS_ERR_UNSUPPORTED 6
 #define FGS_ERR_CANCELLED 7 /* the progress callback asked to stop */
+#define FGS_ERR_COMM 8      /* NCCL missing or a collective failed */
 
 /* gene.score.fn built-ins: flexgsea_s2n (R/flexgsea.R:689-723),
  * flexgsea_lm (:647-676) */
@@ -173,6 +174,93 @@ int fgs_sig_finish(fgs_ctx *ctx, const double *nes, const long long *null_counts
                    const long long *glob, int n_sets, int abs_flag, double *fdr,
                    long long *fdr_counts, long long *glob_counts);
 
+/* ---- permutations sharded over GPUs (R/flexgsea.R:422-472, :314-321) ------ */
+/* flexgsea_perm_parallel hands blocks of permutations to foreach workers
+ * (%dopar%, :432-470) and flexgsea_calc_sig then sees the abind()-ed null.  Here
+ * GPU g of N takes the contiguous span [g*P/N, (g+1)*P/N) of the permutations
+ * (x, the gene sets and the observed ES are replicated; Philox streams are keyed
+ * by the global permutation id, so the null does not depend on N), and the one
+ * exchange step happens inside the library over NCCL (NVLink / NVSwitch):
+ *   - ncclAllGather of the per-set double-double null sums [S x 4], combined in
+ *     rank order on every rank => the NES means are bit-identical for any N;
+ *   - ncclAllReduce (int64) of the p-value counts [S x 6];
+ *   - ncclAllReduce (int64) of the pooled-FDR exceedance counts [S + 2] -- the
+ *     exact equivalent of all-gathering the null NES (calc_fdr_nes :500-533
+ *     only counts), S*8 bytes instead of S*P*8;
+ *   - fgs_comm_allgather_null: the null itself, device to device, when the
+ *     caller wants es_null back (return_values) or asks for the exchange
+ *     north_star names (exchange = 1 below).
+ * NCCL is loaded at run time (libnccl.so.2); single-GPU use does not need it.
+ *
+ * Two ways in.  (1) One process per GPU (torchrun, MPI, ...): rank 0 makes an id,
+ * the host program carries its FGS_COMM_ID_BYTES bytes to the other ranks by any
+ * means, every rank calls fgs_comm_init on its own context. */
+#define FGS_COMM_ID_BYTES 128
+int fgs_comm_unique_id(char *id /* [FGS_COMM_ID_BYTES] */);
+int fgs_comm_init(fgs_ctx *ctx, const char *id, int n_ranks, int rank);
+int fgs_comm_destroy(fgs_ctx *ctx);
+/* n_ranks = 1, rank = 0 when no communicator is attached */
+int fgs_comm_info(fgs_ctx *ctx, int *n_ranks, int *rank);
+/* the span of n_perm permutations rank `rank` of `n_ranks` takes: [*lo, *hi) */
+int fgs_shard_span(long long n_perm, int n_ranks, int rank, long long *lo, long long *hi);
+/* flexgsea_calc_sig over the sharded null: same arguments and outputs as
+ * fgs_calc_sig, every rank receives the full result.  n_perm_total = P over all
+ * ranks.  exchange = 0: counts (default); 1: all-gather the null shards first
+ * (fgs_comm_allgather_null) and let every rank compute the whole significance
+ * locally.  Without a communicator it is fgs_calc_sig. */
+int fgs_calc_sig_sharded(fgs_ctx *ctx, const double *es, int response, int split_p,
+                         int calc_nes, int abs_flag, long long n_perm_total, int exchange,
+                         double *p, double *p_high, double *p_low, double *nes, double *fdr,
+                         double *fwer, long long *p_counts, long long *fdr_counts,
+                         long long *glob_counts);
+/* All-gather the resident null shards (rank r holds fgs_shard_span(n_perm_total,
+ * n_ranks, r)) device to device; afterwards every rank's resident null is the
+ * full [S, R, n_perm_total].  es_null_out (host, optional) receives a copy. */
+int fgs_comm_allgather_null(fgs_ctx *ctx, long long n_perm_total, double *es_null_out);
+/* device time (ms) of the most recent significance call on this context: [0] the
+ * whole call, [1] the NCCL collectives inside it (includes waiting for the slowest
+ * rank), [2] from the start of the most recent null loop to the end of this call
+ * (one "step" on the device timeline, host gaps included), [3] collectives issued */
+int fgs_last_sig_timings(fgs_ctx *ctx, float *ms /* [4] */);
+
+/* (2) One process, several GPUs -- what flexgsea(parallel = N) binds from R: a
+ * group owns one context per device, a communicator made with ncclCommInitAll
+ * and fans every call out over one host thread per GPU.  Uploads are replicated;
+ * the observed pass runs on every GPU (S*R units) so that each holds the
+ * observed ES for the near-tie hand-over of the null loop; the null loop takes
+ * the whole permutation range (perm: the full [n_sample x n_perm] matrix or
+ * NULL for Philox; es_null_out: the full [S, R, n_perm] host array or NULL, each
+ * GPU writes its span); significance is fgs_calc_sig_sharded on every rank,
+ * outputs from rank 0.  Arguments are those of the single-context functions. */
+typedef struct fgs_group fgs_group;
+int fgs_group_create(int n_gpu, const int *devices /* NULL: 0 .. n_gpu-1 */, fgs_group **out);
+int fgs_group_destroy(fgs_group *g);
+int fgs_group_size(const fgs_group *g);
+fgs_ctx *fgs_group_ctx(fgs_group *g, int rank);
+int fgs_group_set_x(fgs_group *g, const double *x, int n_sample, int n_gene);
+int fgs_group_set_gene_sets(fgs_group *g, const int *offsets, const int *index, int n_sets);
+int fgs_group_set_response_s2n(fgs_group *g, const int *y_bin, int n_sample, int n_response);
+int fgs_group_set_response_lm(fgs_group *g, const double *design, int n_sample, int n_col,
+                              int has_intercept);
+int fgs_group_set_option(fgs_group *g, const char *name, long long value);
+int fgs_group_score_observed(fgs_group *g, int score_kind, int abs_flag, double *scores);
+int fgs_group_observed_es(fgs_group *g, int es_kind, double p_exponent, const double *scores,
+                          int n_gene, int n_response, double *es, double *max_es_at,
+                          double *le_prop, int *running_es_at, double *running_es_pos,
+                          double *running_es_neg, int *le_first, int *le_count);
+int fgs_group_perm_null(fgs_group *g, int score_kind, int es_kind, double p_exponent,
+                        int abs_flag, const int *perm, unsigned long long seed, int n_perm,
+                        double *es_null_out);
+int fgs_group_es_from_scores(fgs_group *g, int es_kind, double p_exponent, const double *scores,
+                             int n_gene, int n_response, int n_perm, double *es_out);
+int fgs_group_calc_sig(fgs_group *g, const double *es, int response, int split_p, int calc_nes,
+                       int abs_flag, int exchange, double *p, double *p_high, double *p_low,
+                       double *nes, double *fdr, double *fwer, long long *p_counts,
+                       long long *fdr_counts, long long *glob_counts);
+/* max over the group's GPUs of fgs_last_timings()[4] (null loop) and of
+ * fgs_last_sig_timings(): ms[0] null loop, [1] significance, [2] collectives, [3] step */
+int fgs_group_last_timings(fgs_group *g, float *ms /* [4] */);
+
 /* ---- gene-set ingest (host only, no device work) ------------------------- */
 /* GMT text -> CSR of 1-based gene indices, done once and natively.  Replaces
  * read_gmt (R/flexgsea.R:966-973: name <tab> description <tab> gene ...),
@@ -224,7 +312,12 @@ int fgs_set_progress(fgs_ctx *ctx, fgs_progress_fn cb, void *user);
  * columns and the block-wise return of es.null through pinned memory; 0: plain
  * copies),
  * "es_exact_small" (1, default: problems that cost well under a millisecond that
- * way compute every weighted-KS unit in the reference's operation order) */
+ * way compute every weighted-KS unit in the reference's operation order),
+ * "nperm_total" (0, default: this call's n_perm; a caller that shards the
+ * permutations over contexts sets the total, so that routing decisions such as
+ * es_exact_small do not depend on the shard -- the groups do it themselves),
+ * "tail_split" (1, default: the ES kernels split the columns of a partial last
+ * round over the idle SMs) */
 int fgs_set_option(fgs_ctx *ctx, const char *name, long long value);
 
 #ifdef __cplusplus

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(fg._native.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.fgs_abi_version() == 1
+    assert lib.fgs_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():
@@ -166,6 +166,12 @@ r = sh.all_reduce_sum(np.arange(5, dtype=np.int64) * (sh.rank + 1))
 assert list(r) == [0, 3, 6, 9, 12]
 tot = sh.all_reduce_sum(np.array([hi - lo], dtype=np.int64))
 assert tot[0] == 101
+# the NCCL unique id of the library's communicator travels from rank 0 like this
+b = sh.broadcast_bytes(bytes(range(128)) if sh.rank == 0 else b"", 128)
+assert b == bytes(range(128))
+seeds = sh.all_gather(np.array([sh.random_seed()], dtype=np.int64))
+assert seeds[0, 0] == seeds[1, 0] and seeds[0, 0] >= 0                      # one seed for all ranks
+assert nat.shard_span(101, 2, sh.rank) == (lo, hi)                          # library and host agree on the spans
 dist.destroy_process_group()
 print("ok")
 '''

@@ -1,0 +1,155 @@
+"""Permutations sharded over GPUs, on real NCCL: the result of
+N = 2 must equal N = 1 bit for bit -- the null (Philox keyed by the global permutation id, or a
+shared permutation matrix), p, NES, FDR and every count.  Needs two GPUs (skipped otherwise; run
+with `gpurun --gpus 2`).  Replaces flexgsea_perm_parallel + sig.fun on the abind()-ed null
+(R/flexgsea.R:422-472, :314-321)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import flexgsea_r_b200 as fg
+from flexgsea_r_b200 import _native as nat, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _need(n):
+    if nat.device_count() < n:
+        pytest.skip("needs %d GPUs" % n)
+
+
+def _problem(seed=0, G=2500, n=30, S=400, P=203):
+    off, idx = synth.gene_sets_csr(G, S, (10, 300), "loguniform", seed=seed + 1)
+    x, y = synth.two_class(G, n, off, idx, seed=seed + 2)
+    perm = synth.perm_matrix(n, P, seed=seed + 4)
+    return x, y, perm, off, idx
+
+
+SIG_KEYS = ("p", "nes", "fdr", "fwer", "p_counts", "fdr_counts", "glob_counts")
+
+
+def _same_sig(a, b):
+    for k in SIG_KEYS:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("es_kind", [nat.ES_WEIGHTED_KS, nat.ES_MAXMEAN])
+@pytest.mark.parametrize("philox", [False, True])
+def test_group_of_two_equals_single_gpu(es_kind, philox):
+    _need(2)
+    x, y, perm, off, idx = _problem()
+    P = perm.shape[1]
+    one = fg.Context(0)
+    one.set_x(x); one.set_gene_sets(off, idx); one.set_response_s2n(y)
+    sc = one.score_observed(nat.SCORE_S2N)
+    obs = one.observed_es(es_kind, sc, ragged=False)
+    null1 = one.perm_null(nat.SCORE_S2N, es_kind, P, perm=None if philox else perm, seed=77)
+    sig1 = one.calc_sig(obs["es"][:, 0])
+    simple1 = one.calc_sig(obs["es"][:, 0], 0, False, False)
+
+    grp = nat.Group(2)
+    try:
+        assert grp.size == 2
+        grp.set_x(x); grp.set_gene_sets(off, idx); grp.set_response_s2n(y)
+        sc2 = grp.score_observed(nat.SCORE_S2N)
+        assert np.array_equal(sc, sc2)
+        obs2 = grp.observed_es(es_kind, sc2, ragged=False)
+        assert np.array_equal(obs["es"], obs2["es"])
+        null2 = grp.perm_null(nat.SCORE_S2N, es_kind, P, perm=None if philox else perm, seed=77)
+        assert np.array_equal(null1, null2, equal_nan=True)
+        # each GPU holds its span only
+        assert [c.null_device_ptr()[3] for c in grp.ctx] == [P // 2, P - P // 2]
+        sig2 = grp.calc_sig(obs2["es"][:, 0])
+        _same_sig(sig1, sig2)
+        t = grp.last_timings()
+        assert t["collectives"] > 0 and t["sig"] >= t["collectives"]
+        simple2 = grp.calc_sig(obs2["es"][:, 0], 0, False, False)
+        for k in ("p", "p_high", "p_low", "fdr", "fwer", "p_counts"):
+            assert np.array_equal(simple1[k], simple2[k], equal_nan=True), k
+        # the exchange north_star names: all-gather of the null, every rank computes locally
+        sig3 = grp.calc_sig(obs2["es"][:, 0], exchange=1)
+        _same_sig(sig1, sig3)
+        assert [c.null_device_ptr()[3] for c in grp.ctx] == [P, P]
+    finally:
+        grp.close()
+        one.close()
+
+
+def test_flexgsea_parallel_two_equals_one():
+    """the R-API mirror: flexgsea(parallel = 2) in one process == flexgsea() on one GPU"""
+    _need(2)
+    G, n, S = 1500, 24, 120
+    off, idx = synth.gene_sets_csr(G, S, (10, 120), "loguniform", seed=5)
+    x, y = synth.two_class(G, n, off, idx, seed=6)
+    names = ["g%d" % i for i in range(G)]
+    sets = {"s%d" % k: [names[i - 1] for i in idx[off[k]:off[k + 1]]] for k in range(S)}
+    kw = dict(gene_names=names, nperm=301, gs_size_min=1, gs_size_max=500, verbose=False, seed=9,
+              return_values=["es_null"])
+    a = fg.flexgsea(x, y[:, 0], sets, **kw)
+    b = fg.flexgsea(x, y[:, 0], sets, parallel=2, **kw)
+    ta, tb = a["table"]["Response 1"], b["table"]["Response 1"]
+    for col in ("es", "p", "nes", "fdr", "fwer", "max_es_at", "le_prop"):
+        assert np.array_equal(np.asarray(ta[col]), np.asarray(tb[col]), equal_nan=True), col
+    assert np.array_equal(a["es_null"], b["es_null"], equal_nan=True)
+
+
+_WORKER = r'''
+import os, sys, time, numpy as np
+sys.path.insert(0, %(root)r)
+rank, world, tmp = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+import flexgsea_r_b200 as fg
+from flexgsea_r_b200 import _native as nat, synth
+sys.path.insert(0, os.path.join(%(root)r, "tests"))
+from test_multi_gpu import _problem, SIG_KEYS
+x, y, perm, off, idx = _problem(seed=3, P=517)
+P = perm.shape[1]
+ctx = fg.Context(rank)
+idf = os.path.join(tmp, "nccl_id")
+if rank == 0:
+    open(idf + ".tmp", "wb").write(nat.comm_unique_id()); os.rename(idf + ".tmp", idf)
+while not os.path.exists(idf):
+    time.sleep(0.05)
+ctx.comm_init(open(idf, "rb").read(), world, rank)
+assert ctx.comm_info() == (world, rank)
+ctx.set_option("nperm_total", P)
+ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+sc = ctx.score_observed(nat.SCORE_S2N)
+es = ctx.observed_es(nat.ES_WEIGHTED_KS, sc, ragged=False)["es"][:, 0]
+lo, hi = nat.shard_span(P, world, rank)
+mine = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, hi - lo, perm=perm[:, lo:hi], perm_id0=lo)
+sig = ctx.calc_sig_sharded(es, P)
+assert ctx.last_sig_timings()["n_collectives"] == 2
+full = ctx.allgather_null(P)
+assert np.array_equal(full[:, :, lo:hi], mine, equal_nan=True)
+np.savez(os.path.join(tmp, "r%%d.npz" %% rank), full=full, **{k: sig[k] for k in SIG_KEYS})
+ctx.comm_destroy()
+print("ok", rank)
+'''
+
+
+def test_one_process_per_gpu_comm_equals_single_gpu(tmp_path):
+    """fgs_comm_unique_id / fgs_comm_init (one process per GPU, the id carried through a file
+    -- no torch involved), fgs_calc_sig_sharded and fgs_comm_allgather_null against one GPU."""
+    _need(2)
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER % {"root": ROOT})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), "2", str(tmp_path)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    x, y, perm, off, idx = _problem(seed=3, P=517)
+    one = fg.Context(0)
+    one.set_x(x); one.set_gene_sets(off, idx); one.set_response_s2n(y)
+    es = one.observed_es(nat.ES_WEIGHTED_KS, one.score_observed(nat.SCORE_S2N), ragged=False)["es"][:, 0]
+    null = one.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, perm.shape[1], perm=perm)
+    sig = one.calc_sig(es)
+    one.close()
+    for r in range(2):
+        got = np.load(os.path.join(tmp_path, "r%d.npz" % r))
+        assert np.array_equal(got["full"], null, equal_nan=True)
+        for k in SIG_KEYS:
+            assert np.array_equal(got[k], sig[k], equal_nan=True), (r, k)
