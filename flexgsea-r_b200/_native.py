@@ -26,7 +26,7 @@ SYMBOLS = [
     "fgs_n_response", "fgs_score_observed", "fgs_observed_es", "fgs_set_observed_es", "fgs_perm_null",
     "fgs_es_from_scores", "fgs_debug_last_scores", "fgs_null_device_ptr", "fgs_set_null",
     "fgs_calc_sig", "fgs_sig_stage1", "fgs_sig_stage2", "fgs_sig_finish", "fgs_launch_count",
-    "fgs_last_timings", "fgs_set_profiling", "fgs_set_option", "fgs_set_progress",
+    "fgs_last_timings", "fgs_set_profiling", "fgs_set_option", "fgs_get_stat", "fgs_set_progress",
     "fgs_gmt_parse", "fgs_gmt_read", "fgs_gmt_n_sets", "fgs_gmt_nnz", "fgs_gmt_offsets", "fgs_gmt_index",
     "fgs_gmt_set_name", "fgs_gmt_stats", "fgs_gmt_free",
     "fgs_comm_unique_id", "fgs_comm_init", "fgs_comm_destroy", "fgs_comm_info", "fgs_shard_span",
@@ -407,6 +407,11 @@ class Context:
 
     def set_option(self, name, value):
         self._check(self._lib.fgs_set_option(self._h, name.encode(), C.c_longlong(int(value))))
+
+    def get_stat(self, name):
+        v = C.c_longlong(0)
+        self._check(self._lib.fgs_get_stat(self._h, name.encode(), C.byref(v)))
+        return v.value
 
 
 class Group:

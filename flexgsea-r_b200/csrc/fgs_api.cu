@@ -10,6 +10,7 @@
 #include <cstring>
 #include <climits>
 #include <thread>
+#include <unordered_map>
 
 #include "fgs_common.cuh"
 
@@ -318,6 +319,35 @@ static bool small_problem(const fgs_ctx *c, int es_kind, long long C) {
   return es_kind == FGS_ES_WEIGHTED_KS ? small_wks_problem(c, C) : small_mean_problem(c, C);
 }
 
+// Few samples: a permutation only matters through the class labels it gives every response, and
+// there are at most prod_r n! / (n1_r! n2_r! nNA_r!) distinct labellings -- 6 for 2 + 2 samples,
+// 20 for 3 + 3, 924 for 6 + 6.  When that is well below the number of permutations, each distinct
+// labelling is computed ONCE and its column copied to the permutations that share it
+// (fgs_perm_null).  Faster, and permutations that repeat a labelling get identical values by
+// construction -- what the `<=` / `>=` / `>` counts of flexgsea_calc_sig and calc_fdr_nes
+// (R/flexgsea.R:578-587, :500-533) see in the reference, which runs the same code on the same data.
+static double distinct_labellings(const fgs_ctx *c) {
+  if (c->s2n_n <= 0 || c->s2n_n > 32 || c->h_n1n2.empty()) return INFINITY;
+  double prod = 1.0;
+  for (int r = 0; r < c->s2n_R; r++) {
+    const int n1 = c->h_n1n2[2 * r], n2 = c->h_n1n2[2 * r + 1], n = c->s2n_n;
+    double m = 1.0;  // n! / (n1! n2! (n - n1 - n2)!) = C(n, n1) * C(n - n1, n2)
+    for (int i = 1; i <= n1; i++) m = m * (double)(n - n1 + i) / (double)i;
+    for (int i = 1; i <= n2; i++) m = m * (double)(n - n1 - n2 + i) / (double)i;
+    prod *= m;
+    if (prod > 1e15) return INFINITY;
+  }
+  return prod;
+}
+// With the labellings deduplicated the all-exact path (every unit in the reference's operation
+// order) is affordable for far larger problems: budget ~2e10 warp instructions (tens of ms).
+static bool small_problem_dedup(const fgs_ctx *c, int es_kind, double columns) {
+  if (!c->opt_exact_small) return false;
+  const double cost = es_kind == FGS_ES_WEIGHTED_KS ? c->sum_m2 * columns * (25.0 / 32.0)
+                                                    : (double)c->nnz * columns * (10.0 / 32.0);
+  return cost <= 2e10;
+}
+
 // rank + ES of the score columns currently in c->scores
 static int rank_and_es(fgs_ctx *c, int es_kind, double p_exp, int abs_flag, long long Cb,
                        double *d_es, StageTimer &tm) {
@@ -334,12 +364,22 @@ static int rank_and_es(fgs_ctx *c, int es_kind, double p_exp, int abs_flag, long
       tc.list = c->cert_list.p + c->opt_cert_cap; tc.count = c->cert_ctr.p + 1; tc.cap = c->opt_cert_cap;
       FGS_TRY(c->cert_redo.ensure((size_t)Cb + 8));
       FGS_CUDA(cudaMemsetAsync(c->cert_redo.p, 0, (size_t)Cb * sizeof(int), c->stream));
-      tc.redo = c->cert_redo.p; tc.overflow = c->flags.p + (c->flags.n - 1);
+      tc.redo = c->cert_redo.p; tc.overflow = c->cur_ovf + 1;
       tc.rel_tol = 1e-10; tc.abs_tol = 1e-12;  // >= 50x the contraction-vs-reference error bound (k_s2n_mma.cu)
+      tc.dup = c->has_dups ? c->dupclass.p : nullptr;
       FGS_TRY(launch_sort(c, c->scores.p, G, Cb, abs_flag, p_exp, c->rank16.p, c->sabs.p, nullptr, &tc));
       FGS_TRY(launch_s2n_exact_entries(c, c->x.p, c->n, G, c->cur_labels, c->n1n2.p, c->s2n_R, tc.list,
                                        tc.count, c->opt_cert_cap, c->scores.p, c->flags.p + c->cur_flag0,
-                                       /*after_patch=*/true));
+                                       /*after_patch=*/true, c->cur_ovf + 1));
+      // More near-tied pairs than the list holds (thousands of duplicated genes, heavily tied
+      // data): THIS BLOCK's scores are recomputed with the bit-faithful kernel and every column
+      // of it ranked again -- queued behind the device flag, no host round trip, and the other
+      // blocks keep the tensor-core path.  (Not needed when the epilogue list already overflowed:
+      // the block was recomputed before the first ranking.)
+      FGS_TRY(launch_s2n(c, c->x.p, c->n, G, c->cur_labels, c->n1n2.p, c->s2n_R, Cb, c->scores.p,
+                         c->flags.p + c->cur_flag0, c->cur_ovf + 1, c->cur_ovf));
+      FGS_TRY(launch_s2n_patch(c, c->scores.p, G, c->s2n_R, c->cur_P, c->flags.p + c->cur_flag0));
+      FGS_TRY(launch_mark_all_if(c, c->cert_redo.p, Cb, c->cur_ovf + 1, c->cur_ovf));
       FGS_TRY(launch_sort(c, c->scores.p, G, Cb, abs_flag, p_exp, c->rank16.p, c->sabs.p, c->cert_redo.p,
                           nullptr));
     } else {
@@ -468,7 +508,7 @@ int fgs_destroy(fgs_ctx *c) {
     for (int i = 0; i < 16; i++) if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
   }
   for (int i = 0; i < 8; i++) if (c->sig_ev[i]) cudaEventDestroy(c->sig_ev[i]);
-  c->null_full.release();
+  c->null_full.release(); c->class_lists.release(); c->blk_ovf.release(); c->perm_map.release(); c->es_uniq.release(); c->dupclass.release(); c->sig_t.release();
   cudaStreamDestroy(c->stream);
   delete c;
   return FGS_OK;
@@ -523,9 +563,19 @@ int fgs_set_option(fgs_ctx *c, const char *name, long long value) {
   else if (!strcmp(name, "s2n_mode")) c->opt_s2n_mode = (int)value;
   else if (!strcmp(name, "es_exact_small")) c->opt_exact_small = (int)value;
   else if (!strcmp(name, "tail_split")) c->opt_tail_split = (int)value;
+  else if (!strcmp(name, "dedup_labels")) c->opt_dedup = (int)value;
   else if (!strcmp(name, "nperm_total")) c->opt_nperm_total = value > 0 ? value : 0;
   else if (!strcmp(name, "cert_cap")) c->opt_cert_cap = value > 2 ? (int)value : 2;
   else { set_error("unknown option '%s'", name); return FGS_ERR_ARG; }
+  return FGS_OK;
+}
+
+int fgs_get_stat(fgs_ctx *c, const char *name, long long *value) {
+  if (!c || !name || !value) return FGS_ERR_ARG;
+  if (!strcmp(name, "dedup_labellings")) *value = c->last_dedup;
+  else if (!strcmp(name, "fallback_blocks")) *value = c->last_fallback_blocks;
+  else if (!strcmp(name, "duplicated_rows")) *value = c->has_dups ? 1 : 0;
+  else { set_error("unknown stat '%s'", name); return FGS_ERR_ARG; }
   return FGS_OK;
 }
 
@@ -539,7 +589,40 @@ int fgs_set_x(fgs_ctx *c, const double *x, int n_sample, int n_gene) {
   c->obs_valid = false;
   c->gene_sd_valid = false;
   c->xc_valid = false;
-  FGS_TRY(sync(c));
+  // genes whose expression rows are bit-identical (duplicated probes): hashed on the device,
+  // confirmed here on the caller's array; see TieCert::dup
+  c->has_dups = false;
+  {
+    DevBuf<unsigned long long> &dh = c->sort_keys;   // scratch
+    FGS_TRY(dh.ensure((size_t)n_gene));
+    FGS_TRY(launch_row_hash(c, c->x.p, n_sample, n_gene, dh.p));
+    std::vector<unsigned long long> h((size_t)n_gene);
+    FGS_CUDA(cudaMemcpyAsync(h.data(), dh.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    FGS_TRY(sync(c));
+    std::vector<int> order((size_t)n_gene), dup((size_t)n_gene);
+    for (int g = 0; g < n_gene; g++) { order[g] = g; dup[g] = g; }
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return h[a] != h[b] ? h[a] < h[b] : a < b; });
+    const size_t row = (size_t)n_sample * sizeof(double);
+    for (int i = 0; i < n_gene;) {
+      int j = i + 1;
+      while (j < n_gene && h[order[j]] == h[order[i]]) j++;
+      for (int a = i; a < j; a++) {            // (groups are almost always of size one)
+        if (dup[order[a]] != order[a]) continue;
+        for (int b = a + 1; b < j; b++)
+          if (dup[order[b]] == order[b] &&
+              !memcmp(x + (size_t)order[a] * n_sample, x + (size_t)order[b] * n_sample, row)) {
+            dup[order[b]] = order[a];
+            c->has_dups = true;
+          }
+      }
+      i = j;
+    }
+    if (c->has_dups) {
+      FGS_TRY(c->dupclass.ensure((size_t)n_gene));
+      FGS_TRY(h2d(c, c->dupclass.p, dup.data(), (size_t)n_gene));
+      FGS_TRY(sync(c));
+    }
+  }
   return FGS_OK;
 }
 
@@ -642,6 +725,8 @@ int fgs_set_response_s2n(fgs_ctx *c, const int *y_bin, int n_sample, int n_respo
   FGS_TRY(h2d(c, c->ybin.p, y_bin, (size_t)n_sample * n_response));
   FGS_TRY(h2d(c, c->n1n2.p, nn.data(), nn.size()));
   FGS_TRY(sync(c));
+  c->h_n1n2 = nn;
+  c->s2n_n = n_sample;
   c->s2n_R = n_response;
   c->obs_valid = false;
   c->s2n_has_na = c->s2n_has_na_pending;
@@ -699,12 +784,17 @@ static int score_block(fgs_ctx *c, int score_kind, const int *d_perm, const uint
       FGS_TRY(c->cert_ctr.ensure(4));
       FGS_CUDA(cudaMemsetAsync(c->cert_ctr.p, 0, 4 * sizeof(int), c->stream));
       FGS_TRY(launch_s2n_mma(c, c->xc.p, c->xtot.p, n, G, d_labels, c->n1n2.p, R, Cb, c->scores.p,
-                             c->cert_list.p, c->cert_ctr.p, c->opt_cert_cap));
+                             c->cert_list.p, c->cert_ctr.p, c->opt_cert_cap, c->cur_ovf));
       FGS_TRY(launch_s2n_exact_entries(c, c->x.p, n, G, d_labels, c->n1n2.p, R, c->cert_list.p,
-                                       c->cert_ctr.p, c->opt_cert_cap, c->scores.p, c->flags.p + flag0));
+                                       c->cert_ctr.p, c->opt_cert_cap, c->scores.p, c->flags.p + flag0, false,
+                                       c->cur_ovf));
+      // epilogue list full (most entries cancelled: near-constant genes): the block is rescored bit-faithfully
+      FGS_TRY(launch_s2n(c, c->x.p, n, G, d_labels, c->n1n2.p, R, Cb, c->scores.p, c->flags.p + flag0, c->cur_ovf,
+                         nullptr));
       c->cur_cert = true;
       c->cur_labels = d_labels;
       c->cur_flag0 = flag0;
+      c->cur_P = P;
     } else {
       FGS_TRY(launch_s2n(c, c->x.p, n, G, d_labels, c->n1n2.p, R, Cb, c->scores.p, c->flags.p + flag0));
     }
@@ -804,8 +894,13 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
   c->null_exact_near_obs = c->cur_obs != nullptr;
   // (routing by the TOTAL permutation count when the caller shards: the same units take the same
   // path on one GPU and on eight)
-  c->cur_exact_all = score_kind == FGS_SCORE_S2N &&
-                     small_problem(c, es_kind, (long long)R * std::max<long long>(P, c->opt_nperm_total));
+  const long long P_total = std::max<long long>(P, c->opt_nperm_total);
+  c->cur_exact_all = score_kind == FGS_SCORE_S2N && small_problem(c, es_kind, (long long)R * P_total);
+  // tiny label space (see distinct_labellings): decided from the class sizes and the TOTAL
+  // permutation count, so every shard of a sharded null takes the same route
+  const double n_lab = (score_kind == FGS_SCORE_S2N && c->opt_dedup) ? distinct_labellings(c) : INFINITY;
+  const bool try_dedup = n_lab * 2.0 <= (double)P_total && P >= 2;
+  if (try_dedup && small_problem_dedup(c, es_kind, n_lab * R)) c->cur_exact_all = true;
   if (c->cur_exact_all) c->null_exact_near_obs = true;
   if (P == 0) return FGS_OK;
   FGS_TRY(flags_reset(c, P));
@@ -819,24 +914,62 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
   else FGS_TRY(launch_philox_perm(c, seed, perm_id0, n, P, c->perm.p));
   const int W = (n + 31) / 32;
   c->cur_ident = nullptr;
+  // Pe "effective permutations" computed below: all of them, or the distinct labellings only
+  int Pe = P;
+  double *es_e = c->es_null.p;
+  bool dedup = false;
   if (score_kind == FGS_SCORE_S2N) {
     FGS_TRY(c->labels.ensure((size_t)P * R * 2 * W));
     FGS_TRY(launch_labels(c, c->perm.p, c->ybin.p, n, R, P, c->labels.p));
+    if (try_dedup && W == 1) {
+      // the label masks are tiny (2 R words per permutation): group them on the host
+      const size_t key_words = (size_t)R * 2;
+      std::vector<uint32_t> h((size_t)P * key_words), hu;
+      FGS_CUDA(cudaMemcpyAsync(h.data(), c->labels.p, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+      FGS_TRY(sync(c));
+      std::unordered_map<std::string, int> seen;
+      std::vector<int> map(P);
+      for (int p = 0; p < P; p++) {
+        std::string key((const char *)&h[(size_t)p * key_words], key_words * sizeof(uint32_t));
+        auto it = seen.find(key);
+        if (it == seen.end()) {
+          it = seen.emplace(std::move(key), (int)seen.size()).first;
+          hu.insert(hu.end(), h.begin() + (size_t)p * key_words, h.begin() + (size_t)(p + 1) * key_words);
+        }
+        map[p] = it->second;
+      }
+      const int U = (int)seen.size();
+      if ((long long)U * 2 <= P) {
+        dedup = true;
+        Pe = U;
+        FGS_TRY(c->perm_map.ensure((size_t)P));
+        FGS_TRY(h2d(c, c->perm_map.p, map.data(), (size_t)P));
+        FGS_TRY(h2d(c, c->labels.p, hu.data(), hu.size()));   // the distinct labellings, in order of first use
+        FGS_TRY(c->es_uniq.ensure((size_t)S * R * U));
+        es_e = c->es_uniq.p;
+        FGS_TRY(sync(c));  // (map / hu are host temporaries)
+      }
+    }
     if (c->cur_obs) {  // label-preserving permutations get the observed ES as it is
       FGS_TRY(c->obs_labels.ensure((size_t)R * 2 * W));
-      FGS_TRY(c->ident.ensure((size_t)P));
+      FGS_TRY(c->ident.ensure((size_t)Pe));
       FGS_TRY(launch_labels(c, nullptr, c->ybin.p, n, R, 1, c->obs_labels.p));
-      FGS_TRY(launch_label_identity(c, c->labels.p, c->obs_labels.p, R, W, P, c->ident.p));
+      FGS_TRY(launch_label_identity(c, c->labels.p, c->obs_labels.p, R, W, Pe, c->ident.p));
     }
   }
+  c->last_dedup = dedup ? Pe : 0;
   c->last_launches[0] = c->launches - l0;
   float pro_ms = 0;
   if (c->profiling) { cudaEventRecord(e1, c->stream); }
   StageTimer tm(c);
-  const long long Cb_max = block_columns(c, (long long)P * R);
+  const long long Cb_max = block_columns(c, (long long)Pe * R);
   const int Pb_max = (int)std::max<long long>(1, Cb_max / R);
-  for (int p0 = 0; p0 < P; p0 += Pb_max) {
-    const int Pb = std::min(Pb_max, P - p0);
+  const int n_blk = (Pe + Pb_max - 1) / Pb_max;
+  FGS_TRY(c->blk_ovf.ensure((size_t)2 * n_blk + 2));
+  FGS_CUDA(cudaMemsetAsync(c->blk_ovf.p, 0, ((size_t)2 * n_blk + 2) * sizeof(int), c->stream));
+  for (int p0 = 0; p0 < Pe; p0 += Pb_max) {
+    const int Pb = std::min(Pb_max, Pe - p0);
+    c->cur_ovf = c->blk_ovf.p + 2 * (size_t)(p0 / Pb_max);
     tm.mark();
     l0 = c->launches;
     FGS_TRY(score_block(c, score_kind, c->perm.p + (size_t)p0 * n,
@@ -844,16 +977,14 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
     c->last_launches[1] += c->launches - l0;
     tm.mark();
     c->cur_ident = (c->cur_obs && score_kind == FGS_SCORE_S2N) ? c->ident.p + p0 : nullptr;
-    FGS_TRY(rank_and_es(c, es_kind, p_exp, abs_flag, (long long)Pb * R,
-                        c->es_null.p + (size_t)p0 * R * S, tm));
+    FGS_TRY(rank_and_es(c, es_kind, p_exp, abs_flag, (long long)Pb * R, es_e + (size_t)p0 * R * S, tm));
     if (c->cur_ident)
-      FGS_TRY(launch_copy_observed(c, c->cur_obs, c->cur_ident, R, (long long)Pb * R,
-                                   c->es_null.p + (size_t)p0 * R * S));
+      FGS_TRY(launch_copy_observed(c, c->cur_obs, c->cur_ident, R, (long long)Pb * R, es_e + (size_t)p0 * R * S));
     if (c->progress) {
-      const int prc = block_progress(c, p0 / Pb_max, (long long)Pb_max * R, (long long)P * R);
+      const int prc = block_progress(c, p0 / Pb_max, (long long)Pb_max * R, (long long)Pe * R);
       if (prc != FGS_OK) { c->cur_ident = nullptr; c->cur_exact_all = false; return prc; }
     }
-    if (es_null_out) {
+    if (es_null_out && !dedup) {
       // es.null goes back block by block: block k-1 leaves (pinned staging ring, several host
       // threads) while block k, already queued, is computed
       const int k = p0 / Pb_max;
@@ -870,8 +1001,19 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
   }
   c->cur_ident = nullptr;
   c->cur_exact_all = false;
+  if (dedup) {  // every permutation takes the column of its labelling
+    FGS_TRY(launch_scatter_null(c, c->es_uniq.p, c->perm_map.p, (long long)S * R, P, c->es_null.p));
+    if (es_null_out) {
+      FGS_CUDA(cudaEventRecord(c->blk_out[0], c->stream));
+      FGS_TRY(download_block(c, 0, es_null_out, c->es_null.p, (size_t)S * R * P));
+    }
+  }
   FGS_CUDA(cudaEventRecord(c->ev[1], c->stream));
-  int rc = flags_check(c, P);
+  std::vector<int> h_ovf((size_t)2 * n_blk);
+  FGS_CUDA(cudaMemcpyAsync(h_ovf.data(), c->blk_ovf.p, h_ovf.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  int rc = flags_check(c, Pe);  // (synchronises)
+  c->last_fallback_blocks = 0;
+  for (int k = 0; k < n_blk; k++) c->last_fallback_blocks += (h_ovf[2 * k] || h_ovf[2 * k + 1]) ? 1 : 0;
   if (c->profiling) {
     cudaEventSynchronize(e1);
     cudaEventElapsedTime(&pro_ms, e0, e1);

@@ -55,6 +55,10 @@ struct TieCert {
   int *redo = nullptr;    // [C] columns to rank again
   int *overflow = nullptr;  // bit 16 raised when the list is full
   double rel_tol = 0, abs_tol = 0;
+  // dup[g] = first gene whose expression row is bit-identical to gene g's (NULL: no duplicated
+  // rows).  Such genes score identically in the reference AND here, whatever the arithmetic, so
+  // an exact tie between them needs no recomputation: index order decides in both.
+  const int *dup = nullptr;
 };
 
 // error bits accumulated on the device during a run
@@ -108,6 +112,8 @@ struct fgs_ctx {
   fgs::DevBuf<int> cert_redo;   // [Cb]
   fgs::DevBuf<uint16_t> sort_glist;  // [grid][Gp] gene lists of the score-range buckets (long columns)
   fgs::DevBuf<int> sort_redo;   // [Cb] columns the 32-bit sort hands to the 64-bit sort
+  fgs::DevBuf<int> dupclass;    // [G] first gene with a bit-identical expression row (see TieCert::dup)
+  bool has_dups = false;
   fgs::DevBuf<double> gene_sd;  // sd(x[,g]) for lm
   bool gene_sd_valid = false;
 
@@ -152,6 +158,8 @@ struct fgs_ctx {
   int s2n_R = 0;
   bool s2n_has_na = false, s2n_has_na_pending = false;  // NA_LOGICAL present in y_bin
   bool cur_cert = false;            // scores of the current block came from the tensor-core path
+  int *cur_ovf = nullptr;           // this block's two overflow flags (epilogue list, tie list) in blk_ovf
+  int cur_P = 0;                    // permutations of the current block
   const uint32_t *cur_labels = nullptr;
   long long cur_flag0 = 0;
   fgs::DevBuf<int> ybin;
@@ -164,6 +172,13 @@ struct fgs_ctx {
   // permutation machinery
   fgs::DevBuf<int> perm;          // [n x Pb] 1-based
   fgs::DevBuf<uint32_t> labels;   // [Pb*R][2][W]
+  fgs::DevBuf<uint16_t> class_lists;  // [Cb][n] samples of class 1 then class 2 per column (bit-faithful s2n)
+  fgs::DevBuf<int> perm_map;      // [P] permutation -> distinct labelling (few samples: fgs_perm_null)
+  fgs::DevBuf<double> es_uniq;    // [S, R, U] ES of the distinct labellings
+  int opt_dedup = 1, last_dedup = 0, last_fallback_blocks = 0;
+  std::vector<int> h_n1n2;        // host copy of the class sizes [R][2]
+  int s2n_n = 0;
+  fgs::DevBuf<int> blk_ovf;       // [2 * blocks] certification-list overflow of a block (epilogue list, tie list)
   fgs::DevBuf<double> lm_B;       // [n x Cb] permuted design block
 
   // per-block scratch
@@ -188,6 +203,7 @@ struct fgs_ctx {
   fgs::DevBuf<double> api_d[5];    // grow-only scratch of the observed / significance entry points
   fgs::DevBuf<int> api_i[3];
   fgs::DevBuf<long long> api_l;
+  fgs::DevBuf<double> sig_t;       // [n1 + n2] the two threshold lists as one ascending list
   fgs::DevBuf<int> sig_lut;        // coarse cell index over the sorted NES thresholds (pooled FDR)
 
   // permutations sharded over GPUs (fgs_multi.cu): NCCL communicator of this rank
@@ -208,8 +224,10 @@ int launch_philox_perm(fgs_ctx *c, unsigned long long seed, long long perm_id0, 
 int launch_labels(fgs_ctx *c, const int *d_perm, const int *d_ybin, int n, int R, int P,
                   uint32_t *d_labels);
 // K2'
+// only_if / unless: device flags that make the launch conditional (block-level fallback of the tensor path)
 int launch_s2n(fgs_ctx *c, const double *d_x, int n, int G, const uint32_t *d_labels,
-               const int *d_n1n2, int R, long long C, double *d_scores, int *d_flags);
+               const int *d_n1n2, int R, long long C, double *d_scores, int *d_flags,
+               const int *only_if = nullptr, const int *unless = nullptr);
 int launch_s2n_patch(fgs_ctx *c, double *d_scores, int G, int R, int P, int *d_flags);
 // K2 (lm)
 int launch_lm_build_B(fgs_ctx *c, const double *d_H, const int *d_perm, int n, int R, int P,
@@ -217,6 +235,7 @@ int launch_lm_build_B(fgs_ctx *c, const double *d_H, const int *d_perm, int n, i
 int launch_lm_gemm(fgs_ctx *c, const double *d_x, int n, int G, const double *d_B, long long C,
                    const double *d_gene_sd, double *d_scores, int *d_flags, int R);
 int launch_gene_sd(fgs_ctx *c, const double *d_x, int n, int G, double *d_sd);
+int launch_row_hash(fgs_ctx *c, const double *d_x, int n, int G, unsigned long long *d_hash);
 // generic helpers
 int launch_check_finite(fgs_ctx *c, const double *d_v, long long len, long long per_flag,
                         int *d_flags);
@@ -228,14 +247,17 @@ int launch_sort(fgs_ctx *c, const double *d_scores, int G, long long C, int abs_
 int launch_center(fgs_ctx *c, const double *d_x, int n, int G, double *d_xc, double *d_tot);
 int launch_s2n_mma(fgs_ctx *c, const double *d_xc, const double *d_tot, int n, int G,
                    const uint32_t *d_labels, const int *d_n1n2, int R, long long C, double *d_scores,
-                   int2 *d_list, int *d_count, int cap);
+                   int2 *d_list, int *d_count, int cap, int *d_overflow);
+int launch_mark_all_if(fgs_ctx *c, int *d_redo, long long C, const int *only_if, const int *unless);
 int launch_s2n_exact_entries(fgs_ctx *c, const double *d_x, int n, int G, const uint32_t *d_labels,
                              const int *d_n1n2, int R, const int2 *d_list, const int *d_count, int cap,
-                             double *d_scores, int *d_flags, bool after_patch = false);
+                             double *d_scores, int *d_flags, bool after_patch = false,
+                             const int *unless = nullptr);
 // K4 / K5
 int launch_prep_sets(fgs_ctx *c, int S, int *h_status, unsigned char *h_slow);
 int launch_es_wks(fgs_ctx *c, const uint16_t *d_rank16, const double *d_sabs, int G, long long C,
                   double *d_es, bool defer_ties = false);
+int launch_scatter_null(fgs_ctx *c, const double *d_uniq, const int *d_map, long long unit, int P, double *d_null);
 int launch_copy_observed(fgs_ctx *c, const double *d_obs, const int *d_ident, int R, long long C,
                          double *d_es);
 int launch_label_identity(fgs_ctx *c, const uint32_t *d_labels, const uint32_t *d_obs, int R, int W, int P,

@@ -67,6 +67,27 @@ __global__ void gene_sd_kernel(const double *__restrict__ x, int n, int G, doubl
   for (int i = 0; i < n; i++) { double d = xg[i] - mean; dd_acc(h3, l3, d * d); }
   sd[g] = sqrt((h3 + l3) / (n - 1));
 }
+// 64-bit hash of every gene's expression row (bit pattern of its n doubles): groups candidate
+// duplicated rows for fgs_set_x, which confirms them on the host by comparing the rows
+__global__ void row_hash_kernel(const double *__restrict__ x, int n, int G, unsigned long long *__restrict__ hash) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const unsigned long long *row = (const unsigned long long *)(x + (size_t)g * n);
+  unsigned long long h = 0x9E3779B97F4A7C15ull;
+  for (int i = 0; i < n; i++) {
+    h ^= row[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xFF51AFD7ED558CCDull;
+    h ^= h >> 33;
+  }
+  hash[g] = h;
+}
+int launch_row_hash(fgs_ctx *c, const double *d_x, int n, int G, unsigned long long *d_hash) {
+  row_hash_kernel<<<ceil_div(G, 128), 128, 0, c->stream>>>(d_x, n, G, d_hash);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
+}
+
 int launch_gene_sd(fgs_ctx *c, const double *d_x, int n, int G, double *d_sd) {
   gene_sd_kernel<<<ceil_div(G, 128), 128, 0, c->stream>>>(d_x, n, G, d_sd);
   c->launches++;

@@ -5,6 +5,8 @@
 // (same RNG stream as the reference), or each permutation is drawn on the
 // device: Fisher-Yates driven by Philox4x32-10 keyed by (seed, global
 // permutation id), so results do not depend on how permutations are sharded.
+#include <algorithm>
+
 #include "fgs_common.cuh"
 
 namespace fgs {
@@ -101,6 +103,27 @@ int launch_label_identity(fgs_ctx *c, const uint32_t *d_labels, const uint32_t *
                           int *d_ident) {
   if (P <= 0) return FGS_OK;
   label_identity_kernel<<<ceil_div(P, 128), 128, 0, c->stream>>>(d_labels, d_obs, R, W, P, d_ident);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
+}
+
+// es_null[, , p] = es_uniq[, , map[p]]: every permutation takes the column of its labelling
+__global__ void scatter_null_kernel(const double *__restrict__ uniq, const int *__restrict__ map, long long unit,
+                                    double *__restrict__ null) {
+  const int p = blockIdx.y;
+  const double *src = uniq + (size_t)map[p] * unit;
+  double *dst = null + (size_t)p * unit;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < unit; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+int launch_scatter_null(fgs_ctx *c, const double *d_uniq, const int *d_map, long long unit, int P, double *d_null) {
+  if (P <= 0 || unit <= 0) return FGS_OK;
+  const int gx = (int)std::min<long long>(ceil_div(unit, 256), 64);
+  for (int p0 = 0; p0 < P; p0 += 65535) {  // grid.y limit
+    const int np = std::min(65535, P - p0);
+    scatter_null_kernel<<<dim3(gx, np), 256, 0, c->stream>>>(d_uniq, d_map + p0, unit, d_null + (size_t)p0 * unit);
+  }
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   return FGS_OK;

@@ -12,27 +12,67 @@
 //
 // Mapping: lane <-> gene (32 genes per CTA tile, transposed into shared memory
 // so a warp reads 32 consecutive doubles per sample), warp <-> PPT permutation
-// columns.  The class label of a sample is then warp-uniform, so the
-// class-conditional accumulation is a uniform predicate, and every x value
-// loaded from shared memory is reused by PPT columns.  FP64-pipe bound:
-// ~(n1 + 5n) double ops per (gene, column).
+// columns.  The reference walks the samples once per pass and picks the class
+// accumulator by a branch (:30-37, :46-53, :60-67); an accumulator therefore only
+// ever sees the samples of ITS class, in index order.  Here each column's samples
+// are first split into the two index lists (class 1 in index order, then class 2:
+// class_lists_kernel) and every pass runs one loop per class over its list -- the
+// same operation sequence per accumulator, hence the same bits, but no
+// class-conditional arithmetic at all.  (Written as `if (class1) s1 += d; else s2
+// += d` the compiler if-converts to "compute both, select": twice the FP64 work.
+// Round 1 measured that form at 47 ms per 10 000 columns at C2.)
+// FP64-pipe bound: n1 + 5n double operations per (gene, column); a visit costs one add for the
+// address (the lists hold ready-made offsets), one shared-memory load and its FP64 work.
 #include "fgs_common.cuh"
 
 namespace fgs {
 
 constexpr int S2N_THREADS = 256;
-constexpr int S2N_PPT = 4;
+constexpr int S2N_PPT = 2;
+
+// lists[col][0 .. n1) = samples of class 1 in index order, lists[col][n1 .. n1 + n2) = class 2
+// (NA samples are in neither mask and in neither list).  A warp per column.
+__global__ void __launch_bounds__(256)
+class_lists_kernel(const uint32_t *__restrict__ labels, int n, int W, long long C,
+                   uint16_t *__restrict__ lists, const int *__restrict__ only_if,
+                   const int *__restrict__ unless) {
+  if (only_if && *only_if == 0) return;
+  if (unless && *unless != 0) return;
+  const long long col = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (col >= C) return;
+  uint16_t *out = lists + (size_t)col * n;
+  int at = 0;
+  for (int cls = 0; cls < 2; cls++) {
+    const uint32_t *m = labels + ((size_t)col * 2 + cls) * W;
+    for (int wb = 0; wb < W; wb++) {
+      const uint32_t w = __ldg(m + wb);
+      if ((w >> lane) & 1u) out[at + __popc(w & ((1u << lane) - 1u))] = (uint16_t)(wb * 32 + lane);
+      at += __popc(w);
+    }
+  }
+}
 
 template <int PPT, bool SMEM_TILE>
 __global__ void __launch_bounds__(S2N_THREADS)
-s2n_kernel(const double *__restrict__ x, int n, int G, const uint32_t *__restrict__ labels,
-           const int *__restrict__ n1n2, int R, long long C, int W, long long cols_per_cta,
-           double *__restrict__ scores, int *__restrict__ flags) {
-  extern __shared__ double xs[];  // [n][32] when SMEM_TILE
+s2n_kernel(const double *__restrict__ x, int n, int G, const uint16_t *__restrict__ lists,
+           const int *__restrict__ n1n2, int R, long long C, long long cols_per_cta,
+           double *__restrict__ scores, int *__restrict__ flags, const int *__restrict__ only_if,
+           const int *__restrict__ unless) {
+  // a conditional launch: the block-level fallback of the tensor-core path (fgs_api.cu) queues
+  // this kernel behind a device flag and it leaves at once when the flag says "not needed"
+  if (only_if && *only_if == 0) return;
+  if (unless && *unless != 0) return;
+  extern __shared__ double xs[];  // [n][32] when SMEM_TILE, then the warps' sample lists
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = blockIdx.x * 32 + lane;
   const bool gvalid = g < G;
   const double *xg = x + (size_t)(gvalid ? g : 0) * n;
+  // per warp and column: the samples as ready-made offsets (bytes into the tile row of this
+  // lane's gene, or elements of xg), so that a visit is one add, one load and its FP64 work
+  // (each class's list starts on a 16-byte boundary: four offsets per shared-memory load)
+  const int npad = ((n + 3) & ~3) + 4;
+  uint32_t *sl = (uint32_t *)(xs + (SMEM_TILE ? (size_t)n * 32 : 0)) + (size_t)warp * PPT * npad;
   if (SMEM_TILE) {
     // lanes over genes: conflict-free shared stores; the strided global reads
     // hit L2 (x is resident there) and happen once per CTA
@@ -41,34 +81,57 @@ s2n_kernel(const double *__restrict__ x, int n, int G, const uint32_t *__restric
   }
   const long long cbeg = (long long)blockIdx.y * cols_per_cta;
   const long long cend = (cbeg + cols_per_cta < C) ? cbeg + cols_per_cta : C;
+  const char *xrow = (const char *)(xs + lane);
+  auto xat = [&](uint32_t o) -> double {
+    return SMEM_TILE ? *(const double *)(xrow + o) : __ldg(xg + o);
+  };
 
   for (long long c0 = cbeg + (long long)warp * PPT; c0 < cend; c0 += (long long)nwarps * PPT) {
     double s1[PPT], s2[PPT], mean1[PPT], mean2[PPT];
-    int n1[PPT], n2[PPT];
-    const uint32_t *lab[PPT];
+    int n1[PPT], n2[PPT], o2[PPT];
+    __syncwarp();
 #pragma unroll
     for (int q = 0; q < PPT; q++) {
-      long long col = (c0 + q < cend) ? c0 + q : c0;  // tail columns recompute c0, not stored
-      lab[q] = labels + (size_t)col * 2 * W;
-      int r = (int)(col % R);
+      const long long col = (c0 + q < cend) ? c0 + q : c0;  // tail columns recompute c0, not stored
+      const int r = (int)(col % R);
       n1[q] = n1n2[2 * r]; n2[q] = n1n2[2 * r + 1];
+      o2[q] = (n1[q] + 3) & ~3;
+      const uint16_t *src = lists + (size_t)col * n;
+      for (int i = lane; i < n1[q] + n2[q]; i += 32)
+        sl[q * npad + (i < n1[q] ? i : o2[q] + (i - n1[q]))] = SMEM_TILE ? (uint32_t)src[i] * 256u : (uint32_t)src[i];
       s1[q] = 0.0;
     }
-    // pass 1 (src/ggsea.cpp:28-38): only sum1 is consumed (mean2 = sum1 / n2, :40)
-    for (int wb = 0; wb < W; wb++) {
-      uint32_t m1[PPT];
-#pragma unroll
-      for (int q = 0; q < PPT; q++) m1[q] = __ldg(lab[q] + wb);
-      const int i0 = wb * 32, jn = (n - i0 < 32) ? n - i0 : 32;
-      for (int j = 0; j < jn; j++) {
-        double xv = SMEM_TILE ? xs[(i0 + j) * 32 + lane] : xg[i0 + j];
-#pragma unroll
-        for (int q = 0; q < PPT; q++) {
-          if (m1[q] & 1u) s1[q] = __dadd_rn(s1[q], xv);
-          m1[q] >>= 1;
-        }
-      }
+    __syncwarp();
+    // The columns of a warp advance together while both have samples left (two independent
+    // FP64 chains in flight), then each finishes on its own.  `OP` is the pass's update.
+#define S2N_SWEEP(ACC, MEAN, OFF, CNT, OP)                                                         \
+    {                                                                                              \
+      int kc = CNT[0];                                                                             \
+      _Pragma("unroll") for (int q = 1; q < PPT; q++) kc = min(kc, CNT[q]);                        \
+      kc &= ~3;                                                                                    \
+      for (int k = 0; k < kc; k += 4) {                                                            \
+        uint4 o4[PPT];                                                                             \
+        _Pragma("unroll") for (int q = 0; q < PPT; q++) o4[q] = *(const uint4 *)(sl + q * npad + OFF[q] + k); \
+        _Pragma("unroll") for (int q = 0; q < PPT; q++) { const double xv = xat(o4[q].x); OP(ACC[q], xv, MEAN[q]); } \
+        _Pragma("unroll") for (int q = 0; q < PPT; q++) { const double xv = xat(o4[q].y); OP(ACC[q], xv, MEAN[q]); } \
+        _Pragma("unroll") for (int q = 0; q < PPT; q++) { const double xv = xat(o4[q].z); OP(ACC[q], xv, MEAN[q]); } \
+        _Pragma("unroll") for (int q = 0; q < PPT; q++) { const double xv = xat(o4[q].w); OP(ACC[q], xv, MEAN[q]); } \
+      }                                                                                            \
+      _Pragma("unroll") for (int q = 0; q < PPT; q++) {                                            \
+        for (int k = kc; k < CNT[q]; k++) {                                                        \
+          const double xv = xat(sl[q * npad + OFF[q] + k]);                                        \
+          OP(ACC[q], xv, MEAN[q]);                                                                 \
+        }                                                                                          \
+      }                                                                                            \
     }
+#define S2N_OP_SUM(A, X, M) A = __dadd_rn(A, X)
+#define S2N_OP_DEV(A, X, M) A = __dadd_rn(A, __dsub_rn(X, M))
+#define S2N_OP_SQ(A, X, M) { const double d__ = __dsub_rn(X, M); A = __dadd_rn(A, __dmul_rn(d__, d__)); }
+    int zero[PPT];
+#pragma unroll
+    for (int q = 0; q < PPT; q++) zero[q] = 0;
+    // pass 1 (src/ggsea.cpp:28-38): only sum1 is consumed (mean2 = sum1 / n2, :40)
+    S2N_SWEEP(s1, mean1, zero, n1, S2N_OP_SUM)
 #pragma unroll
     for (int q = 0; q < PPT; q++) {
       mean1[q] = __ddiv_rn(s1[q], (double)n1[q]);
@@ -76,21 +139,8 @@ s2n_kernel(const double *__restrict__ x, int n, int G, const uint32_t *__restric
       s1[q] = 0.0; s2[q] = 0.0;
     }
     // pass 2 (:44-54)
-    for (int wb = 0; wb < W; wb++) {
-      uint32_t m1[PPT], m2[PPT];
-#pragma unroll
-      for (int q = 0; q < PPT; q++) { m1[q] = __ldg(lab[q] + wb); m2[q] = __ldg(lab[q] + W + wb); }
-      const int i0 = wb * 32, jn = (n - i0 < 32) ? n - i0 : 32;
-      for (int j = 0; j < jn; j++) {
-        double xv = SMEM_TILE ? xs[(i0 + j) * 32 + lane] : xg[i0 + j];
-#pragma unroll
-        for (int q = 0; q < PPT; q++) {
-          if (m1[q] & 1u) s1[q] = __dadd_rn(s1[q], __dsub_rn(xv, mean1[q]));
-          else if (m2[q] & 1u) s2[q] = __dadd_rn(s2[q], __dsub_rn(xv, mean2[q]));
-          m1[q] >>= 1; m2[q] >>= 1;
-        }
-      }
-    }
+    S2N_SWEEP(s1, mean1, zero, n1, S2N_OP_DEV)
+    S2N_SWEEP(s2, mean2, o2, n2, S2N_OP_DEV)
 #pragma unroll
     for (int q = 0; q < PPT; q++) {
       mean1[q] = __dadd_rn(mean1[q], __ddiv_rn(s1[q], (double)n1[q]));
@@ -98,21 +148,9 @@ s2n_kernel(const double *__restrict__ x, int n, int G, const uint32_t *__restric
       s1[q] = 0.0; s2[q] = 0.0;
     }
     // pass 3 (:58-68)
-    for (int wb = 0; wb < W; wb++) {
-      uint32_t m1[PPT], m2[PPT];
-#pragma unroll
-      for (int q = 0; q < PPT; q++) { m1[q] = __ldg(lab[q] + wb); m2[q] = __ldg(lab[q] + W + wb); }
-      const int i0 = wb * 32, jn = (n - i0 < 32) ? n - i0 : 32;
-      for (int j = 0; j < jn; j++) {
-        double xv = SMEM_TILE ? xs[(i0 + j) * 32 + lane] : xg[i0 + j];
-#pragma unroll
-        for (int q = 0; q < PPT; q++) {
-          if (m1[q] & 1u) { double m = __dsub_rn(xv, mean1[q]); s1[q] = __dadd_rn(s1[q], __dmul_rn(m, m)); }
-          else if (m2[q] & 1u) { double m = __dsub_rn(xv, mean2[q]); s2[q] = __dadd_rn(s2[q], __dmul_rn(m, m)); }
-          m1[q] >>= 1; m2[q] >>= 1;
-        }
-      }
-    }
+    S2N_SWEEP(s1, mean1, zero, n1, S2N_OP_SQ)
+    S2N_SWEEP(s2, mean2, o2, n2, S2N_OP_SQ)
+#undef S2N_SWEEP
 #pragma unroll
     for (int q = 0; q < PPT; q++) {
       if (c0 + q < cend && gvalid) {
@@ -131,13 +169,20 @@ s2n_kernel(const double *__restrict__ x, int n, int G, const uint32_t *__restric
 }
 
 int launch_s2n(fgs_ctx *c, const double *d_x, int n, int G, const uint32_t *d_labels,
-               const int *d_n1n2, int R, long long C, double *d_scores, int *d_flags) {
+               const int *d_n1n2, int R, long long C, double *d_scores, int *d_flags,
+               const int *only_if, const int *unless) {
   if (C <= 0 || G <= 0) return FGS_OK;
+  if (n > 65535) { set_error("more than 65535 samples"); return FGS_ERR_UNSUPPORTED; }
   const int W = (n + 31) / 32;
+  FGS_TRY(c->class_lists.ensure((size_t)C * n));
+  class_lists_kernel<<<ceil_div(C, 8), 256, 0, c->stream>>>(d_labels, n, W, C, c->class_lists.p, only_if, unless);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
   const int tiles = ceil_div(G, 32);
-  const size_t smem = (size_t)n * 32 * sizeof(double);
-  const bool tile_fits = smem <= (size_t)c->smem_optin;
   const int nwarps = S2N_THREADS / 32;
+  const size_t smem_lists = (size_t)nwarps * S2N_PPT * (((n + 3) & ~3) + 4) * sizeof(uint32_t);
+  const size_t smem = (size_t)n * 32 * sizeof(double) + smem_lists;
+  const bool tile_fits = smem <= (size_t)c->smem_optin;
   // enough CTAs for ~2 waves at 4 CTAs/SM, but every CTA keeps >= 1 full sweep
   long long want_y = ((long long)c->num_sms * 8 + tiles - 1) / tiles;
   long long max_y = (C + (long long)nwarps * S2N_PPT - 1) / ((long long)nwarps * S2N_PPT);
@@ -150,12 +195,29 @@ int launch_s2n(fgs_ctx *c, const double *d_x, int n, int G, const uint32_t *d_la
   if (tile_fits) {
     auto k = s2n_kernel<S2N_PPT, true>;
     FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, S2N_THREADS, smem, c->stream>>>(d_x, n, G, d_labels, d_n1n2, R, C, W, cols_per_cta,
-                                              d_scores, d_flags);
+    k<<<grid, S2N_THREADS, smem, c->stream>>>(d_x, n, G, c->class_lists.p, d_n1n2, R, C, cols_per_cta,
+                                              d_scores, d_flags, only_if, unless);
   } else {
-    s2n_kernel<S2N_PPT, false><<<grid, S2N_THREADS, 0, c->stream>>>(
-        d_x, n, G, d_labels, d_n1n2, R, C, W, cols_per_cta, d_scores, d_flags);
+    if (smem_lists > (size_t)c->smem_optin) { set_error("%d samples: the class lists do not fit on chip", n); return FGS_ERR_UNSUPPORTED; }
+    FGS_CUDA(cudaFuncSetAttribute(s2n_kernel<S2N_PPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lists));
+    s2n_kernel<S2N_PPT, false><<<grid, S2N_THREADS, smem_lists, c->stream>>>(
+        d_x, n, G, c->class_lists.p, d_n1n2, R, C, cols_per_cta, d_scores, d_flags, only_if, unless);
   }
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
+}
+
+// redo[0 .. C) = 1 when the device flag says so (block-level fallback: every column is ranked again)
+__global__ void mark_all_if_kernel(int *__restrict__ redo, long long C, const int *__restrict__ only_if,
+                                   const int *__restrict__ unless) {
+  if (*only_if == 0 || (unless && *unless != 0)) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) redo[i] = 1;
+}
+int launch_mark_all_if(fgs_ctx *c, int *d_redo, long long C, const int *only_if, const int *unless) {
+  if (C <= 0) return FGS_OK;
+  mark_all_if_kernel<<<ceil_div(C, 256), 256, 0, c->stream>>>(d_redo, C, only_if, unless);
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   return FGS_OK;

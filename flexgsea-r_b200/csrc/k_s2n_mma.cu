@@ -199,12 +199,11 @@ s2n_mma_kernel(const double *__restrict__ xc, const double *__restrict__ tot, in
 
 int launch_s2n_mma(fgs_ctx *c, const double *d_xc, const double *d_tot, int n, int G,
                    const uint32_t *d_labels, const int *d_n1n2, int R, long long C, double *d_scores,
-                   int2 *d_list, int *d_count, int cap) {
+                   int2 *d_list, int *d_count, int cap, int *d_overflow) {
   if (C <= 0 || G <= 0) return FGS_OK;
   dim3 grid(ceil_div(G, SM_BG), ceil_div(C, SM_BN));
   s2n_mma_kernel<<<grid, 256, 0, c->stream>>>(d_xc, d_tot, n, G, d_labels, d_n1n2, R, C, (n + 31) / 32,
-                                              d_scores, d_list, d_count, cap,
-                                              c->flags.p + (c->flags.n - 1));
+                                              d_scores, d_list, d_count, cap, d_overflow);
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   return FGS_OK;
@@ -218,7 +217,8 @@ __global__ void s2n_exact_entries_kernel(const double *__restrict__ x, int n, in
                                          const int *__restrict__ n1n2, int R, int W,
                                          const int2 *__restrict__ list, const int *__restrict__ count,
                                          int cap, double *__restrict__ scores, int *__restrict__ flags,
-                                         int after_patch) {
+                                         int after_patch, const int *__restrict__ unless) {
+  if (unless && *unless != 0) return;  // the list overflowed: the whole block is rescored instead
   int total = *count;
   if (total > cap) total = cap;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -260,10 +260,10 @@ __global__ void s2n_exact_entries_kernel(const double *__restrict__ x, int n, in
 
 int launch_s2n_exact_entries(fgs_ctx *c, const double *d_x, int n, int G, const uint32_t *d_labels,
                              const int *d_n1n2, int R, const int2 *d_list, const int *d_count, int cap,
-                             double *d_scores, int *d_flags, bool after_patch) {
+                             double *d_scores, int *d_flags, bool after_patch, const int *unless) {
   s2n_exact_entries_kernel<<<c->num_sms * 4, 128, 0, c->stream>>>(d_x, n, G, d_labels, d_n1n2, R,
                                                                   (n + 31) / 32, d_list, d_count, cap,
-                                                                  d_scores, d_flags, after_patch ? 1 : 0);
+                                                                  d_scores, d_flags, after_patch ? 1 : 0, unless);
   c->launches++;
   FGS_CUDA(cudaGetLastError());
   return FGS_OK;

@@ -12,6 +12,8 @@
 // :602-616) are accumulated in double-double and combined in a fixed order, so
 // the means round like R's long-double mean() and are reproducible across any
 // split of the permutations over chunks or GPUs.
+#include <algorithm>
+
 #include "fgs_common.cuh"
 
 namespace fgs {
@@ -66,20 +68,33 @@ sig_partial_kernel(const double *__restrict__ null, int S, int R, int P, int res
   const double e = es[s];
   const bool pos_side = (e >= 0.0) || abs_flag;
   dd sp = {0.0, 0.0}, sn = {0.0, 0.0};
-  long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+  int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;  // a chunk is far below 2^31 permutations
   const double *base = null + (size_t)s + (size_t)S * resp;
   const size_t stride = (size_t)S * R;
-  for (int p = p0; p < p1; p++) {
-    const double v = snap_to_observed(base[stride * p], e, snap_rel);
-    if (v >= 0.0) { c0++; sp = dd_add_d(sp, v); }
-    if (v < 0.0) { c1++; sn = dd_add_d(sn, v); }
-    if (v <= 0.0) c2++;
-    if (split_p) {  // :579-587
-      if (pos_side) { if (v >= 0.0 && e <= v) c3++; }
-      else { if (v <= 0.0 && e >= v) c4++; }
-    } else {        // :589-597
-      if (e <= v) c3++;
-      if (e >= v) c4++;
+  // one streaming read of the null (8 S P bytes): SIG_U loads in flight per thread, and ONE
+  // double-double add per value -- the accumulator of the value's sign is selected, updated and
+  // put back (written as two guarded adds the compiler computes both and selects: twice the FP64 work)
+  constexpr int SIG_U = 8;
+  for (int pb = p0; pb < p1; pb += SIG_U) {
+    double vv[SIG_U];
+#pragma unroll
+    for (int u = 0; u < SIG_U; u++) vv[u] = (pb + u < p1) ? __ldg(base + stride * (pb + u)) : nan("");
+#pragma unroll
+    for (int u = 0; u < SIG_U; u++) {
+      const double v = snap_to_observed(vv[u], e, snap_rel);
+      const bool nonneg = v >= 0.0, neg = v < 0.0;  // NaN (and the padding of the last group): neither
+      c0 += nonneg; c1 += neg; c2 += (v <= 0.0);
+      dd acc = nonneg ? sp : sn;
+      acc = dd_add_d(acc, (nonneg || neg) ? v : 0.0);
+      if (nonneg) sp = acc;
+      if (neg) sn = acc;
+      if (split_p) {  // :579-587
+        c3 += pos_side && nonneg && e <= v;
+        c4 += !pos_side && (v <= 0.0) && e >= v;
+      } else {        // :589-597
+        c3 += (e <= v);
+        c4 += (e >= v);
+      }
     }
   }
   double *ps = psums + ((size_t)chunk * S + s) * SIG_NF;
@@ -247,7 +262,7 @@ __global__ void scatter_sorted_kernel(const double *__restrict__ key, const int 
 // smallest and largest value, lut[c] = #{t < edge(c)} (or <=), so a value's count
 // is bracketed by lut[c], lut[c + 1] and the bisection that finishes the job runs
 // over a cell's population (about one threshold) instead of the whole list.
-constexpr int FDR_NC = 4096;
+constexpr int FDR_NC = 8192;
 __device__ __forceinline__ double lut_edge(double t0, double w, int c) { return __fma_rn((double)c, w, t0); }
 __global__ void fdr_lut_kernel(const double *__restrict__ t, int n, int upper, int *__restrict__ lut) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -263,10 +278,9 @@ __global__ void fdr_lut_kernel(const double *__restrict__ t, int n, int upper, i
   }
   lut[c] = lo;
 }
-// #{t < v} (UPPER = false) or #{t <= v} (UPPER = true) through the cell index
-template <bool UPPER>
+// #{t < v} (nonstrict = false) or #{t <= v} (nonstrict = true) through the cell index
 __device__ __forceinline__ int lut_count(const double *__restrict__ a, int n, const int *__restrict__ lut,
-                                         double t0, double w, double invw, double tmax, double v) {
+                                         double t0, double w, double invw, double tmax, double v, bool nonstrict) {
   if (n == 0 || v < t0) return 0;
   if (v > tmax) return n;
   int lo = 0, hi = n;
@@ -274,75 +288,96 @@ __device__ __forceinline__ int lut_count(const double *__restrict__ a, int n, co
     int c = min(max((int)((v - t0) * invw), 0), FDR_NC - 1);
     while (c > 0 && v < lut_edge(t0, w, c)) c--;                  // rounding of the cell guess
     while (c < FDR_NC - 1 && v >= lut_edge(t0, w, c + 1)) c++;
-    lo = lut[c]; hi = lut[c + 1];
+    lo = lut[c]; hi = lut[c + 1];    // #{t < edge(c)} <= either count <= #{t < edge(c + 1)}
   }
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (UPPER ? (a[mid] <= v) : (a[mid] < v)) lo = mid + 1; else hi = mid;
+    const double t = a[mid];
+    if ((t < v) || (nonstrict && t == v)) lo = mid + 1; else hi = mid;
   }
   return lo;
 }
 
+// The count for a value known only approximately: `va` is within FDR_APPROX_REL of the exact
+// normalised value.  The count is a step function of the value with steps at the thresholds, so it
+// is the exact value's count unless a threshold lies within that distance of `va`; `sure` says so.
+constexpr double FDR_APPROX_REL = 1e-15;  // v * fl(1 / m) is within 2 ulp (4.5e-16) of fl(v / m)
+
+// ONE sorted list serves both sides: T = [thresholds of group 2 (all negative), ascending] followed
+// by [thresholds of group 1 (all >= 0; every set in abs mode), ascending].  A non-negative (or abs)
+// value nv needs #{t1 < nv} = #{T < nv} - n2; a negative one #{t2 <= nv} = #{T <= nv}.  Both land in
+// one histogram H[n + 2]: a value with count B goes to H[B] (negative side: hist2[b] = H[b]) or
+// H[B + 1] (positive side: hist1[b] = H[n2 + 1 + b]) -- no branch on the sign of the value, so a
+// warp whose lanes hold values of both signs runs one instruction stream, not two.
+constexpr int FDR_T_SMEM = 1024, FDR_T_GLOBAL = 256;  // threads per CTA of the two variants
 template <bool T_SMEM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(T_SMEM ? FDR_T_SMEM : FDR_T_GLOBAL)
 fdr_count_kernel(const double *__restrict__ null, int S, int R, int P, int resp, int abs_flag,
                  const double *__restrict__ es, const double *__restrict__ mpos,
-                 const double *__restrict__ mneg,
-                 const double *__restrict__ t1, int n1, const double *__restrict__ t2, int n2,
+                 const double *__restrict__ mneg, const double *__restrict__ T, int n, int n2,
                  const int *__restrict__ lut_g, int chunk_len, double snap_rel,
-                 unsigned long long *__restrict__ hist1,
-                 unsigned long long *__restrict__ hist2, unsigned long long *__restrict__ glob) {
+                 unsigned long long *__restrict__ hist, unsigned long long *__restrict__ glob) {
   extern __shared__ __align__(16) unsigned char smem[];
-  double *st1 = (double *)smem;
-  double *st2 = st1 + (T_SMEM ? n1 : 0);
-  unsigned int *h1 = (unsigned int *)(st2 + (T_SMEM ? n2 : 0));
-  unsigned int *h2 = h1 + (n1 + 1);
-  int *lut1 = (int *)(h2 + (n2 + 1)), *lut2 = lut1 + (FDR_NC + 1);
-  for (int i = threadIdx.x; i < n1 + n2 + 2; i += blockDim.x) h1[i] = 0;
-  for (int i = threadIdx.x; i < 2 * (FDR_NC + 1); i += blockDim.x) lut1[i] = lut_g[i];
-  if (T_SMEM) {
-    for (int i = threadIdx.x; i < n1; i += blockDim.x) st1[i] = t1[i];
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) st2[i] = t2[i];
-  }
+  double *st = (double *)smem;
+  unsigned int *h = (unsigned int *)(st + (T_SMEM ? n : 0));
+  int *lut = (int *)(h + (n + 2));
+  for (int i = threadIdx.x; i < n + 2; i += blockDim.x) h[i] = 0;
+  for (int i = threadIdx.x; i < FDR_NC + 1; i += blockDim.x) lut[i] = lut_g[i];
+  if (T_SMEM)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) st[i] = T[i];
   __syncthreads();
-  const double *a1 = T_SMEM ? st1 : t1, *a2 = T_SMEM ? st2 : t2;
-  const double t10 = n1 > 0 ? t1[0] : 0.0, t1max = n1 > 0 ? t1[n1 - 1] : 0.0, w1 = (t1max - t10) / FDR_NC;
-  const double t20 = n2 > 0 ? t2[0] : 0.0, t2max = n2 > 0 ? t2[n2 - 1] : 0.0, w2 = (t2max - t20) / FDR_NC;
-  const double iw1 = w1 > 0.0 ? 1.0 / w1 : 0.0, iw2 = w2 > 0.0 ? 1.0 / w2 : 0.0;
+  const double *a = T_SMEM ? st : T;
+  const double t0 = n > 0 ? T[0] : 0.0, tmax = n > 0 ? T[n - 1] : 0.0, w = (tmax - t0) / FDR_NC;
+  const double iw = w > 0.0 ? 1.0 / w : 0.0;
   const int p0 = blockIdx.y * chunk_len, p1 = min(P, p0 + chunk_len);
-  // a value is searched in ONE threshold list: positive (or abs) values can only
-  // exceed group-1 thresholds, negative ones only undercut group-2 thresholds.
-  // Four permutations in flight per thread hide the global-load latency.
-  constexpr int U = 4;
+  // One streaming read of the null (8 S P bytes): U permutations in flight per thread.  The
+  // normalisation nes_null = v / mean (:608-610, :619-621) is an exact division in the
+  // reference and decides `>` / `<` against the observed NES; here the value is first
+  // located with v * (1 / mean) -- one multiply instead of a division per value -- and only
+  // when a threshold lies within the error of that product is the division done and the value
+  // located again (a null NES that ties with an observed one takes that path: counts exact).
+  constexpr int U = 8;
   unsigned long long gpos = 0, gneg = 0;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
     const double mp = mpos[s], mg = mneg[s], e = es[s];
+    const double dpos = mp, dneg = abs_flag ? mp : -mg;  // the divisor of a value by its sign
+    const double rpos = 1.0 / dpos, rneg = 1.0 / dneg;
     const double *base = null + (size_t)s + (size_t)S * resp;
     const size_t stride = (size_t)S * R;
+    unsigned int lpos = 0, lneg = 0;
     for (int pb = p0; pb < p1; pb += U) {
       double v[U];
 #pragma unroll
-      for (int u = 0; u < U; u++) v[u] = (pb + u < p1) ? snap_to_observed(base[stride * (pb + u)], e, snap_rel) : nan("");
+      for (int u = 0; u < U; u++) v[u] = (pb + u < p1) ? __ldg(base + stride * (pb + u)) : nan("");
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const double nv = abs_flag ? v[u] / mp : v[u] / (v[u] >= 0.0 ? mp : -mg);  // :608-610, :619-621
-        if (nv > 0.0) gpos++;                                                      // :503
-        if (nv < 0.0) gneg++;                                                      // :504
-        if (isnan(nv)) continue;
-        // bins that no set's count reads are skipped: they are also the crowded ones
-        if (abs_flag || nv >= 0.0) {
-          const int b = lut_count<false>(a1, n1, lut1, t10, w1, iw1, t1max, nv);   // #{t1 <  nv}
-          if (b > 0) atomicAdd(&h1[b], 1u);
-        } else {
-          const int b = lut_count<true>(a2, n2, lut2, t20, w2, iw2, t2max, nv);    // #{t2 <= nv}
-          if (b < n2) atomicAdd(&h2[b], 1u);
+        const double vs = snap_to_observed(v[u], e, snap_rel);
+        const bool vneg = !(vs >= 0.0);
+        double nv = vs * (vneg ? rneg : rpos);
+        bool sure = isfinite(nv) && fabs(nv) > 1e-290;
+        bool nonstrict = !abs_flag && nv < 0.0;   // a negative value undercuts: `<`, i.e. count T <= nv
+        int B = 0;
+        if (sure) {
+          B = lut_count(a, n, lut, t0, w, iw, tmax, nv, nonstrict);
+          const double d = FDR_APPROX_REL * fabs(nv);
+          sure = (B == 0 || nv - a[B - 1] > d) && (B == n || a[B] - nv > d);
         }
+        if (!sure) {  // the reference's own arithmetic
+          nv = vs / (vneg ? dneg : dpos);
+          if (isnan(nv)) continue;
+          nonstrict = !abs_flag && nv < 0.0;
+          B = lut_count(a, n, lut, t0, w, iw, tmax, nv, nonstrict);
+        }
+        lpos += nv > 0.0;                                                          // :503
+        lneg += nv < 0.0;                                                          // :504
+        // bins that no set's count reads are skipped: they are also the crowded ones
+        if (nonstrict ? (B < n2) : (B > n2)) atomicAdd(&h[nonstrict ? B : B + 1], 1u);
       }
     }
+    gpos += lpos; gneg += lneg;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i <= n1; i += blockDim.x) if (h1[i]) atomicAdd(&hist1[i], (unsigned long long)h1[i]);
-  for (int i = threadIdx.x; i <= n2; i += blockDim.x) if (h2[i]) atomicAdd(&hist2[i], (unsigned long long)h2[i]);
+  for (int i = threadIdx.x; i < n + 2; i += blockDim.x) if (h[i]) atomicAdd(&hist[i], (unsigned long long)h[i]);
   for (int o = 16; o; o >>= 1) {
     gpos += __shfl_xor_sync(0xffffffffu, gpos, o);
     gneg += __shfl_xor_sync(0xffffffffu, gneg, o);
@@ -522,36 +557,50 @@ int launch_sig_stage2(fgs_ctx *c, const double *d_null, int S, int R, int P, int
   FGS_CUDA(cudaMemcpyAsync(h_gn, gn, sizeof(h_gn), cudaMemcpyDeviceToHost, c->stream));
   FGS_CUDA(cudaStreamSynchronize(c->stream));
   const int n1 = h_gn[1], n2 = h_gn[2];
+  const int n12 = n1 + n2;
+  // T = [group-2 thresholds][group-1 thresholds], one ascending list (see fdr_count_kernel)
+  FGS_TRY(c->sig_t.ensure((size_t)std::max(n12, 1)));
+  if (n2 > 0) FGS_CUDA(cudaMemcpyAsync(c->sig_t.p, t2, (size_t)n2 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if (n1 > 0) FGS_CUDA(cudaMemcpyAsync(c->sig_t.p + n2, t1, (size_t)n1 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  unsigned long long *H = h1;   // [n12 + 2]: hist2 = H[0 .. n2], hist1 = H[n2 + 1 .. n12 + 1]
   if (P > 0) {
-    int gx = ceil_div(S, 256);
-    int gy = (c->num_sms * 8) / gx + 1;
+    FGS_TRY(c->sig_lut.ensure((size_t)(FDR_NC + 1)));
+    fdr_lut_kernel<<<ceil_div(FDR_NC + 1, 256), 256, 0, c->stream>>>(c->sig_t.p, n12, 0, c->sig_lut.p);
+    c->launches += 1;
+    const size_t smem_lut = (size_t)(FDR_NC + 1) * 4;
+    const size_t smem_h = (size_t)(n12 + 2) * 4 + smem_lut;      // histogram + cell index
+    const size_t smem_t = (size_t)n12 * 8 + smem_h;              // + the thresholds themselves
+    if (smem_h > (size_t)c->smem_optin) {
+      // (about 50,000 gene sets: the per-CTA histogram no longer fits on chip)
+      set_error("pooled FDR over %d gene sets needs %zu bytes of shared memory per CTA, %d available", S, smem_h,
+                c->smem_optin);
+      return FGS_ERR_UNSUPPORTED;
+    }
+    const bool t_smem = smem_t <= (size_t)c->smem_optin;
+    const int threads = t_smem ? FDR_T_SMEM : FDR_T_GLOBAL;
+    const int per_sm = t_smem ? 1 : std::max(1, std::min(8, (int)((size_t)c->smem_optin / smem_h)));
+    int gx = ceil_div(S, threads);
+    int gy = std::max(1, (c->num_sms * per_sm) / gx);    // one wave of CTAs, each streaming its chunk
     if (gy > P) gy = P;
     int chunk_len = (P + gy - 1) / gy;
     gy = (P + chunk_len - 1) / chunk_len;
-    FGS_TRY(c->sig_lut.ensure((size_t)2 * (FDR_NC + 1)));
-    fdr_lut_kernel<<<ceil_div(FDR_NC + 1, 256), 256, 0, c->stream>>>(t1, n1, 0, c->sig_lut.p);
-    fdr_lut_kernel<<<ceil_div(FDR_NC + 1, 256), 256, 0, c->stream>>>(t2, n2, 1, c->sig_lut.p + FDR_NC + 1);
-    c->launches += 2;
-    const size_t smem_lut = (size_t)2 * (FDR_NC + 1) * 4;
-    size_t smem_t = (size_t)(n1 + n2) * 8 + (size_t)(n1 + n2 + 2) * 4 + smem_lut;
-    size_t smem_h = (size_t)(n1 + n2 + 2) * 4 + smem_lut;
     dim3 grid(gx, gy);
-    if (smem_t <= (size_t)c->smem_optin / 2) {
+    const double snap = c->null_exact_near_obs ? 0.0 : SIG_SNAP_REL;
+    if (t_smem) {
       auto k = fdr_count_kernel<true>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-      k<<<grid, 256, smem_t, c->stream>>>(d_null, S, R, P, response, abs_flag, d_es, d_mpos, d_mneg, t1, n1,
-                                          t2, n2, c->sig_lut.p, chunk_len, c->null_exact_near_obs ? 0.0 : SIG_SNAP_REL, h1, h2,
-                                          (unsigned long long *)d_glob);
+      k<<<grid, threads, smem_t, c->stream>>>(d_null, S, R, P, response, abs_flag, d_es, d_mpos, d_mneg, c->sig_t.p,
+                                              n12, n2, c->sig_lut.p, chunk_len, snap, H, (unsigned long long *)d_glob);
     } else {
       auto k = fdr_count_kernel<false>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
-      k<<<grid, 256, smem_h, c->stream>>>(d_null, S, R, P, response, abs_flag, d_es, d_mpos, d_mneg, t1, n1,
-                                          t2, n2, c->sig_lut.p, chunk_len, c->null_exact_near_obs ? 0.0 : SIG_SNAP_REL, h1, h2,
-                                          (unsigned long long *)d_glob);
+      k<<<grid, threads, smem_h, c->stream>>>(d_null, S, R, P, response, abs_flag, d_es, d_mpos, d_mneg, c->sig_t.p,
+                                              n12, n2, c->sig_lut.p, chunk_len, snap, H, (unsigned long long *)d_glob);
     }
     c->launches++;
     FGS_CUDA(cudaGetLastError());
   }
+  h2 = H; h1 = H + n2 + 1;
   hist_to_counts_kernel<<<1, 256, 0, c->stream>>>(h1, id1, n1, h2, id2, n2, S, d_null_counts);
   c->launches++;
   FGS_CUDA(cudaGetLastError());

@@ -27,6 +27,7 @@ __device__ __forceinline__ void certify_pair(const TieCert &tc, long long col, d
                                              uint32_t ga, uint32_t gb) {
   const double gap = fabs(a - b), scale = fmax(fabs(a), fabs(b));
   if (gap <= tc.abs_tol || gap <= tc.rel_tol * scale) {
+    if (gap == 0.0 && tc.dup && tc.dup[ga] == tc.dup[gb]) return;  // duplicated rows: tied in the reference too
     const int at = atomicAdd(tc.count, 2);
     if (at + 1 < tc.cap) {
       tc.list[at] = make_int2((int)col, (int)ga);

@@ -317,8 +317,18 @@ int fgs_set_progress(fgs_ctx *ctx, fgs_progress_fn cb, void *user);
  * permutations over contexts sets the total, so that routing decisions such as
  * es_exact_small do not depend on the shard -- the groups do it themselves),
  * "tail_split" (1, default: the ES kernels split the columns of a partial last
- * round over the idle SMs) */
+ * round over the idle SMs),
+ * "dedup_labels" (1, default: with few samples -- at most 32, and fewer distinct
+ * class labellings than half the permutations -- fgs_perm_null computes every
+ * distinct labelling once and copies its column to the permutations that share
+ * it; such problems also take the all-exact path up to a far larger size) */
 int fgs_set_option(fgs_ctx *ctx, const char *name, long long value);
+/* read-only counters of the most recent call: "dedup_labellings" (distinct
+ * labellings the last fgs_perm_null computed, 0 when it did not deduplicate),
+ * "fallback_blocks" (blocks of the last fgs_perm_null whose certification lists
+ * overflowed and were rescored by the bit-faithful kernel), "duplicated_rows"
+ * (1 when the resident x holds genes with bit-identical rows) */
+int fgs_get_stat(fgs_ctx *ctx, const char *name, long long *value);
 
 #ifdef __cplusplus
 }

@@ -969,3 +969,78 @@ def test_progress_hook_reports_and_cancels(ctx, oracle):
     finally:
         ctx.set_progress(None)
         ctx.set_option("perm_block", 0)
+
+
+def test_near_duplicated_genes_take_the_block_fallback(ctx, oracle):
+    """Thousands of genes that are copies of others up to the last bits (a rescaled copy: s2n is
+    scale invariant) nearly tie in every permutation: the near-tie list of the tensor-core path
+    overflows and the BLOCK is rescored by the bit-faithful kernel and ranked again (device-side,
+    no whole-call rerun).  Ranks bit-exact, scores bit-identical to the reference arithmetic in
+    that block, ES within 1e-10.  Bit-identical copies need none of that: the reference ties them
+    exactly too, index order decides, and the block keeps the tensor path."""
+    G0, ndup, n, S, P = 4000, 2200, 20, 60, 2072
+    off, idx = synth.gene_sets_csr(G0 + ndup, S, (10, 300), "loguniform", seed=51)
+    x0, y = synth.two_class(G0, n, seed=52)
+    perm = synth.perm_matrix(n, P, seed=54)
+    oracle.use_all_cores()
+    for scale, want_fallback in ((1.0 + 2.0 ** -30, 2), (1.0, 0)):
+        x = np.asfortranarray(np.concatenate([x0, x0[:, :ndup] * scale], axis=1))
+        ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+        assert ctx.get_stat("duplicated_rows") == (1 if scale == 1.0 else 0)
+        ctx.set_option("perm_block", 1036)        # two blocks, each 2 * 2200 * 1036 = 4.6 M entries > the 4 M list
+        try:
+            got = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm)
+            gsc, grk = ctx.debug_last(P - 1036)   # the last block
+        finally:
+            ctx.set_option("perm_block", 0)
+        assert ctx.get_stat("fallback_blocks") == want_fallback
+        rc, want, sc = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, oracle.ES_WKS,
+                                        return_scores=True)
+        assert rc == 0
+        ref_last = sc[:, 0, 1036:]
+        assert np.array_equal(grk, _ranks(oracle, ref_last))
+        if want_fallback:
+            assert np.array_equal(gsc, ref_last)  # the fallback block holds the reference's own bits
+        else:
+            assert np.allclose(gsc, ref_last, rtol=1e-11, atol=1e-13)
+        assert np.abs(got - want).max() <= ES_TOL
+
+
+@pytest.mark.parametrize("es_kind", ["wks", "maxmean"])
+def test_few_samples_many_genes_dedup_counts_identical(oracle, es_kind):
+    """VERDICT r1 item 7: a LARGE problem with very few samples (4 samples: six labellings;
+    20,000 genes, 2,000 sets).  Every distinct labelling is computed once, in the reference's
+    operation order, and copied to the permutations that share it: p AND pooled-FDR counts are
+    identical to the oracle's, the null is bit-identical across repeated labellings."""
+    G, n, S, P = 20000, 4, 2000, 1500
+    off, idx = synth.gene_sets_csr(G, S, (15, 300), "loguniform", seed=61)
+    x, y = synth.two_class(G, n, off, idx, seed=62)
+    perm = synth.perm_matrix(n, P, seed=64)
+    gk = nat.ES_WEIGHTED_KS if es_kind == "wks" else nat.ES_MAXMEAN
+    ok = oracle.ES_WKS if es_kind == "wks" else oracle.ES_MAXMEAN
+    c = fg.Context(0)      # default options: es_exact_small and dedup_labels on
+    try:
+        c.set_x(x); c.set_gene_sets(off, idx); c.set_response_s2n(y)
+        sc = c.score_observed(nat.SCORE_S2N)
+        es = c.observed_es(gk, sc, ragged=False)["es"][:, 0]
+        null = c.perm_null(nat.SCORE_S2N, gk, P, perm=perm)
+        assert c.get_stat("dedup_labellings") == 6
+        sig = c.calc_sig(es)
+        oracle.use_all_cores()
+        rc, want = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, ok)
+        assert rc == 0 and np.abs(null - want).max() <= ES_TOL
+        osig = oracle.calc_sig(es, want[:, 0, :])
+        assert np.array_equal(sig["p_counts"], osig["p_counts"])
+        assert np.array_equal(sig["fdr_counts"], osig["fdr_counts"])
+        assert np.array_equal(sig["glob_counts"], osig["glob_counts"])
+        # permutations that give the same labelling hold the same column, bit for bit
+        lab = y[:, 0][perm - 1]                                   # [n x P] labels after permutation
+        _, first, inv = np.unique(lab.T, axis=0, return_index=True, return_inverse=True)
+        assert np.array_equal(null, null[:, :, first[inv.ravel()]], equal_nan=True)
+        # the Philox path and a sharded call deduplicate the same way
+        c.set_option("dedup_labels", 0)
+        plain = c.perm_null(nat.SCORE_S2N, gk, P, perm=perm)
+        assert c.get_stat("dedup_labellings") == 0
+        assert np.abs(plain - null).max() <= ES_TOL
+    finally:
+        c.close()
