@@ -24,7 +24,7 @@ SYMBOLS = [
     "fgs_abi_version", "fgs_last_error", "fgs_device_count", "fgs_create", "fgs_destroy",
     "fgs_s2n", "fgs_set_x", "fgs_set_gene_sets", "fgs_set_response_s2n", "fgs_set_response_lm",
     "fgs_n_response", "fgs_score_observed", "fgs_observed_es", "fgs_set_observed_es", "fgs_perm_null",
-    "fgs_es_from_scores", "fgs_debug_last_scores", "fgs_null_device_ptr", "fgs_set_null",
+    "fgs_es_from_scores", "fgs_es_from_scores_tile", "fgs_null_finish", "fgs_debug_last_scores", "fgs_null_device_ptr", "fgs_set_null",
     "fgs_calc_sig", "fgs_sig_stage1", "fgs_sig_stage2", "fgs_sig_finish", "fgs_launch_count",
     "fgs_last_timings", "fgs_set_profiling", "fgs_set_option", "fgs_get_stat", "fgs_set_progress",
     "fgs_gmt_parse", "fgs_gmt_read", "fgs_gmt_n_sets", "fgs_gmt_nnz", "fgs_gmt_offsets", "fgs_gmt_index",
@@ -34,7 +34,7 @@ SYMBOLS = [
     "fgs_group_create", "fgs_group_destroy", "fgs_group_size", "fgs_group_ctx", "fgs_group_set_x",
     "fgs_group_set_gene_sets", "fgs_group_set_response_s2n", "fgs_group_set_response_lm",
     "fgs_group_set_option", "fgs_group_score_observed", "fgs_group_observed_es", "fgs_group_perm_null",
-    "fgs_group_es_from_scores", "fgs_group_calc_sig", "fgs_group_last_timings",
+    "fgs_group_es_from_scores", "fgs_group_es_from_scores_tile", "fgs_group_null_finish", "fgs_group_calc_sig", "fgs_group_last_timings",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -270,6 +270,20 @@ class Context:
         out = np.zeros((self.S, R, P), order="F") if want_host else None
         self._check(self._lib.fgs_es_from_scores(self._h, es_kind, C.c_double(p), _p(sc, _dp), G, R, P,
                                                  _p(out, _dp)))
+        return out
+
+    def es_from_scores_tile(self, es_kind, scores, perm_offset, n_perm_total, p=1.0):
+        """queue one tile [G, R, B] of user scores (permutations perm_offset ..); returns at once"""
+        sc = _f(scores)
+        G, R, B = sc.shape
+        self._check(self._lib.fgs_es_from_scores_tile(self._h, es_kind, C.c_double(p), _p(sc, _dp), G, R, B,
+                                                      C.c_longlong(perm_offset), C.c_longlong(n_perm_total)))
+        self._tile_keep = sc   # the helper thread reads it until the next call on this context
+
+    def null_finish(self, want_host=True):
+        _, S, R, P = self.null_device_ptr()
+        out = np.zeros((S, R, P), order="F") if want_host else None
+        self._check(self._lib.fgs_null_finish(self._h, _p(out, _dp)))
         return out
 
     def debug_last(self, n_col, G=None):
@@ -528,6 +542,21 @@ class Group:
         out = np.zeros((self.S, R, P), order="F") if want_host else None
         self._check(self._lib.fgs_group_es_from_scores(self._h, es_kind, C.c_double(p), _p(sc, _dp), G, R, P,
                                                        _p(out, _dp)))
+        return out
+
+    def es_from_scores_tile(self, es_kind, scores, perm_offset, n_perm_total, p=1.0):
+        sc = _f(scores)
+        G, R, B = sc.shape
+        self._tile_shape = (R, int(n_perm_total))
+        self._check(self._lib.fgs_group_es_from_scores_tile(self._h, es_kind, C.c_double(p), _p(sc, _dp), G, R, B,
+                                                            C.c_longlong(perm_offset), C.c_longlong(n_perm_total)))
+        self._tile_keep = getattr(self, "_tile_keep2", None), sc   # tiles may straddle two GPUs' spans
+        self._tile_keep2 = sc
+
+    def null_finish(self, want_host=True):
+        R, P = self._tile_shape
+        out = np.zeros((self.S, R, P), order="F") if want_host else None
+        self._check(self._lib.fgs_group_null_finish(self._h, _p(out, _dp)))
         return out
 
     def calc_sig(self, es, response=0, split_p=True, calc_nes=True, abs_flag=False, exchange=0):

@@ -14,6 +14,7 @@ on the host per permutation (:393-394) and its [G, R, P] score array is shipped
 once; a user-defined ``es_fn`` / ``sig_fun`` is arbitrary host code and keeps
 the reference's plugin loop.  The built-ins never run on the CPU.
 """
+import inspect
 import os
 
 import numpy as np
@@ -62,6 +63,19 @@ class ModelMatrix:
         self.values = np.asarray(values, dtype=np.float64)
         self.colnames = list(colnames)
         assert self.values.ndim == 2 and self.values.shape[1] == len(self.colnames)
+
+
+class EList:
+    """limma's EList as far as flexgsea() looks at it (R/flexgsea.R:159-173, t.x = TRUE): ``E`` is
+    [genes x samples] (log-expression, e.g. from voom), ``genes`` its row names, ``weights`` the
+    optional [genes x samples] precision weights limma::lmFit uses."""
+
+    def __init__(self, E, genes=None, weights=None):
+        self.E = np.asarray(E, dtype=np.float64)
+        assert self.E.ndim == 2
+        self.genes = None if genes is None else [str(g) for g in genes]
+        self.weights = None if weights is None else np.asarray(weights, dtype=np.float64)
+        assert self.weights is None or self.weights.shape == self.E.shape
 
 
 def _y_matrix(y):
@@ -196,6 +210,86 @@ flexgsea_maxmean = EsFn("maxmean", nat.ES_MAXMEAN)
 flexgsea_mean = EsFn("mean", nat.ES_MEAN)
 
 
+def _trigamma_inverse(x):
+    """limma::trigammaInverse: Newton iterations on 1 / trigamma (x > 0)."""
+    from scipy.special import polygamma
+    x = float(x)
+    if x > 1e7:
+        return 1.0 / np.sqrt(x)
+    if x < 1e-6:
+        return 1.0 / x
+    y = 0.5 + 1.0 / x
+    for _ in range(50):
+        tri = float(polygamma(1, y))
+        dif = tri * (1.0 - tri / x) / float(polygamma(2, y))
+        y += dif
+        if -dif / y < 1e-8:
+            break
+    return y
+
+
+def flexgsea_limma(x, y, abs=False):
+    """The reference's limma adaptor (R/flexgsea_limma.R:15-31) as a client of the user-score
+    path: moderated t of every non-intercept design column, ``fit <- eBayes(lmFit(x, y)); fit$t``.
+    ``x`` is an EList (E [genes x samples], optional precision weights, as voom makes it) or a
+    [genes x samples] matrix, ``y`` a ModelMatrix.  limma itself is third-party R code; this is
+    a numpy restatement of lmFit (weighted least squares per gene) and eBayes' variance shrinkage
+    (squeezeVar / fitFDist, Smyth 2004), host code in the plugin position like any user-defined
+    gene.score.fn -- its scores are shipped to the device in tiles, ranking onward runs there.
+    Numeric parity with limma is not pinned (limma is absent here)."""
+    from scipy.special import digamma, polygamma
+    if not isinstance(y, ModelMatrix):
+        raise ValueError("is.model.matrix(y) is not TRUE")  # :16
+    E = x.E if isinstance(x, EList) else np.asarray(x, dtype=np.float64)
+    W = x.weights if isinstance(x, EList) else None
+    D = y.values
+    G, n = E.shape
+    q = D.shape[1]
+    if W is None:
+        A = np.broadcast_to(D.T @ D, (G, q, q))
+        b = E @ D
+    else:
+        A = np.einsum("ni,gn,nj->gij", D, W, D)
+        b = np.einsum("ni,gn,gn->gi", D, W, E)
+    Ainv = np.linalg.inv(A)
+    beta = np.einsum("gij,gj->gi", Ainv, b)
+    res = E - beta @ D.T
+    rss = (res * res * (1.0 if W is None else W)).sum(axis=1)
+    df = float(n - q)
+    s2 = rss / df
+    unscaled = np.sqrt(np.einsum("gii->gi", Ainv))
+    # eBayes: s2 ~ s0^2 * F(df, df0); moment estimates on log s2 (limma::fitFDist)
+    ok = s2 > 0
+    z = np.log(s2[ok])
+    e = z - digamma(df / 2.0) + np.log(df / 2.0)
+    emean = e.mean()
+    evar = ((e - emean) ** 2).sum() / max(e.size - 1, 1) - float(polygamma(1, df / 2.0))
+    if evar > 0:
+        df0 = 2.0 * _trigamma_inverse(evar)
+        s02 = np.exp(emean + digamma(df0 / 2.0) - np.log(df0 / 2.0))
+        s2_post = (df0 * s02 + df * s2) / (df0 + df)
+    else:  # df0 = Inf: every gene gets the prior variance
+        s2_post = np.full(G, np.exp(emean))
+    t = beta / (unscaled * np.sqrt(s2_post)[:, None])
+    names = list(y.colnames)
+    if names[0] == "(Intercept)":  # :22-24
+        t, names = t[:, 1:], names[1:]
+    t = np.abs(t) if abs else t
+    if _pd is not None:
+        return _pd.DataFrame(t, columns=names)
+    return t
+
+
+def _call_score(fn, x, y, t_x, abs):
+    """gene.score.fn(x, y, [t.x = t.x,] abs = abs): t.x is passed only to functions that take it
+    (R/flexgsea.R:246-250, :393-394)."""
+    try:
+        takes = "t_x" in inspect.signature(fn).parameters
+    except (TypeError, ValueError):
+        takes = False
+    return fn(x, y, t_x=t_x, abs=abs) if takes else fn(x, y, abs=abs)
+
+
 def _table(cols):
     if _pd is not None:
         return _pd.DataFrame(cols)
@@ -304,6 +398,8 @@ def gene_sets_to_csr(gene_sets, gene_names):
 
 # --------------------------------------------------------------------------
 def _x_values(x):
+    if isinstance(x, EList):  # genes x samples; the device wants a gene's samples contiguous
+        return np.asfortranarray(x.E.T), x.genes
     if _pd is not None and isinstance(x, _pd.DataFrame):
         return np.asfortranarray(x.to_numpy(dtype=np.float64)), [str(c) for c in x.columns]
     a = np.asarray(x)
@@ -451,6 +547,7 @@ def flexgsea(x, y, gene_sets, gene_score_fn=flexgsea_s2n, es_fn=flexgsea_weighte
     contexts, which is what the R binding does.
     """
     # ---- prepare and check input (:152-239) -----------------------------
+    t_x = isinstance(x, EList)   # :159-173
     xv, xnames = _x_values(x)
     n_samples, n_genes = xv.shape
     yv, _ = _y_matrix(y)
@@ -523,10 +620,11 @@ def flexgsea(x, y, gene_sets, gene_score_fn=flexgsea_s2n, es_fn=flexgsea_weighte
             raise ValueError("Gene scoring function returned NA or Inf. Check that all genes in x "
                              "have a positive variance.")  # :252
     else:
-        scores = np.asarray(gene_score_fn(x, y, abs=abs), dtype=np.float64)
+        scores = _call_score(gene_score_fn, x, y, t_x, abs)
         responses = None
         if _pd is not None and isinstance(scores, _pd.DataFrame):
             responses = [str(c) for c in scores.columns]
+        scores = np.asarray(scores, dtype=np.float64)
         if not np.isfinite(scores).all():
             raise ValueError("Gene scoring function returned NA or Inf. Check that all genes in x "
                              "have a positive variance.")
@@ -575,6 +673,27 @@ def flexgsea(x, y, gene_sets, gene_score_fn=flexgsea_s2n, es_fn=flexgsea_weighte
                                            perm_id0=lo, abs_flag=abs, want_host=want_null_host)
         except nat.NonFiniteScoreError:
             raise ValueError("Gene scoring function returned NA or Inf.")  # :401
+    elif builtin_es and not builtin_score:
+        # A user-defined gene.score.fn (limma's moderated t, say) runs on the host per permutation
+        # (:383-394); its scores go to the device in tiles of block.size permutations, and the
+        # call that hands a tile over only queues the work, so tile k is uploaded, ranked and
+        # scored while the host computes tile k + 1.
+        tile = max(1, int(block_size))
+        try:
+            in_flight = None   # the tile the library's helper thread is still reading
+            for t0 in range(0, local, tile):
+                B = min(tile, local - t0)
+                sc_tile = np.zeros((n_genes, R, B), order="F")
+                for j in range(B):
+                    yp = _permute_rows(y, pm_local[:, t0 + j] - 1)
+                    sc_tile[:, :, j] = np.asarray(_call_score(gene_score_fn, x, yp, t_x, abs), dtype=np.float64)
+                if not np.isfinite(sc_tile).all():
+                    raise ValueError("Gene scoring function returned NA or Inf.")  # :400-402
+                ctx.es_from_scores_tile(es_fn.kind, sc_tile, t0, local)
+                in_flight = sc_tile
+            null_local = ctx.null_finish(want_host=want_null_host) if local > 0 else np.zeros((len(set_names), R, 0), order="F")
+        except nat.NonFiniteScoreError:
+            raise ValueError("Gene scoring function returned NA or Inf.")  # :401
     else:
         sc_null = np.zeros((n_genes, R, local), order="F")
         for j in range(local):  # user closure per permutation (:383-394)
@@ -582,7 +701,7 @@ def flexgsea(x, y, gene_sets, gene_score_fn=flexgsea_s2n, es_fn=flexgsea_weighte
             if builtin_score:
                 sc_null[:, :, j] = gene_score_fn(x, yp, abs=abs, device=device)
             else:
-                sc_null[:, :, j] = np.asarray(gene_score_fn(x, yp, abs=abs), dtype=np.float64)
+                sc_null[:, :, j] = np.asarray(_call_score(gene_score_fn, x, yp, t_x, abs), dtype=np.float64)
         if not np.isfinite(sc_null).all():
             raise ValueError("Gene scoring function returned NA or Inf.")
         if builtin_es:

@@ -30,7 +30,21 @@ int launch_sig_means(fgs_ctx *c, const double *d_sums_parts, int nparts, const l
                      double *d_mneg, double *d_nes, double *d_fwer);
 int launch_bh(fgs_ctx *c, const double *d_p, int S, double *d_fdr);
 
+}  // namespace fgs (reopened below)
+// a tile still in flight (fgs_es_from_scores_tile) finishes before anything else touches the context
+int fgs::settle_tile(fgs_ctx *c) {
+  if (c->tile_job.joinable()) c->tile_job.join();
+  if (c->tile_rc != FGS_OK) {
+    const int rc = c->tile_rc;
+    c->tile_rc = FGS_OK;
+    set_error("%s", c->tile_err.c_str());
+    return rc;
+  }
+  return FGS_OK;
+}
+namespace fgs {
 static int use_device(fgs_ctx *c) {
+  FGS_TRY(settle_tile(c));
   FGS_CUDA(cudaSetDevice(c->device));
   return FGS_OK;
 }
@@ -268,6 +282,10 @@ struct StageTimer {
     cudaEventRecord(e, c->stream);
     evs.push_back(e);
   }
+  void drop() {
+    for (auto e : evs) cudaEventDestroy(e);
+    evs.clear();
+  }
   void finish(float prologue_ms) {
     for (int i = 0; i < 5; i++) c->last_ms[i] = 0;
     if (!c->profiling) return;
@@ -483,6 +501,7 @@ int fgs_create(int device, fgs_ctx **out) {
 
 int fgs_destroy(fgs_ctx *c) {
   if (!c) return FGS_OK;
+  if (c->tile_job.joinable()) c->tile_job.join();
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   fgs_comm_destroy(c);
@@ -872,6 +891,7 @@ int fgs_score_observed(fgs_ctx *c, int score_kind, int abs_flag, double *scores)
   if (abs_flag) FGS_TRY(launch_abs_inplace(c, c->scores.p, (long long)G * R));
   FGS_TRY(d2h(c, scores, c->scores.p, (size_t)G * R));
   FGS_TRY(flags_check(c, 1));
+  c->pend_score_kind = score_kind; c->pend_abs = abs_flag ? 1 : 0;
   return FGS_OK;
 }
 
@@ -976,7 +996,11 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
                         c->labels.p + (size_t)p0 * R * 2 * W, Pb, p0, /*force_exact=*/c->cur_exact_all));
     c->last_launches[1] += c->launches - l0;
     tm.mark();
-    c->cur_ident = (c->cur_obs && score_kind == FGS_SCORE_S2N) ? c->ident.p + p0 : nullptr;
+    // (the observed ES is copied to label-preserving permutations only when it is known to be the
+    // ES of THESE scores: made by fgs_score_observed with this score kind and abs flag, same exponent)
+    c->cur_ident = (c->cur_obs && score_kind == FGS_SCORE_S2N && c->obs_score_kind == score_kind &&
+                    c->obs_abs == (abs_flag ? 1 : 0) && (es_kind != FGS_ES_WEIGHTED_KS || c->obs_p == p_exp))
+                       ? c->ident.p + p0 : nullptr;
     FGS_TRY(rank_and_es(c, es_kind, p_exp, abs_flag, (long long)Pb * R, es_e + (size_t)p0 * R * S, tm));
     if (c->cur_ident)
       FGS_TRY(launch_copy_observed(c, c->cur_obs, c->cur_ident, R, (long long)Pb * R, es_e + (size_t)p0 * R * S));
@@ -1035,10 +1059,16 @@ int fgs_perm_null(fgs_ctx *c, int score_kind, int es_kind, double p_exp, int abs
   return FGS_OK;   // es_null_out was filled block by block inside the loop
 }
 
-int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scores, int n_gene,
-                       int n_response, int n_perm, double *es_out) {
-  if (!c || !scores || n_gene <= 0 || n_response <= 0 || n_perm < 0) { set_error("fgs_es_from_scores: bad argument"); return FGS_ERR_ARG; }
-  FGS_TRY(use_device(c));
+// scores of permutations [perm_off, perm_off + n_perm) of a null of P_total permutations; `async`:
+// queue the work and return (fgs_null_finish waits and reports)
+static int es_from_scores_impl(fgs_ctx *c, int es_kind, double p_exp, const double *scores, int n_gene,
+                               int n_response, int n_perm, long long perm_off, long long P_total, double *es_out,
+                               bool async) {
+  if (!c || !scores || n_gene <= 0 || n_response <= 0 || n_perm < 0 || perm_off < 0 || perm_off + n_perm > P_total) {
+    set_error("fgs_es_from_scores: bad argument");
+    return FGS_ERR_ARG;
+  }
+  FGS_CUDA(cudaSetDevice(c->device));   // (not use_device: this may BE the tile in flight)
   if (c->S <= 0) { set_error("fgs_set_gene_sets has not been called"); return FGS_ERR_STATE; }
   if (c->G != 0 && c->G != n_gene && c->x.p) { /* x not needed on this path; sets decide */ }
   if (c->max_set > n_gene) { set_error("gene set index %d exceeds %d genes", c->max_set, n_gene); return FGS_ERR_ARG; }
@@ -1046,20 +1076,28 @@ int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scor
   c->G = n_gene;
   c->cur_cert = false;  // user scores: nothing to certify
   const int S = c->S, R = n_response, P = n_perm;
-  const long long C = (long long)R * P;
+  const long long C = (long long)R * P, C_total = (long long)R * P_total, col0 = (long long)R * perm_off;
   for (int i = 0; i < 5; i++) c->last_launches[i] = 0;
   int rc = FGS_OK;
   auto body = [&]() -> int {
-    FGS_TRY(c->es_null.ensure(std::max<size_t>((size_t)S * C, 1)));
-    c->null_S = S; c->null_R = R; c->null_P = P;
+    if (perm_off == 0) {
+      FGS_TRY(c->es_null.ensure(std::max<size_t>((size_t)S * C_total, 1)));
+    } else if (c->es_null.n < (size_t)S * C_total || c->null_S != S || c->null_R != R || c->null_P != P_total) {
+      set_error("fgs_es_from_scores_tile: tiles must start at permutation 0 and keep the gene sets, the number of "
+                "responses and the total");
+      return FGS_ERR_STATE;
+    }
+    c->null_S = S; c->null_R = R; c->null_P = (int)P_total;
+    double *const d_null = c->es_null.p + (size_t)col0 * S;   // this call's columns of the resident null
     c->cur_obs = (c->obs_valid && c->obs_kind == es_kind && c->obs_S == S && c->obs_R == R) ? c->obs_es.p : nullptr;
     c->cur_obs_R = R;
     c->cur_ident = nullptr;
     c->null_exact_near_obs = c->cur_obs != nullptr;
-    c->cur_exact_all = small_problem(c, es_kind, std::max<long long>(C, (long long)R * c->opt_nperm_total));
+    c->cur_exact_all = small_problem(c, es_kind, std::max<long long>(C_total, (long long)R * c->opt_nperm_total));
     if (c->cur_exact_all) c->null_exact_near_obs = true;
     if (C == 0) return FGS_OK;
-    FGS_TRY(flags_reset(c, C));
+    if (perm_off == 0) FGS_TRY(flags_reset(c, C_total));
+    int *const d_flags = c->flags.p + col0;
     FGS_CUDA(cudaEventRecord(c->ev[0], c->stream));
     StageTimer tm(c);
     // Blocks of score columns stream in: block k+1 is uploaded on copy_stream into the second
@@ -1091,19 +1129,19 @@ int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scor
       const int slot = (int)(k & 1);
       tm.mark();
       FGS_CUDA(cudaStreamWaitEvent(c->stream, c->blk_copy[slot], 0));
-      FGS_TRY(launch_check_finite(c, c->scores.p, (long long)n_gene * Cb, n_gene, c->flags.p + c0));
+      FGS_TRY(launch_check_finite(c, c->scores.p, (long long)n_gene * Cb, n_gene, d_flags + c0));
       tm.mark();
-      FGS_TRY(rank_and_es(c, es_kind, p_exp, 0, Cb, c->es_null.p + (size_t)c0 * S, tm));
+      FGS_TRY(rank_and_es(c, es_kind, p_exp, 0, Cb, d_null + (size_t)c0 * S, tm));
       if (c->progress && k >= 2) FGS_CUDA(cudaEventSynchronize(c->blk_done[slot]));
       FGS_CUDA(cudaEventRecord(c->blk_done[slot], c->stream));
       if (es_out) FGS_CUDA(cudaEventRecord(c->blk_out[slot], c->stream));
       if (k + 1 < n_blk) FGS_TRY(upload(k + 1, c->scores2.p));
       if (es_out && k > 0) {  // results of block k-1 go back while block k is computed
         const size_t o = (size_t)(c0 - Cb_max) * S;
-        FGS_TRY(download_block(c, slot ^ 1, es_out + o, c->es_null.p + o, (size_t)Cb_max * S));
+        FGS_TRY(download_block(c, slot ^ 1, es_out + o, d_null + o, (size_t)Cb_max * S));
       }
       if (es_out && k + 1 == n_blk)
-        FGS_TRY(download_block(c, slot, es_out + (size_t)c0 * S, c->es_null.p + (size_t)c0 * S, (size_t)Cb * S));
+        FGS_TRY(download_block(c, slot, es_out + (size_t)c0 * S, d_null + (size_t)c0 * S, (size_t)Cb * S));
       if (c->progress && c->progress(c->progress_user, std::min(C, std::max<long long>(0, k - 1) * Cb_max), C) != 0) {
         set_error("stopped by the progress callback");
         brc = FGS_ERR_CANCELLED;
@@ -1113,7 +1151,8 @@ int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scor
     c->cur_exact_all = false;
     if (brc != FGS_OK) { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream); return brc; }
     FGS_CUDA(cudaEventRecord(c->ev[1], c->stream));
-    int r2 = flags_check(c, C);
+    if (async) { tm.drop(); return FGS_OK; }   // fgs_null_finish waits and checks the flags
+    int r2 = flags_check(c, C_total);
     tm.finish(0.f);
     if (cudaEventSynchronize(c->ev[1]) == cudaSuccess) cudaEventElapsedTime(&c->last_ms[4], c->ev[0], c->ev[1]);
     if (r2 != FGS_OK) return r2;
@@ -1122,6 +1161,44 @@ int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scor
   rc = body();
   c->G = saveG;
   return rc;
+}
+
+int fgs_es_from_scores(fgs_ctx *c, int es_kind, double p_exp, const double *scores, int n_gene,
+                       int n_response, int n_perm, double *es_out) {
+  if (!c) return FGS_ERR_ARG;
+  FGS_TRY(settle_tile(c));
+  return es_from_scores_impl(c, es_kind, p_exp, scores, n_gene, n_response, n_perm, 0, n_perm, es_out, false);
+}
+
+int fgs_es_from_scores_tile(fgs_ctx *c, int es_kind, double p_exp, const double *scores, int n_gene,
+                            int n_response, int n_perm_tile, long long perm_offset, long long n_perm_total) {
+  if (!c) return FGS_ERR_ARG;
+  if (n_perm_total > INT_MAX) { set_error("too many permutations"); return FGS_ERR_ARG; }
+  // the previous tile must be through (its buffer is the caller's again from here on) ...
+  FGS_TRY(settle_tile(c));
+  // ... and this one is uploaded, ranked and scored by a helper thread while the caller scores the next:
+  // even the staging copy out of the caller's pageable array is off the caller's critical path
+  c->tile_rc = FGS_OK;
+  c->tile_job = std::thread([=]() {
+    const int rc = es_from_scores_impl(c, es_kind, p_exp, scores, n_gene, n_response, n_perm_tile, perm_offset,
+                                       n_perm_total, nullptr, true);
+    if (rc != FGS_OK) { c->tile_rc = rc; c->tile_err = fgs_last_error(); }
+  });
+  return FGS_OK;
+}
+
+int fgs_null_finish(fgs_ctx *c, double *es_null_out) {
+  if (!c) return FGS_ERR_ARG;
+  FGS_TRY(use_device(c));   // (waits for the tile in flight)
+  if (c->null_S <= 0) { set_error("no resident null"); return FGS_ERR_STATE; }
+  const long long C_total = (long long)c->null_R * c->null_P;
+  FGS_CUDA(cudaStreamSynchronize(c->copy_stream));
+  FGS_TRY(flags_check(c, C_total));   // (synchronises the compute stream)
+  if (es_null_out) {
+    FGS_CUDA(cudaEventRecord(c->blk_out[0], c->stream));
+    FGS_TRY(download_block(c, 0, es_null_out, c->es_null.p, (size_t)c->null_S * C_total));
+  }
+  return FGS_OK;
 }
 
 int fgs_debug_last_scores(fgs_ctx *c, double *scores, int *rank, long long n_col) {
@@ -1196,6 +1273,7 @@ int fgs_observed_es(fgs_ctx *c, int es_kind, double p_exp, const double *scores,
       FGS_TRY(c->obs_es.ensure(SR));
       FGS_CUDA(cudaMemcpyAsync(c->obs_es.p, d_es.p, SR * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
       c->obs_S = S; c->obs_R = R; c->obs_valid = true; c->obs_kind = FGS_ES_WEIGHTED_KS;
+      c->obs_p = p_exp; c->obs_score_kind = c->pend_score_kind; c->obs_abs = c->pend_abs; c->pend_score_kind = -1;
       c->last_cols = R; c->last_G = G;
       FGS_TRY(d2h(c, max_es_at, d_mea.p, SR)); FGS_TRY(d2h(c, le_prop, d_lep.p, SR));
       FGS_TRY(d2h(c, le_first, d_lf.p, SR)); FGS_TRY(d2h(c, le_count, d_lc.p, SR));
@@ -1213,6 +1291,7 @@ int fgs_observed_es(fgs_ctx *c, int es_kind, double p_exp, const double *scores,
       FGS_TRY(c->obs_es.ensure(SR));
       FGS_CUDA(cudaMemcpyAsync(c->obs_es.p, d_es.p, SR * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
       c->obs_S = S; c->obs_R = R; c->obs_valid = true; c->obs_kind = es_kind;
+      c->obs_p = p_exp; c->obs_score_kind = c->pend_score_kind; c->obs_abs = c->pend_abs; c->pend_score_kind = -1;
     } else { set_error("unknown es_kind %d", es_kind); return FGS_ERR_ARG; }
     FGS_TRY(d2h(c, es, d_es.p, SR));
     return flags_check(c, R);
@@ -1231,6 +1310,7 @@ int fgs_set_observed_es(fgs_ctx *c, int es_kind, const double *es, int n_sets, i
   FGS_TRY(h2d(c, c->obs_es.p, es, SR));
   FGS_TRY(sync(c));
   c->obs_S = n_sets; c->obs_R = n_response; c->obs_kind = es_kind; c->obs_valid = true;
+  c->obs_score_kind = -1;   // made elsewhere: never copied into the null, only used to spot near-ties
   return FGS_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "flexgsea_b200.h"
@@ -88,6 +89,12 @@ struct fgs_ctx {
   int (*progress)(void *, long long, long long) = nullptr;
   void *progress_user = nullptr;
 
+  // fgs_es_from_scores_tile: the tile handed over last is uploaded, ranked and scored by this
+  // helper thread while the caller scores the next one; joined by the next call on the context
+  std::thread tile_job;
+  int tile_rc = 0;
+  std::string tile_err;
+
   // options
   int opt_perm_block = 0;      // 0 = auto
   int opt_force_generic = 0;
@@ -137,6 +144,11 @@ struct fgs_ctx {
   fgs::DevBuf<double> obs_es;      // [S x R]
   int obs_S = 0, obs_R = 0, obs_kind = -1;
   bool obs_valid = false;
+  // what the observed ES was made from: weight exponent, and -- when its scores came from
+  // fgs_score_observed of this context -- the score kind and abs flag (-1: unknown provenance)
+  double obs_p = 1.0;
+  int obs_score_kind = -1, obs_abs = 0;
+  int pend_score_kind = -1, pend_abs = 0;   // the last fgs_score_observed, until an observed pass takes it
   const double *cur_obs = nullptr;   // set by rank_and_es for the ES launches of the current call
   int cur_obs_R = 1;
   const int *cur_ident = nullptr;    // [Pb] label-preserving permutations of the current block (or NULL)
@@ -289,6 +301,7 @@ int launch_sig_finish(fgs_ctx *c, const double *d_nes, const long long *d_null_c
                       const long long *d_glob, int S, int abs_flag, double *d_fdr,
                       long long *d_fdr_counts, long long *d_glob_counts);
 
+int settle_tile(fgs_ctx *c);  // joins the tile in flight (fgs_es_from_scores_tile), reports its failure
 // collectives of the significance exchange on c->stream (fgs_multi.cu); no-ops without a communicator
 int comm_allgather_f64(fgs_ctx *c, const double *send, double *recv, size_t count);
 int comm_allreduce_i64(fgs_ctx *c, long long *buf, size_t count);

@@ -386,6 +386,40 @@ int fgs_group_es_from_scores(fgs_group *g, int es_kind, double p_exponent, const
   });
 }
 
+// A tile of user scores goes to the GPU(s) whose span of the permutations it falls into; the
+// calls only queue work (fgs_es_from_scores_tile), so the caller can go on scoring the next tile.
+int fgs_group_es_from_scores_tile(fgs_group *g, int es_kind, double p_exponent, const double *scores, int n_gene,
+                                  int n_response, int n_perm_tile, long long perm_offset, long long n_perm_total) {
+  if (!g || !scores || n_perm_tile < 0 || perm_offset < 0 || perm_offset + n_perm_tile > n_perm_total) return FGS_ERR_ARG;
+  const int N = (int)g->ctx.size();
+  // the previous tile's buffer is the caller's again when this call returns: every GPU is through with it
+  for (int r = 0; r < N; r++) FGS_TRY(settle_tile(g->ctx[r]));
+  for (int r = 0; r < N; r++) {
+    long long lo, hi;
+    span_of(n_perm_total, N, r, &lo, &hi);
+    const long long a = std::max(lo, perm_offset), b = std::min(hi, perm_offset + n_perm_tile);
+    if (a >= b) continue;
+    g->ctx[r]->opt_nperm_total = n_perm_total;
+    const int rc = fgs_es_from_scores_tile(g->ctx[r], es_kind, p_exponent,
+                                           scores + (size_t)(a - perm_offset) * n_response * n_gene, n_gene,
+                                           n_response, (int)(b - a), a - lo, hi - lo);
+    if (rc != FGS_OK) { g->err[r] = fgs_last_error(); set_error("GPU %d of %d: %s", r, N, g->err[r].c_str()); return rc; }
+  }
+  return FGS_OK;
+}
+
+int fgs_group_null_finish(fgs_group *g, double *es_null_out) {
+  if (!g) return FGS_ERR_ARG;
+  long long before = 0;
+  std::vector<long long> off(g->ctx.size());
+  for (size_t r = 0; r < g->ctx.size(); r++) { off[r] = before; before += g->ctx[r]->null_P; }
+  return g->each([&](int r, fgs_ctx *c) {
+    if (c->null_S <= 0) return (int)FGS_OK;   // a rank without permutations
+    double *out = es_null_out ? es_null_out + (size_t)off[r] * c->null_R * c->null_S : nullptr;
+    return fgs_null_finish(c, out);
+  });
+}
+
 int fgs_group_calc_sig(fgs_group *g, const double *es, int response, int split_p, int calc_nes, int abs_flag,
                        int exchange, double *p, double *p_high, double *p_low, double *nes, double *fdr,
                        double *fwer, long long *p_counts, long long *fdr_counts, long long *glob_counts) {

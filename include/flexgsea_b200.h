@@ -102,7 +102,12 @@ int fgs_score_observed(fgs_ctx *ctx, int score_kind, int abs_flag, double *score
  * every null unit that lands within rounding of it in the reference's own
  * operation order, so the `<=` / `>=` comparisons of flexgsea_calc_sig see the
  * ties the reference sees (label-preserving permutations, small universes).
- * Call it before the null loop, as flexgsea() does (:266-305). */
+ * Call it before the null loop, as flexgsea() does (:266-305).  When the scores
+ * are the ones fgs_score_observed just returned, fgs_perm_null with the same
+ * score kind, abs flag and exponent also copies the observed ES verbatim to
+ * the permutations that leave every class label in place; an observed ES of
+ * any other provenance (other scores, fgs_set_observed_es) is only used to
+ * spot the near-ties, never copied. */
 int fgs_observed_es(fgs_ctx *ctx, int es_kind, double p_exponent, const double *scores,
                     int n_gene, int n_response, double *es, double *max_es_at, double *le_prop,
                     int *running_es_at, double *running_es_pos, double *running_es_neg,
@@ -128,6 +133,23 @@ int fgs_perm_null(fgs_ctx *ctx, int score_kind, int es_kind, double p_exponent,
  * scores [n_gene, n_response, n_perm] (:393-394); ranking onward runs here. */
 int fgs_es_from_scores(fgs_ctx *ctx, int es_kind, double p_exponent, const double *scores,
                        int n_gene, int n_response, int n_perm, double *es_out);
+/* The same in tiles, for a gene.score.fn that is slow on the host (limma's
+ * moderated t, R/flexgsea_limma.R:15-31): the caller scores block.size
+ * permutations, hands the tile over and goes on scoring the next one while the
+ * device uploads, ranks and scores this one -- the call only queues the work.
+ * Tiles must be given in order from permutation 0 and cover [0, n_perm_total).
+ * A helper thread of the context takes the tile -- staging copy, upload and
+ * kernel launches -- so the call returns at once; `scores` [n_gene, n_response,
+ * n_perm_tile] must stay valid and unmodified until the NEXT call on this
+ * context returns (the next tile, fgs_null_finish, or any other entry point:
+ * each waits for the tile in flight first).  A failed tile is reported by that
+ * next call.  fgs_null_finish waits for the device, reports what the tiles found
+ * (FGS_ERR_NONFINITE like :400-402) and optionally copies es_null
+ * [S, R, n_perm_total] to the host; the null then is the resident one. */
+int fgs_es_from_scores_tile(fgs_ctx *ctx, int es_kind, double p_exponent, const double *scores,
+                            int n_gene, int n_response, int n_perm_tile, long long perm_offset,
+                            long long n_perm_total);
+int fgs_null_finish(fgs_ctx *ctx, double *es_null_out);
 /* debug / parity taps for the block most recently processed by fgs_perm_null
  * or fgs_es_from_scores when n_perm * R <= the internal block (tests only):
  * scores [G x C], rank (1-based descending, R/flexgsea.R:929-931) [G x C] */
@@ -253,6 +275,12 @@ int fgs_group_perm_null(fgs_group *g, int score_kind, int es_kind, double p_expo
                         double *es_null_out);
 int fgs_group_es_from_scores(fgs_group *g, int es_kind, double p_exponent, const double *scores,
                              int n_gene, int n_response, int n_perm, double *es_out);
+/* tiles of a user gene.score.fn (fgs_es_from_scores_tile): each goes to the GPU(s)
+ * whose span it falls into; fgs_group_null_finish waits for all of them */
+int fgs_group_es_from_scores_tile(fgs_group *g, int es_kind, double p_exponent,
+                                  const double *scores, int n_gene, int n_response,
+                                  int n_perm_tile, long long perm_offset, long long n_perm_total);
+int fgs_group_null_finish(fgs_group *g, double *es_null_out);
 int fgs_group_calc_sig(fgs_group *g, const double *es, int response, int split_p, int calc_nes,
                        int abs_flag, int exchange, double *p, double *p_high, double *p_low,
                        double *nes, double *fdr, double *fwer, long long *p_counts,

@@ -130,23 +130,30 @@ flexgsea_perm_native <- function(x, y, gene.sets, gene.names, nperm, block.size,
         es.null <- .fgs_call('_flexgsea_session_perm_null', st$sess, st$kind$score, st$kind$es, 1.0, abs,
                              perm, 0, as.integer(nperm), st$n.sets, st$want.null)
     } else {
-        # user-defined gene.score.fn: the R closure per permutation (:383-394), scores shipped once
+        # user-defined gene.score.fn (flexgsea_limma, say): the R closure per permutation
+        # (:383-394), in tiles of block.size permutations.  Handing a tile over only queues its
+        # upload, ranking and ES, so the GPUs work on tile k while R scores tile k + 1.
         t.x <- methods::is(x, 'EList')
         pass.t.x <- 't.x' %in% methods::formalArgs(gene.score.fn)
-        gene.scores <- array(NA_real_, c(length(gene.names), length(responses), nperm))
-        for (perm.i in seq_len(nperm)) {
-            y.perm <- y[perm[, perm.i], , drop=F]
-            for (a in setdiff(names(attributes(y)), c('dim', 'dimnames'))) {   # :385-392
-                attr(y.perm, a) <- attr(y, a)
+        for (tile.start in seq(1, nperm, by=block.size)) {
+            tile <- seq(tile.start, min(nperm, tile.start + block.size - 1))
+            gene.scores <- array(NA_real_, c(length(gene.names), length(responses), length(tile)))
+            for (k in seq_along(tile)) {
+                y.perm <- y[perm[, tile[k]], , drop=F]
+                for (a in setdiff(names(attributes(y)), c('dim', 'dimnames'))) {   # :385-392
+                    attr(y.perm, a) <- attr(y, a)
+                }
+                gene.scores[, , k] <- if (pass.t.x) gene.score.fn(x, y.perm, t.x=t.x, abs=abs)
+                                      else gene.score.fn(x, y.perm, abs=abs)
             }
-            gene.scores[, , perm.i] <- if (pass.t.x) gene.score.fn(x, y.perm, t.x=t.x, abs=abs)
-                                       else gene.score.fn(x, y.perm, abs=abs)
+            if (any(!is.finite(gene.scores))) {
+                stop("Gene scoring function returned NA or Inf.")   # :400-402
+            }
+            .fgs_call('_flexgsea_session_es_from_scores_tile', st$sess, st$kind$es, 1.0, gene.scores,
+                      tile.start - 1, as.numeric(nperm))
         }
-        if (any(!is.finite(gene.scores))) {
-            stop("Gene scoring function returned NA or Inf.")   # :400-402
-        }
-        es.null <- .fgs_call('_flexgsea_session_es_from_scores', st$sess, st$kind$es, 1.0, gene.scores,
-                             st$n.sets, st$want.null)
+        es.null <- .fgs_call('_flexgsea_session_null_finish', st$sess, st$n.sets, length(responses),
+                             as.integer(nperm), st$want.null)
     }
     if (length(es.null)) {
         dimnames(es.null) <- list(GeneSet=st$set.names, Response=responses, perm=NULL)   # :363-368

@@ -68,6 +68,15 @@ fgs_group *session_of(SEXP p) {
   return g;
 }
 
+// the tile a GPU helper thread is still reading (fgs_es_from_scores_tile): kept from R's collector
+// until the next tile or the finish has returned
+SEXP g_tile_in_flight = nullptr;
+void hold_tile(SEXP s) {
+  if (g_tile_in_flight) R_ReleaseObject(g_tile_in_flight);
+  g_tile_in_flight = s;
+  if (s) R_PreserveObject(s);
+}
+
 // the package-level context s2n_C() runs on (created on first use, lives as long as the DLL)
 fgs_ctx *g_s2n_ctx = nullptr;
 fgs_ctx *s2n_ctx() {
@@ -278,6 +287,38 @@ SEXP _flexgsea_session_es_from_scores(SEXP sess, SEXP es_kind, SEXP p_exp, SEXP 
   END_RCPP
 }
 
+// One tile of that loop: scores [G, R, B] of permutations perm_offset .. (0-based) out of nperm.
+// Only queues the work, so R goes on scoring the next tile while this one is uploaded, ranked
+// and scored; _flexgsea_session_null_finish waits and returns es.null (or a zero-length vector).
+SEXP _flexgsea_session_es_from_scores_tile(SEXP sess, SEXP es_kind, SEXP p_exp, SEXP scores, SEXP perm_offset,
+                                           SEXP nperm) {
+  BEGIN_RCPP
+  fgs_group *g = session_of(sess);
+  const int G = dim_of(scores, 0), R = dim_of(scores, 1), B = dim_of(scores, 2);
+  const int rc = fgs_group_es_from_scores_tile(g, Rf_asInteger(es_kind), Rf_asReal(p_exp), real_arg(scores, "scores"),
+                                               G, R, B, (long long)Rf_asReal(perm_offset), (long long)Rf_asReal(nperm));
+  hold_tile(rc == FGS_OK ? scores : nullptr);   // (the previous tile is through once the call has returned)
+  if (rc == FGS_ERR_CANCELLED) { Rf_onintr(); return R_NilValue; }
+  check(rc);
+  return R_NilValue;
+  END_RCPP
+}
+
+SEXP _flexgsea_session_null_finish(SEXP sess, SEXP n_sets, SEXP n_response, SEXP nperm, SEXP want_null) {
+  BEGIN_RCPP
+  fgs_group *g = session_of(sess);
+  const bool want = Rf_asLogical(want_null);
+  SEXP out = PROTECT(want ? Rf_alloc3DArray(REALSXP, Rf_asInteger(n_sets), Rf_asInteger(n_response), Rf_asInteger(nperm))
+                          : Rf_allocVector(REALSXP, 0));
+  const int rc = fgs_group_null_finish(g, want ? REAL(out) : nullptr);
+  hold_tile(nullptr);
+  if (rc == FGS_ERR_CANCELLED) { UNPROTECT(1); Rf_onintr(); return R_NilValue; }
+  check(rc);
+  UNPROTECT(1);
+  return out;
+  END_RCPP
+}
+
 // sig.fun(es[, r], es.null[, r, ]) on the null the GPUs hold (R/flexgsea.R:314-330): the columns
 // of flexgsea_calc_sig's tibble (:564-629) or of flexgsea_calc_sig_simple's (:544-547), in order
 SEXP _flexgsea_session_calc_sig(SEXP sess, SEXP esSEXP, SEXP response, SEXP split_p, SEXP calc_nes, SEXP abs) {
@@ -352,6 +393,8 @@ static const R_CallMethodDef CallEntries[] = {
     {"_flexgsea_session_observed_es", (DL_FUNC)&_flexgsea_session_observed_es, 7},
     {"_flexgsea_session_perm_null", (DL_FUNC)&_flexgsea_session_perm_null, 10},
     {"_flexgsea_session_es_from_scores", (DL_FUNC)&_flexgsea_session_es_from_scores, 6},
+    {"_flexgsea_session_es_from_scores_tile", (DL_FUNC)&_flexgsea_session_es_from_scores_tile, 6},
+    {"_flexgsea_session_null_finish", (DL_FUNC)&_flexgsea_session_null_finish, 5},
     {"_flexgsea_session_calc_sig", (DL_FUNC)&_flexgsea_session_calc_sig, 6},
     {"_flexgsea_session_set_null", (DL_FUNC)&_flexgsea_session_set_null, 2},
     {"_flexgsea_gmt_read", (DL_FUNC)&_flexgsea_gmt_read, 4},

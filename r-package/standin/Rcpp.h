@@ -63,6 +63,8 @@ SEXP R_MakeExternalPtr(void *p, SEXP tag, SEXP prot);
 void *R_ExternalPtrAddr(SEXP s);
 void R_ClearExternalPtr(SEXP s);
 void R_RegisterCFinalizerEx(SEXP s, void (*fin)(SEXP), Rboolean onexit);
+void R_PreserveObject(SEXP s);
+void R_ReleaseObject(SEXP s);
 Rboolean R_ToplevelExec(void (*fn)(void *), void *data);
 void R_CheckUserInterrupt(void);
 void Rf_onintr(void);

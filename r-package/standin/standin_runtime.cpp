@@ -101,6 +101,10 @@ SEXP R_MakeExternalPtr(void *p, SEXP, SEXP) { SEXP s = new SEXPREC(); s->type = 
 void *R_ExternalPtrAddr(SEXP s) { return s->ptr; }
 void R_ClearExternalPtr(SEXP s) { s->ptr = nullptr; }
 void R_RegisterCFinalizerEx(SEXP s, void (*fin)(SEXP), Rboolean) { s->fin = fin; }
+static int g_preserved = 0;
+void R_PreserveObject(SEXP) { g_preserved++; }
+void R_ReleaseObject(SEXP) { g_preserved--; }
+int standin_preserved(void) { return g_preserved; }
 void R_CheckUserInterrupt(void) { if (g_interrupt_pending) throw Unwind(); }
 Rboolean R_ToplevelExec(void (*fn)(void *), void *data) {
   try { fn(data); } catch (Unwind &) { return FALSE; }

@@ -1044,3 +1044,146 @@ def test_few_samples_many_genes_dedup_counts_identical(oracle, es_kind):
         assert np.abs(plain - null).max() <= ES_TOL
     finally:
         c.close()
+
+
+# ------------------------------------ f3: user score functions in tiles, EList, limma-style client
+def test_user_score_tiles_equal_one_shot(ctx, oracle):
+    """fgs_es_from_scores_tile + fgs_null_finish: the tiles of a user gene.score.fn give the null the
+    one-shot call gives, bit for bit, the resident null serves calc_sig, and a non-finite score in
+    any tile is reported at the finish with the reference's meaning (R/flexgsea.R:400-402)."""
+    rng = np.random.default_rng(71)
+    G, R, P, S = 3000, 2, 230, 150
+    off, idx = synth.gene_sets_csr(G, S, (10, 300), "loguniform", seed=72)
+    sc = rng.normal(size=(G, R, P))
+    sc[:, 0, 7] = np.round(sc[:, 0, 7], 1)                     # ties
+    ctx.set_gene_sets(off, idx)
+    one = ctx.es_from_scores(nat.ES_WEIGHTED_KS, sc)
+    for tile in (1, 37, 100, 230):
+        for t0 in range(0, P, tile):
+            ctx.es_from_scores_tile(nat.ES_WEIGHTED_KS, np.asfortranarray(sc[:, :, t0:t0 + tile]), t0, P)
+        got = ctx.null_finish()
+        assert np.array_equal(got, one, equal_nan=True), tile
+    es = rng.normal(size=S) * 0.3
+    a = ctx.calc_sig(es, 1)
+    ctx.set_null(one[:, 1, :])
+    b = ctx.calc_sig(es, 0)
+    assert np.array_equal(a["p_counts"], b["p_counts"]) and np.array_equal(a["fdr_counts"], b["fdr_counts"])
+    bad = sc.copy(); bad[5, 1, 200] = np.inf
+    for t0 in range(0, P, 100):
+        ctx.es_from_scores_tile(nat.ES_WEIGHTED_KS, np.asfortranarray(bad[:, :, t0:t0 + 100]), t0, P)
+    with pytest.raises(fg.NonFiniteScoreError):
+        ctx.null_finish()
+    with pytest.raises(fg.FlexgseaError):     # a tile out of order: the null was never started
+        ctx.set_gene_sets(off[:50], idx[:off[49]])
+        ctx.es_from_scores_tile(nat.ES_WEIGHTED_KS, np.asfortranarray(sc[:, :, 10:20]), 10, P)
+        ctx.null_finish()                     # (a failed tile is reported by the next call)
+
+
+def test_tiles_hide_the_device_behind_a_slow_host_score_fn(ctx):
+    """SURVEY 8f row 3 / VERDICT r1 item 8: a host score function that costs 5 ms per permutation
+    (limma's moderated t costs about that at 20,000 genes).  Handing tile k over only queues its
+    upload, ranking and ES, so that work runs while the host scores tile k + 1: at least 80 % of
+    the device / transfer time of the tiled run disappears behind the host function."""
+    import time
+    c = synth.CONFIGS["C5"]      # 60,000 transcripts, 20,000 sets: about 75 us of device / transfer work per column
+    G, S = c["G"], c["S"]
+    off, idx = synth.gene_sets_csr(G, S, c["sizes"], c["size_dist"], seed=1)
+    rng = np.random.default_rng(73)
+    P, tile = 320, 16
+    tiles = [np.asfortranarray(rng.normal(size=(G, 1, tile))) for _ in range(P // tile)]
+    ctx.set_gene_sets(off, idx)
+
+    def run(host_ms):
+        t_host = 0.0
+        t0 = time.perf_counter()
+        for k, sc in enumerate(tiles):
+            h0 = time.perf_counter()
+            while (time.perf_counter() - h0) * 1e3 < host_ms * tile:   # the host "scores" this tile
+                pass
+            t_host += time.perf_counter() - h0
+            ctx.es_from_scores_tile(nat.ES_WEIGHTED_KS, sc, k * tile, P)
+        ctx.null_finish(want_host=False)
+        return time.perf_counter() - t0, t_host
+
+    run(0.0)                                   # warm-up (allocations, first launches)
+    t_dev = min(run(0.0)[0] for _ in range(3))   # the tiled device / transfer work on its own
+    total, t_host = run(5.0)
+    exposed = total - t_host
+    hidden = 1.0 - exposed / t_dev
+    assert hidden >= 0.8, "device time %.1f ms, exposed %.1f ms of it (hidden %.0f %%)" % (
+        1e3 * t_dev, 1e3 * exposed, 100 * hidden)
+
+
+def test_flexgsea_with_elist_and_limma_style_client(ctx):
+    """x as a limma EList (t.x = TRUE, R/flexgsea.R:159-173) with the limma adaptor as
+    gene.score.fn (R/flexgsea_limma.R:15-31): moderated-t columns are made on the host per
+    permutation, shipped in tiles of block.size, ranked and scored on the device; the result is
+    the one the untiled user-score path gives, and the built-in lm scores on the same EList use
+    the transposed layout."""
+    rng = np.random.default_rng(75)
+    G, n, S = 1200, 18, 60
+    names = ["g%d" % i for i in range(G)]
+    off, idx = synth.gene_sets_csr(G, S, (10, 120), "loguniform", seed=76)
+    sets = {"s%d" % k: [names[i - 1] for i in idx[off[k]:off[k + 1]]] for k in range(S)}
+    E = rng.normal(size=(G, n)) + rng.uniform(4, 12, size=(G, 1))
+    el = fg.EList(E, genes=names, weights=rng.uniform(0.5, 2.0, size=(G, n)))
+    D = np.column_stack([np.ones(n), rng.normal(size=n), (np.arange(n) % 2).astype(float)])
+    mm = fg.ModelMatrix(D, ["(Intercept)", "dose", "batch"])
+    kw = dict(gene_score_fn=fg.flexgsea_limma, nperm=90, gs_size_min=1, gs_size_max=500, verbose=False,
+              seed=5, rng="R", return_values=["es_null"])
+    a = fg.flexgsea(el, mm, sets, block_size=25, **kw)         # four tiles
+    b = fg.flexgsea(el, mm, sets, block_size=1000, **kw)       # one tile
+    assert list(a["table"]) == ["dose", "batch"]
+    assert np.array_equal(a["es_null"], b["es_null"], equal_nan=True)
+    for r in ("dose", "batch"):
+        for col in ("es", "p", "nes", "fdr"):
+            assert np.array_equal(np.asarray(a["table"][r][col]), np.asarray(b["table"][r][col]), equal_nan=True)
+    # the observed moderated t drives the observed ES: same as scoring the EList directly
+    t_obs = fg.flexgsea_limma(el, mm).to_numpy()
+    ctx.set_gene_sets(off, idx)
+    es = ctx.observed_es(nat.ES_WEIGHTED_KS, t_obs, ragged=False)["es"]
+    assert np.allclose(np.asarray(a["table"]["dose"]["es"]), es[:, 0], rtol=0, atol=1e-12)
+    # built-in lm on an EList: genes x samples is transposed for the device
+    c = fg.flexgsea(el, mm, sets, gene_score_fn=fg.flexgsea_lm, nperm=40, gs_size_min=1, gs_size_max=500,
+                    verbose=False, seed=6)
+    d = fg.flexgsea(E.T, mm, sets, gene_names=names, gene_score_fn=fg.flexgsea_lm, nperm=40, gs_size_min=1,
+                    gs_size_max=500, verbose=False, seed=6)
+    assert np.array_equal(np.asarray(c["table"]["dose"]["fdr"]), np.asarray(d["table"]["dose"]["fdr"]))
+
+
+def test_custom_es_fn_plugin_with_default_arguments(ctx):
+    """a user-defined es.fn record (list(run, prepare, extra_stats, extra),
+    R/flexgsea.R:60-93) with a built-in gene.score.fn and the default rng: the host plugin loop
+    needs the permutations themselves."""
+    G, n, S = 300, 12, 8
+    off, idx = synth.gene_sets_csr(G, S, (5, 30), "uniform", seed=81)
+    x, y = synth.two_class(G, n, off, idx, seed=82)
+    names = ["g%d" % i for i in range(G)]
+    sets = {"s%d" % k: [names[i - 1] for i in idx[off[k]:off[k + 1]]] for k in range(S)}
+    mean_fn = {"prepare": lambda gs: {}, "extra_stats": (), "extra": (),
+               "run": lambda gs, gene_set, prep, return_stats=(), return_values=(): {
+                   "es": gs[np.asarray(gene_set) - 1].mean(axis=0)}}
+    a = fg.flexgsea(x, y[:, 0], sets, es_fn=mean_fn, gene_names=names, nperm=50, gs_size_min=1, verbose=False, seed=3)
+    b = fg.flexgsea(x, y[:, 0], sets, es_fn=fg.flexgsea_mean, gene_names=names, nperm=50, gs_size_min=1,
+                    verbose=False, seed=3, rng="R")
+    ta, tb = a["table"]["Response 1"], b["table"]["Response 1"]
+    assert np.allclose(np.asarray(ta["es"]), np.asarray(tb["es"]), rtol=0, atol=1e-12)
+    assert np.array_equal(np.asarray(ta["p"]), np.asarray(tb["p"]))
+
+
+def test_observed_es_is_copied_only_when_it_belongs_to_the_null(ctx, oracle):
+    """label-preserving permutations get the observed ES copied verbatim -- but only an
+    observed ES made from fgs_score_observed with the null loop's score kind, abs flag and weight
+    exponent.  With few samples (many such permutations) an observed pass with abs = TRUE must not
+    leak into a signed null."""
+    x, y, perm, off, idx = _case(G=400, n=6, S=30, P=300, sizes=(5, 40), seed=91)
+    ctx.set_option("dedup_labels", 0)
+    try:
+        ctx.set_x(x); ctx.set_gene_sets(off, idx); ctx.set_response_s2n(y)
+        sc_abs = ctx.score_observed(nat.SCORE_S2N, True)
+        ctx.observed_es(nat.ES_WEIGHTED_KS, sc_abs, ragged=False)      # |scores|: not the signed null's observed ES
+        got = ctx.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, perm.shape[1], perm=perm, abs_flag=False)
+    finally:
+        ctx.set_option("dedup_labels", 1)
+    rc, want = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, oracle.ES_WKS)
+    assert rc == 0 and np.abs(got - want).max() <= ES_TOL

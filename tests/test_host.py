@@ -188,3 +188,25 @@ def test_sharding_collectives_gloo_world2(tmp_path):
                               stderr=subprocess.STDOUT) for r in range(2)]
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_limma_style_client_on_the_host():
+    """flexgsea_limma (R/flexgsea_limma.R:15-31) in the plugin position: drops the intercept column,
+    takes |t| with abs, needs a model matrix, and shrinks towards the ordinary t statistic."""
+    rng = np.random.default_rng(3)
+    G, n = 400, 14
+    E = rng.normal(size=(G, n))
+    D = np.column_stack([np.ones(n), rng.normal(size=n)])
+    mm = fg.ModelMatrix(D, ["(Intercept)", "dose"])
+    t = fg.flexgsea_limma(fg.EList(E, genes=["g%d" % i for i in range(G)]), mm)
+    assert list(t.columns) == ["dose"] and t.shape == (G, 1) and np.isfinite(t.to_numpy()).all()
+    assert np.array_equal(fg.flexgsea_limma(E, mm, abs=True).to_numpy(), np.abs(t.to_numpy()))
+    beta = np.linalg.lstsq(D, E.T, rcond=None)[0].T
+    res = E - beta @ D.T
+    tord = beta[:, 1] / np.sqrt(np.linalg.inv(D.T @ D)[1, 1] * (res ** 2).sum(1) / (n - 2))
+    assert np.corrcoef(tord, t.to_numpy()[:, 0])[0, 1] > 0.95
+    assert np.abs(t.to_numpy()[:, 0]).max() <= np.abs(tord).max() * 1.5   # moderated: extremes pulled in
+    with pytest.raises(ValueError):
+        fg.flexgsea_limma(E, D)
+    assert api._call_score(lambda x, y, t_x=False, abs=False: t_x, None, None, True, False) is True
+    assert api._call_score(lambda x, y, abs=False: "no t_x", None, None, True, False) == "no t_x"

@@ -38,7 +38,8 @@ def test_every_call_site_in_the_R_file_matches_a_registered_arity(shim):
         assert reg[name] == nargs, "%s: R passes %d arguments, the routine takes %d" % (name, nargs, reg[name])
     called = {n for n, _ in sites}
     # everything registered is reachable from R (s2n_C through the reference's own R/RcppExports.R:4-6)
-    assert set(reg) - called <= {"_flexgsea_s2n_C", "_flexgsea_session_score_observed_n", "_flexgsea_session_set_null"}
+    assert set(reg) - called <= {"_flexgsea_s2n_C", "_flexgsea_session_score_observed_n", "_flexgsea_session_set_null",
+                                 "_flexgsea_session_es_from_scores"}
 
 
 def test_wrong_arity_and_unknown_routine_are_errors_like_in_R(shim):
@@ -169,5 +170,12 @@ def test_elist_layout_and_user_scores_through_dot_call(shim, oracle):
             got = shim.call("_flexgsea_session_es_from_scores", sess, 0, 1.0, sc, S, True)
             rc, want = oracle.es_from_scores(oracle.ES_WKS, sc, off, idx)
             assert rc == 0 and got.shape == (S, 2, 30) and np.abs(got - want).max() <= 1e-10
+            # ... and in tiles of block.size, as flexgsea_perm_native hands them over
+            for t0 in range(0, 30, 8):
+                shim.call("_flexgsea_session_es_from_scores_tile", sess, 0, 1.0, np.asfortranarray(sc[:, :, t0:t0 + 8]),
+                          float(t0), 30.0)
+                assert shim.L.standin_preserved() == 1          # the tile in flight is kept from the collector
+            tiled = shim.call("_flexgsea_session_null_finish", sess, S, 2, 30, True)
+            assert shim.L.standin_preserved() == 0 and np.array_equal(tiled, got)
         shim.call("_flexgsea_session_close", sess)
     assert np.array_equal(res[0], res[1])
