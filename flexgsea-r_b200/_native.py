@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflexgsea_b200.so")
+# (FLEXGSEA_B200_LIB: a differently built copy of the library, for the kernel experiments of profiles/)
+LIB_PATH = os.environ.get("FLEXGSEA_B200_LIB") or os.path.join(_HERE, "libflexgsea_b200.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_NONFINITE, ERR_OOM, ERR_STATE, ERR_UNSUPPORTED, ERR_CANCELLED, ERR_COMM = range(9)
 COMM_ID_BYTES = 128

@@ -67,7 +67,14 @@ __device__ __forceinline__ uint32_t sort_halves(uint32_t v) { return max(v, swap
 // cross-lane comparator: `hi_mask` is 0 on the lane that keeps the minimum and
 // ~0 on the lane that keeps the maximum
 __device__ __forceinline__ uint32_t minmax2_side(uint32_t a, uint32_t o, uint32_t hi_mask) {
+#ifdef FGS_ES_XORCMP
+  // experiment r2-E1 (profiles/README.md): min, then max = a ^ o ^ min on the lanes that keep the
+  // maximum -- VIMNMX + two LOP3 instead of two predicated VIMNMX + moves
+  const uint32_t t = __vminu2(a, o);
+  return t ^ ((a ^ o) & hi_mask);
+#else
   return hi_mask ? __vmaxu2(a, o) : __vminu2(a, o);
+#endif
 }
 
 //
@@ -472,7 +479,13 @@ __global__ void build_idx16_kernel(const int4 *__restrict__ set_info, const int 
     // two members per lane; key = (class, position) is unique, pads sort last
     const int j0 = c0 + lane, j1 = c0 + 32 + lane;
     const int g0 = j0 < m ? set_idx[info.x + j0] : G, g1 = j1 < m ? set_idx[info.x + j1] : G;
+#ifdef FGS_ES_RANKBANK
+    // experiment r2-E2: order by the bank of the uint16 rank array ((g >> 1) & 31) instead of the
+    // bank pair of the fp64 score column (what the maxmean / mean kernel gathers)
+    const int key0 = ((j0 < m ? ((g0 >> 1) & 31) : 32) << 8) | lane, key1 = ((j1 < m ? ((g1 >> 1) & 31) : 32) << 8) | (32 + lane);
+#else
     const int key0 = ((j0 < m ? (g0 & 15) : 16) << 8) | lane, key1 = ((j1 < m ? (g1 & 15) : 16) << 8) | (32 + lane);
+#endif
     int p0 = 0, p1 = 0;
     for (int f = 0; f < 32; f++) {
       const int a = __shfl_sync(0xffffffffu, key0, f), b = __shfl_sync(0xffffffffu, key1, f);
