@@ -429,6 +429,100 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_gpu_group(args):
+    """`python bench.py --gpus N` WITHOUT torchrun: one process, N GPUs through the library's group of
+    contexts (fgs_group_*: one host thread per GPU, ncclCommInitAll) -- the path R's `parallel = N`
+    binds.  Same step (sharded null loop + significance with the NCCL exchange), same fields."""
+    import flexgsea_r_b200 as fg
+    from flexgsea_r_b200 import _native as nat, synth
+    N = args.gpus
+    c, x, resp, icpt, off, idx = workload(args.config)
+    G, n, S, P = c["G"], c["n"], c["S"], c["P"]
+    if args.perms:
+        P = args.perms
+    _, score_name, es_name = KINDS[args.config]
+    score_kind = nat.SCORE_LM if score_name == "lm" else nat.SCORE_S2N
+    es_kind = {"wks": nat.ES_WEIGHTED_KS, "maxmean": nat.ES_MAXMEAN, "mean": nat.ES_MEAN}[es_name]
+    grp = nat.Group(N)
+
+    def upload(xh, rh, oh, ih):
+        grp.set_x(xh); grp.set_gene_sets(oh, ih)
+        if score_kind == nat.SCORE_LM:
+            grp.set_response_lm(rh, icpt)
+        else:
+            grp.set_response_s2n(rh)
+
+    upload(x, resp, off, idx)
+    R = grp.n_response(score_kind)
+    seed = 20261019
+    sc_obs = grp.score_observed(score_kind)
+    es_obs = grp.observed_es(es_kind, sc_obs, ragged=False)["es"]
+
+    def step():
+        grp.perm_null(score_kind, es_kind, P, perm=None, seed=seed, want_host=False)
+        coll = 0.0
+        for r in range(R):
+            sig = grp.calc_sig(es_obs[:, r], r, True, True, False, exchange=args.exchange)
+            coll += grp.last_timings()["collectives"]
+        t = grp.last_timings()
+        return t["step"], t["null"], coll, sig
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = sum(cx.launch_count() for cx in grp.ctx)
+    dev_ms = null_ms = coll_ms = 0.0
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        st, nl, cl, sig = step()
+        dev_ms += st; null_ms += nl; coll_ms += cl
+    wall_ms = 1e3 * (time.perf_counter() - w0)
+    launches = sum(cx.launch_count() for cx in grp.ctx) - l0
+    clocks = sampler.stop()
+    assert np.isfinite(sig["fdr"]).all()
+    perm_h = synth.perm_matrix(n, P, seed=4) if P * n <= 4e7 else None
+    import torch  # pinned host buffers only
+    xp, _k1 = pinned(x); rp, _k2 = pinned(resp); offp, _k4 = pinned(off); idxp, _k5 = pinned(idx)
+    pp = pinned(perm_h)[0] if perm_h is not None else None
+
+    def e2e_step():
+        upload(xp, rp, offp, idxp)
+        sc = grp.score_observed(score_kind)
+        obs = grp.observed_es(es_kind, sc, ragged=False)
+        grp.perm_null(score_kind, es_kind, P, perm=pp, seed=seed, want_host=False)
+        return [grp.calc_sig(obs["es"][:, r], r, True, True, False, exchange=args.exchange) for r in range(R)]
+
+    e2e_step()
+    e0 = time.perf_counter()
+    e_steps = max(1, min(args.steps, 3))
+    for _ in range(e_steps):
+        e2e_step()
+    e2e_s = (time.perf_counter() - e0) / e_steps
+    nnz = int(off[-1])
+    h2d = N * (x.nbytes + resp.nbytes + 4 * (S + 1 + nnz) + 8 * G * R + 8 * S * R) + (4 * n * P if pp is not None else 0)
+    d2h = 8 * G * R + S * R * (8 * 3 + 4 * 2) + R * (S * (6 * 8 + 4 * 8) + 32)
+    print(json.dumps({
+        "metric": "gene-set x permutation ES/sec (null loop + significance)", "value": float(S) * R * P * args.steps / (dev_ms / 1e3),
+        "unit": "ES/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_TEXT[args.config], "nperm": P, "genes": G, "samples": n, "gene_sets": S,
+                   "nnz": nnz, "responses": R, "seeds": {"sets": 1, "x": 2, "philox": seed},
+                   "sharding": "ONE process, %d GPUs through fgs_group_* (one host thread per GPU, ncclCommInitAll): "
+                               "GPU g takes permutations [g*P/N, (g+1)*P/N); NCCL exchange inside the library" % N,
+                   "l2": "inputs larger than L2: every block streams far more than 126 MB of scores/ranks/weights"},
+        "timed_region": "max over the GPUs of (first kernel of the null loop -> last of the significance), CUDA events",
+        "null_loop_ms_per_step": null_ms / args.steps, "collective_ms_per_step": coll_ms / args.steps,
+        "wall_ms_per_step": wall_ms / args.steps,
+        "e2e": {"value": float(S) * R * P / e2e_s, "unit": "ES/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
+                "what": "the fgs_group_* calls of one flexgsea(parallel = N): uploads to every GPU, observed pass, "
+                        "sharded null loop (host permutation matrix), significance with the NCCL exchange"},
+        "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None, "clocks": clocks,
+    }))
+    grp.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -446,6 +540,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.gpus > 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        run_gpu_group(args)      # no torchrun: one process drives the N GPUs (what R's parallel = N does)
     else:
         run_gpu(args)
 

@@ -106,6 +106,7 @@ struct fgs_ctx {
   int opt_cert_cap = 4 << 20;  // entries per certification list (epilogue list, tie list)
   int opt_score_ppt = 0;
   long long opt_nperm_total = 0;  // permutations over ALL ranks when the caller shards them (0: this call's)
+  int opt_arrange = 1;         // member blocks dealt out by bank for the maxmean / mean gathers (arrange_idx16_kernel)
   int opt_tail_split = 1;      // split the columns of a partial last round over the idle SMs (ES kernels)
 
   // expression matrix x [n x G] (gene's samples contiguous)

@@ -497,6 +497,108 @@ __global__ void build_idx16_kernel(const int4 *__restrict__ set_info, const int 
   }
 }
 
+// The same member blocks, arranged for the bank structure of es_mean_smem_kernel's gathers.
+//
+// That kernel reads the fp64 score column by gene id, eight lanes per set and two sets per half
+// warp: the load of step t = 8 b + j takes, from lane ls of a set, the member at position
+// (8 b + ls) * 8 + j.  A half-warp's sixteen 8-byte reads are one shared-memory wavefront only if
+// they fall into sixteen different bank pairs, i.e. the sixteen gene ids differ mod 16.  The
+// order of a set's members is free (sums do not care) and fixed for all columns, so it is chosen
+// here, for the two sets of a pair together: at every step the sixteen residues are dealt out,
+// eight to each set -- a residue goes to the set that has more members of it left -- and each
+// lane takes an unused member of its residue.  That covers the rounds in which all sixteen lanes
+// hold members (64 members of each set per round); what is left over (unequal class sizes, the
+// ragged end, pads) fills the remaining positions in any order.  A warp per pair of sets
+// (2 u, 2 u + 1 in processing order: the pairs es_mean_smem_kernel puts on one half-warp).
+constexpr int ARR_MAX = 4096;  // members of a pair the scratch holds; larger pairs keep build_idx16_kernel's order
+__global__ void __launch_bounds__(256)
+arrange_idx16_kernel(const int4 *__restrict__ set_info, const int *__restrict__ set_idx, int S, int G,
+                     uint16_t *__restrict__ idx16) {
+  extern __shared__ uint16_t arr_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (2 * u >= S) return;
+  uint16_t *cls = arr_smem + (size_t)warp * ARR_MAX;   // members grouped by residue: set A's classes, then set B's
+  const int kA = 2 * u, kB = 2 * u + 1;
+  const int4 iA = set_info[kA];
+  const int4 iB = kB < S ? set_info[kB] : make_int4(0, 0, 0, 0);
+  const int mA = iA.y & 0x7fffffff, mB = iB.y & 0x7fffffff;
+  // rounds in which every lane of both sets holds members (a lone last set: its own rounds)
+  const int rounds = kB < S ? min(mA, mB) / 64 : mA / 64;
+  // the scratch holds both sets' members and, per set, the positions it could not fill (at most
+  // the dealt region); pairs that do not fit keep build_idx16_kernel's order
+  if (mA + mB + 2 * rounds * 64 > ARR_MAX) return;
+  // this lane's class: lanes 0..15 = residues of A, 16..31 = residues of B
+  const bool isB = lane >= 16;
+  const int r = lane & 15;
+  const int m_mine = isB ? mB : mA, off_mine = isB ? iB.x : iA.x;
+  // class sizes and starts (each lane counts its own class; sets are a few hundred members)
+  int cnt = 0;
+  for (int j = 0; j < m_mine; j++) cnt += (set_idx[off_mine + j] & 15) == r;
+  int start = cnt;  // exclusive prefix over the 16 classes of the lane's set
+  for (int d = 1; d < 16; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, start, d, 16);
+    if (r >= d) start += t;
+  }
+  start -= cnt;
+  if (isB) start += mA;
+  for (int j = 0, at = start; j < m_mine; j++) {
+    const int g = set_idx[off_mine + j];
+    if ((g & 15) == r) cls[at++] = (uint16_t)g;
+  }
+  __syncwarp();
+  uint16_t *outA = idx16 + (size_t)iA.z * 8, *outB = idx16 + (size_t)iB.z * 8;
+  uint16_t *out_mine = isB ? outB : outA;
+  int used = 0;                      // members of this lane's class handed out so far
+  // holes: positions of the dealt region a set could not fill (its class had run out)
+  __shared__ int s_nhole[8][2];
+  int *nhole = s_nhole[warp];
+  if (lane < 2) nhole[lane] = 0;
+  __syncwarp();
+  uint16_t *holesA = cls + mA + mB;  // positions (uint16), kept behind the class lists
+  const int hole_cap = rounds * 64;
+  uint16_t *holesB = holesA + hole_cap;
+  for (int t = 0; t < rounds * 8; t++) {
+    const int b = t >> 3, j = t & 7;
+    const int other = __shfl_xor_sync(0xffffffffu, cnt - used, 16);  // the partner set's supply of this residue
+    const int d = isB ? other - (cnt - used) : (cnt - used) - other; // A's surplus of residue r (same on lanes r and r + 16)
+    int rank = 0;                                                     // rank of the residue by surplus, ties by index
+    for (int o = 0; o < 16; o++) {
+      const int dq = __shfl_sync(0xffffffffu, d, o);
+      rank += (dq > d) || (dq == d && o < r);
+    }
+    // A takes the eight residues it has most surplus of (its lane `rank`), B the others (its lane `rank - 8`)
+    const bool mine = isB ? rank >= 8 : rank < 8;
+    if (mine) {
+      const int ls = isB ? rank - 8 : rank;
+      const int pos = (b * 8 + ls) * 8 + j;
+      if (used < cnt) out_mine[pos] = cls[start + used++];
+      else if (m_mine > 0) (isB ? holesB : holesA)[atomicAdd(&nhole[isB], 1)] = (uint16_t)pos;
+    }
+  }
+  __syncwarp();
+  // the rest, in class order: first the holes of the dealt region, then the positions behind it; pads at the end
+  // exclusive prefix of the leftovers over the classes of each set
+  const int left = cnt - used;
+  int lstart = left;
+  for (int dd = 1; dd < 16; dd <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, lstart, dd, 16);
+    if (r >= dd) lstart += t;
+  }
+  lstart -= left;
+  const int nh = nhole[isB];
+  const uint16_t *holes_mine = isB ? holesB : holesA;
+  for (int i = 0; i < left; i++) {
+    const int q = lstart + i;          // index among the set's leftovers
+    const int pos = q < nh ? holes_mine[q] : rounds * 64 + (q - nh);
+    out_mine[pos] = cls[start + used + i];
+  }
+  __syncwarp();
+  // pads behind the last member
+  const int mpad = (m_mine + 7) & ~7;
+  if (r < mpad - m_mine) out_mine[m_mine + r] = (uint16_t)G;
+}
+
 // Order-free weighted KS for sets the bitonic kernel cannot take (duplicates,
 // > ES_MAX_SET members).  One warp per (set, column).  Ties in rank (duplicate
 // members) are ordered by member position, like R's stable order() (:822).
@@ -805,6 +907,13 @@ static int ensure_set_blocks(fgs_ctx *c, int G) {
   build_idx16_kernel<<<ceil_div(c->S, 8), 256, 0, c->stream>>>(c->set_info.p, c->set_idx.p, c->S, G,
                                                                c->set_idx16.p);
   c->launches += 2;
+  if (c->opt_arrange) {  // the bank-aware order for the maxmean / mean gathers (pairs of sets)
+    const size_t smem = (size_t)8 * ARR_MAX * sizeof(uint16_t);
+    FGS_CUDA(cudaFuncSetAttribute(arrange_idx16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    arrange_idx16_kernel<<<ceil_div((c->S + 1) / 2, 8), 256, smem, c->stream>>>(c->set_info.p, c->set_idx.p, c->S, G,
+                                                                                c->set_idx16.p);
+    c->launches++;
+  }
   FGS_CUDA(cudaGetLastError());
   c->invgm_G = G;
   return FGS_OK;

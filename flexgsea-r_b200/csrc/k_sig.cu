@@ -258,36 +258,38 @@ __global__ void scatter_sorted_kernel(const double *__restrict__ key, const int 
 //   #{v' > t_j} = sum_{b > j} hist1[b]
 // hist2[b] += 1 where b = #{thresholds2 <= v'}; set at sorted position j gets
 //   #{v' < t_j} = sum_{b <= j} hist2[b]
-// Coarse index over a sorted threshold list: FDR_NC equal cells between its
-// smallest and largest value, lut[c] = #{t < edge(c)} (or <=), so a value's count
-// is bracketed by lut[c], lut[c + 1] and the bisection that finishes the job runs
-// over a cell's population (about one threshold) instead of the whole list.
-constexpr int FDR_NC = 8192;
+// Cell index over the sorted threshold list: `nc` equal cells between its smallest and largest
+// value, lut[c] = #{t < edge(c)}, so a value's count is bracketed by lut[c], lut[c + 1].  With
+// cells far finer than the typical gap between thresholds (65 536 cells for 8 000 thresholds)
+// nearly every cell holds at most one threshold and the count is one comparison; fuller cells
+// finish with a bisection over the cell's population.  uint16 entries (n < 65 536).
+constexpr int FDR_NC_MAX = 65536, FDR_NC_MIN = 4096;
 __device__ __forceinline__ double lut_edge(double t0, double w, int c) { return __fma_rn((double)c, w, t0); }
-__global__ void fdr_lut_kernel(const double *__restrict__ t, int n, int upper, int *__restrict__ lut) {
+__global__ void fdr_lut_kernel(const double *__restrict__ t, int n, int nc, uint16_t *__restrict__ lut) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > FDR_NC) return;
+  if (c > nc) return;
   if (n <= 0) { lut[c] = 0; return; }
-  if (c == FDR_NC) { lut[c] = n; return; }
-  const double t0 = t[0], w = (t[n - 1] - t[0]) / FDR_NC;
+  if (c == nc) { lut[c] = (uint16_t)n; return; }
+  const double t0 = t[0], w = (t[n - 1] - t[0]) / nc;
   const double x = lut_edge(t0, w, c);
   int lo = 0, hi = n;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (upper ? (t[mid] <= x) : (t[mid] < x)) lo = mid + 1; else hi = mid;
+    if (t[mid] < x) lo = mid + 1; else hi = mid;
   }
-  lut[c] = lo;
+  lut[c] = (uint16_t)lo;
 }
 // #{t < v} (nonstrict = false) or #{t <= v} (nonstrict = true) through the cell index
-__device__ __forceinline__ int lut_count(const double *__restrict__ a, int n, const int *__restrict__ lut,
-                                         double t0, double w, double invw, double tmax, double v, bool nonstrict) {
+__device__ __forceinline__ int lut_count(const double *__restrict__ a, int n, const uint16_t *__restrict__ lut,
+                                         int nc, double t0, double w, double invw, double tmax, double v,
+                                         bool nonstrict) {
   if (n == 0 || v < t0) return 0;
   if (v > tmax) return n;
   int lo = 0, hi = n;
   if (w > 0.0 && w < INFINITY) {  // (a single distinct threshold or an infinite one: plain bisection)
-    int c = min(max((int)((v - t0) * invw), 0), FDR_NC - 1);
+    int c = min(max((int)((v - t0) * invw), 0), nc - 1);
     while (c > 0 && v < lut_edge(t0, w, c)) c--;                  // rounding of the cell guess
-    while (c < FDR_NC - 1 && v >= lut_edge(t0, w, c + 1)) c++;
+    while (c < nc - 1 && v >= lut_edge(t0, w, c + 1)) c++;
     lo = lut[c]; hi = lut[c + 1];    // #{t < edge(c)} <= either count <= #{t < edge(c + 1)}
   }
   while (lo < hi) {
@@ -315,19 +317,19 @@ __global__ void __launch_bounds__(T_SMEM ? FDR_T_SMEM : FDR_T_GLOBAL)
 fdr_count_kernel(const double *__restrict__ null, int S, int R, int P, int resp, int abs_flag,
                  const double *__restrict__ es, const double *__restrict__ mpos,
                  const double *__restrict__ mneg, const double *__restrict__ T, int n, int n2,
-                 const int *__restrict__ lut_g, int chunk_len, double snap_rel,
+                 const uint16_t *__restrict__ lut_g, int nc, int chunk_len, double snap_rel,
                  unsigned long long *__restrict__ hist, unsigned long long *__restrict__ glob) {
   extern __shared__ __align__(16) unsigned char smem[];
   double *st = (double *)smem;
   unsigned int *h = (unsigned int *)(st + (T_SMEM ? n : 0));
-  int *lut = (int *)(h + (n + 2));
+  uint16_t *lut = (uint16_t *)(h + (n + 2));
   for (int i = threadIdx.x; i < n + 2; i += blockDim.x) h[i] = 0;
-  for (int i = threadIdx.x; i < FDR_NC + 1; i += blockDim.x) lut[i] = lut_g[i];
+  for (int i = threadIdx.x; i < nc + 1; i += blockDim.x) lut[i] = lut_g[i];
   if (T_SMEM)
     for (int i = threadIdx.x; i < n; i += blockDim.x) st[i] = T[i];
   __syncthreads();
   const double *a = T_SMEM ? st : T;
-  const double t0 = n > 0 ? T[0] : 0.0, tmax = n > 0 ? T[n - 1] : 0.0, w = (tmax - t0) / FDR_NC;
+  const double t0 = n > 0 ? T[0] : 0.0, tmax = n > 0 ? T[n - 1] : 0.0, w = (tmax - t0) / nc;
   const double iw = w > 0.0 ? 1.0 / w : 0.0;
   const int p0 = blockIdx.y * chunk_len, p1 = min(P, p0 + chunk_len);
   // One streaming read of the null (8 S P bytes): U permutations in flight per thread.  The
@@ -351,14 +353,14 @@ fdr_count_kernel(const double *__restrict__ null, int S, int R, int P, int resp,
       for (int u = 0; u < U; u++) v[u] = (pb + u < p1) ? __ldg(base + stride * (pb + u)) : nan("");
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const double vs = snap_to_observed(v[u], e, snap_rel);
+        const double vs = snap_rel != 0.0 ? snap_to_observed(v[u], e, snap_rel) : v[u];
         const bool vneg = !(vs >= 0.0);
         double nv = vs * (vneg ? rneg : rpos);
         bool sure = isfinite(nv) && fabs(nv) > 1e-290;
         bool nonstrict = !abs_flag && nv < 0.0;   // a negative value undercuts: `<`, i.e. count T <= nv
         int B = 0;
         if (sure) {
-          B = lut_count(a, n, lut, t0, w, iw, tmax, nv, nonstrict);
+          B = lut_count(a, n, lut, nc, t0, w, iw, tmax, nv, nonstrict);
           const double d = FDR_APPROX_REL * fabs(nv);
           sure = (B == 0 || nv - a[B - 1] > d) && (B == n || a[B] - nv > d);
         }
@@ -366,7 +368,7 @@ fdr_count_kernel(const double *__restrict__ null, int S, int R, int P, int resp,
           nv = vs / (vneg ? dneg : dpos);
           if (isnan(nv)) continue;
           nonstrict = !abs_flag && nv < 0.0;
-          B = lut_count(a, n, lut, t0, w, iw, tmax, nv, nonstrict);
+          B = lut_count(a, n, lut, nc, t0, w, iw, tmax, nv, nonstrict);
         }
         lpos += nv > 0.0;                                                          // :503
         lneg += nv < 0.0;                                                          // :504
@@ -564,12 +566,18 @@ int launch_sig_stage2(fgs_ctx *c, const double *d_null, int S, int R, int P, int
   if (n1 > 0) FGS_CUDA(cudaMemcpyAsync(c->sig_t.p + n2, t1, (size_t)n1 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   unsigned long long *H = h1;   // [n12 + 2]: hist2 = H[0 .. n2], hist1 = H[n2 + 1 .. n12 + 1]
   if (P > 0) {
-    FGS_TRY(c->sig_lut.ensure((size_t)(FDR_NC + 1)));
-    fdr_lut_kernel<<<ceil_div(FDR_NC + 1, 256), 256, 0, c->stream>>>(c->sig_t.p, n12, 0, c->sig_lut.p);
+    if (n12 >= 65536) { set_error("pooled FDR over %d gene sets: more than the 65535 the cell index addresses", S); return FGS_ERR_UNSUPPORTED; }
+    // the finest cell index that still fits on chip next to the histogram (and the thresholds, when they fit too)
+    const size_t smem_hist = (size_t)(n12 + 2) * 4 + 16, smem_thr = (size_t)n12 * 8;
+    int nc = FDR_NC_MAX;
+    while (nc > FDR_NC_MIN && smem_hist + smem_thr + (size_t)(nc + 1) * 2 > (size_t)c->smem_optin) nc >>= 1;
+    const size_t smem_lut = (size_t)(nc + 1) * 2;
+    const size_t smem_h = smem_hist + smem_lut;                  // histogram + cell index
+    const size_t smem_t = smem_thr + smem_h;                     // + the thresholds themselves
+    FGS_TRY(c->sig_lut.ensure((size_t)(FDR_NC_MAX + 2) / 2 + 1));
+    uint16_t *d_lut = (uint16_t *)c->sig_lut.p;
+    fdr_lut_kernel<<<ceil_div(nc + 1, 256), 256, 0, c->stream>>>(c->sig_t.p, n12, nc, d_lut);
     c->launches += 1;
-    const size_t smem_lut = (size_t)(FDR_NC + 1) * 4;
-    const size_t smem_h = (size_t)(n12 + 2) * 4 + smem_lut;      // histogram + cell index
-    const size_t smem_t = (size_t)n12 * 8 + smem_h;              // + the thresholds themselves
     if (smem_h > (size_t)c->smem_optin) {
       // (about 50,000 gene sets: the per-CTA histogram no longer fits on chip)
       set_error("pooled FDR over %d gene sets needs %zu bytes of shared memory per CTA, %d available", S, smem_h,
@@ -590,12 +598,12 @@ int launch_sig_stage2(fgs_ctx *c, const double *d_null, int S, int R, int P, int
       auto k = fdr_count_kernel<true>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
       k<<<grid, threads, smem_t, c->stream>>>(d_null, S, R, P, response, abs_flag, d_es, d_mpos, d_mneg, c->sig_t.p,
-                                              n12, n2, c->sig_lut.p, chunk_len, snap, H, (unsigned long long *)d_glob);
+                                              n12, n2, d_lut, nc, chunk_len, snap, H, (unsigned long long *)d_glob);
     } else {
       auto k = fdr_count_kernel<false>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
       k<<<grid, threads, smem_h, c->stream>>>(d_null, S, R, P, response, abs_flag, d_es, d_mpos, d_mneg, c->sig_t.p,
-                                              n12, n2, c->sig_lut.p, chunk_len, snap, H, (unsigned long long *)d_glob);
+                                              n12, n2, d_lut, nc, chunk_len, snap, H, (unsigned long long *)d_glob);
     }
     c->launches++;
     FGS_CUDA(cudaGetLastError());
