@@ -1133,7 +1133,9 @@ static int es_from_scores_impl(fgs_ctx *c, int es_kind, double p_exp, const doub
       FGS_TRY(launch_check_finite(c, c->scores.p, (long long)n_gene * Cb, n_gene, d_flags + c0));
       tm.mark();
       FGS_TRY(rank_and_es(c, es_kind, p_exp, 0, Cb, d_null + (size_t)c0 * S, tm));
-      if (c->progress && k >= 2) FGS_CUDA(cudaEventSynchronize(c->blk_done[slot]));
+      // (no progress hook from a tile's helper thread: an R binding's hook must run on R's own thread)
+      const bool hook = c->progress && !async;
+      if (hook && k >= 2) FGS_CUDA(cudaEventSynchronize(c->blk_done[slot]));
       FGS_CUDA(cudaEventRecord(c->blk_done[slot], c->stream));
       if (es_out) FGS_CUDA(cudaEventRecord(c->blk_out[slot], c->stream));
       if (k + 1 < n_blk) FGS_TRY(upload(k + 1, c->scores2.p));
@@ -1143,7 +1145,7 @@ static int es_from_scores_impl(fgs_ctx *c, int es_kind, double p_exp, const doub
       }
       if (es_out && k + 1 == n_blk)
         FGS_TRY(download_block(c, slot, es_out + (size_t)c0 * S, d_null + (size_t)c0 * S, (size_t)Cb * S));
-      if (c->progress && c->progress(c->progress_user, std::min(C, std::max<long long>(0, k - 1) * Cb_max), C) != 0) {
+      if (hook && c->progress(c->progress_user, std::min(C, std::max<long long>(0, k - 1) * Cb_max), C) != 0) {
         set_error("stopped by the progress callback");
         brc = FGS_ERR_CANCELLED;
       }
