@@ -433,6 +433,7 @@ def run_gpu_group(args):
     """`python bench.py --gpus N` WITHOUT torchrun: one process, N GPUs through the library's group of
     contexts (fgs_group_*: one host thread per GPU, ncclCommInitAll) -- the path R's `parallel = N`
     binds.  Same step (sharded null loop + significance with the NCCL exchange), same fields."""
+    import torch  # first: the library binds whichever libnccl.so.2 the process already holds (torch's, here)
     import flexgsea_r_b200 as fg
     from flexgsea_r_b200 import _native as nat, synth
     N = args.gpus
@@ -482,7 +483,6 @@ def run_gpu_group(args):
     clocks = sampler.stop()
     assert np.isfinite(sig["fdr"]).all()
     perm_h = synth.perm_matrix(n, P, seed=4) if P * n <= 4e7 else None
-    import torch  # pinned host buffers only
     xp, _k1 = pinned(x); rp, _k2 = pinned(resp); offp, _k4 = pinned(off); idxp, _k5 = pinned(idx)
     pp = pinned(perm_h)[0] if perm_h is not None else None
 

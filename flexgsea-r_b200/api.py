@@ -93,7 +93,13 @@ def _y_matrix(y):
 
 
 def _binarise(y):
-    """flexgsea_s2n's y_bin (R/flexgsea.R:695-710) -> int32 [n x R], NA kept."""
+    """flexgsea_s2n's y_bin (R/flexgsea.R:695-710) -> int32 [n x R], NA kept.  A logical y has
+    classes c(TRUE, FALSE), a factor (pandas Categorical) its levels, anything else
+    sort(unique()) per response; class 1 -> TRUE."""
+    levels = None
+    if _pd is not None and isinstance(y, _pd.Series) and isinstance(y.dtype, _pd.CategoricalDtype):
+        levels = list(y.cat.categories)   # is.factor(y): classes = levels(y), :699-701
+        y = y.astype(object)
     vals, names = _y_matrix(y)
     n, R = vals.shape
     out = np.zeros((n, R), dtype=np.int32, order="F")
@@ -103,7 +109,7 @@ def _binarise(y):
             out[:, r] = col.astype(np.int32)  # classes = c(TRUE, FALSE)
             continue
         isna = np.array([v is None or (isinstance(v, float) and np.isnan(v)) for v in col.tolist()])
-        classes = sorted(set(np.asarray(col)[~isna].tolist()))  # sort(unique(phenotype))
+        classes = levels if levels is not None else sorted(set(np.asarray(col)[~isna].tolist()))  # sort(unique(phenotype))
         if len(classes) != 2:
             raise ValueError("length(classes) == 2 is not TRUE")  # stopifnot, :708
         b = np.array([v == classes[0] for v in col.tolist()], dtype=np.int32)

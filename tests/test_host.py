@@ -120,6 +120,12 @@ def test_binarise_like_flexgsea_s2n():
     assert yb[1, 0] == api.NA_LOGICAL
     with pytest.raises(ValueError):
         api._binarise(np.array([1, 2, 3]))
+    import pandas as pd
+    fac = pd.Series(pd.Categorical(["lo", "hi", "hi", "lo"], categories=["hi", "lo"]))
+    yb, _ = api._binarise(fac)
+    assert list(yb[:, 0]) == [0, 1, 1, 0]                            # a factor: class 1 = levels(y)[1] = 'hi'
+    fac2 = pd.Series(pd.Categorical(["lo", "hi", "hi", "lo"], categories=["lo", "hi"]))
+    assert list(api._binarise(fac2)[0][:, 0]) == [1, 0, 0, 1]
 
 
 def test_design_like_flexgsea_lm():
