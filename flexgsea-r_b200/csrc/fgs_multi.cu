@@ -11,6 +11,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -47,8 +48,12 @@ const NcclApi *nccl() {
   static std::once_flag once;
   std::call_once(once, [] {
     g_nccl.tried = true;
-    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    // FLEXGSEA_NCCL_LIB: an explicit copy (a process that will load a NEWER NCCL later -- torch's
+    // bundled one, say -- must either load that first or name it here: both answer to the soname
+    // libnccl.so.2 and the first one loaded serves everybody)
+    const char *names[] = {getenv("FLEXGSEA_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     for (const char *nm : names) {
+      if (!nm || !*nm) continue;
       g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
       if (g_nccl.handle) break;
     }
