@@ -527,7 +527,7 @@ int fgs_destroy(fgs_ctx *c) {
     for (int i = 0; i < 16; i++) if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
   }
   for (int i = 0; i < 8; i++) if (c->sig_ev[i]) cudaEventDestroy(c->sig_ev[i]);
-  c->null_full.release(); c->class_lists.release(); c->blk_ovf.release(); c->perm_map.release(); c->es_uniq.release(); c->dupclass.release(); c->sig_t.release();
+  c->null_full.release(); c->class_lists.release(); c->blk_ovf.release(); c->perm_map.release(); c->es_uniq.release(); c->dupclass.release(); c->sig_t.release(); c->inv_n1n2.release();
   cudaStreamDestroy(c->stream);
   delete c;
   return FGS_OK;
@@ -744,6 +744,10 @@ int fgs_set_response_s2n(fgs_ctx *c, const int *y_bin, int n_sample, int n_respo
   FGS_TRY(c->n1n2.ensure(2 * (size_t)n_response));
   FGS_TRY(h2d(c, c->ybin.p, y_bin, (size_t)n_sample * n_response));
   FGS_TRY(h2d(c, c->n1n2.p, nn.data(), nn.size()));
+  std::vector<double> inv(nn.size());
+  for (size_t i = 0; i < nn.size(); i++) inv[i] = 1.0 / (double)nn[i];
+  FGS_TRY(c->inv_n1n2.ensure(inv.size()));
+  FGS_TRY(h2d(c, c->inv_n1n2.p, inv.data(), inv.size()));
   FGS_TRY(sync(c));
   c->h_n1n2 = nn;
   c->s2n_n = n_sample;
@@ -803,7 +807,7 @@ static int score_block(fgs_ctx *c, int score_kind, const int *d_perm, const uint
       FGS_TRY(c->cert_list.ensure((size_t)2 * c->opt_cert_cap));
       FGS_TRY(c->cert_ctr.ensure(4));
       FGS_CUDA(cudaMemsetAsync(c->cert_ctr.p, 0, 4 * sizeof(int), c->stream));
-      FGS_TRY(launch_s2n_mma(c, c->xc.p, c->xtot.p, n, G, d_labels, c->n1n2.p, R, Cb, c->scores.p,
+      FGS_TRY(launch_s2n_mma(c, c->xc.p, c->xtot.p, n, G, d_labels, c->inv_n1n2.p, R, Cb, c->scores.p,
                              c->cert_list.p, c->cert_ctr.p, c->opt_cert_cap, c->cur_ovf));
       FGS_TRY(launch_s2n_exact_entries(c, c->x.p, n, G, d_labels, c->n1n2.p, R, c->cert_list.p,
                                        c->cert_ctr.p, c->opt_cert_cap, c->scores.p, c->flags.p + flag0, false,

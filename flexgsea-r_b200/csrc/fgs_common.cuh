@@ -177,6 +177,7 @@ struct fgs_ctx {
   long long cur_flag0 = 0;
   fgs::DevBuf<int> ybin;
   fgs::DevBuf<int> n1n2;  // [R][2]
+  fgs::DevBuf<double> inv_n1n2;  // [R][2] reciprocals (tensor-core score epilogue)
   // lm response
   int lm_q = 0, lm_R = 0, lm_icpt = 0;
   fgs::DevBuf<double> lm_H;  // [R x n] rows of R^-1 Q^T for the scored columns
@@ -259,7 +260,7 @@ int launch_sort(fgs_ctx *c, const double *d_scores, int G, long long C, int abs_
                 const TieCert *cert = nullptr);
 int launch_center(fgs_ctx *c, const double *d_x, int n, int G, double *d_xc, double *d_tot);
 int launch_s2n_mma(fgs_ctx *c, const double *d_xc, const double *d_tot, int n, int G,
-                   const uint32_t *d_labels, const int *d_n1n2, int R, long long C, double *d_scores,
+                   const uint32_t *d_labels, const double *d_inv_n, int R, long long C, double *d_scores,
                    int2 *d_list, int *d_count, int cap, int *d_overflow);
 int launch_mark_all_if(fgs_ctx *c, int *d_redo, long long C, const int *only_if, const int *unless);
 int launch_s2n_exact_entries(fgs_ctx *c, const double *d_x, int n, int G, const uint32_t *d_labels,

@@ -93,7 +93,7 @@ __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src, bool 
 //     builds the 1.0 / 0.0 operand from a bit (two integer instructions).
 __global__ void __launch_bounds__(256)
 s2n_mma_kernel(const double *__restrict__ xc, const double *__restrict__ tot, int n, int G,
-               const uint32_t *__restrict__ labels, const int *__restrict__ n1n2, int R, long long C,
+               const uint32_t *__restrict__ labels, const double *__restrict__ inv_n, int R, long long C,
                int W, double *__restrict__ scores, int2 *__restrict__ list, int *__restrict__ count,
                int cap, int *__restrict__ overflow) {
   __shared__ __align__(16) double As[2][SM_BG][SM_BK + SM_PAD];
@@ -178,8 +178,8 @@ s2n_mma_kernel(const double *__restrict__ xc, const double *__restrict__ tot, in
         const long long col = c0 + wn + j * 8 + 2 * tig + h;
         if (col >= C) continue;
         const int r = (int)(col % R);
-        // (reciprocal class sizes: the tensor path is certified to 1e-10, not bit-faithful)
-        const double in1 = 1.0 / (double)n1n2[2 * r], in2 = 1.0 / (double)n1n2[2 * r + 1];
+        // (reciprocal class sizes, made once per response: the tensor path is certified to 1e-10, not bit-faithful)
+        const double in1 = __ldg(inv_n + 2 * r), in2 = __ldg(inv_n + 2 * r + 1);
         const double s1 = acc[i][j][h], q1 = acc[i + 2][j][h];
         const double s2 = t1 - s1, q2 = t2 - q1;
         const double m1 = s1 * in1, m2 = s2 * in2;
@@ -198,11 +198,11 @@ s2n_mma_kernel(const double *__restrict__ xc, const double *__restrict__ tot, in
 }
 
 int launch_s2n_mma(fgs_ctx *c, const double *d_xc, const double *d_tot, int n, int G,
-                   const uint32_t *d_labels, const int *d_n1n2, int R, long long C, double *d_scores,
+                   const uint32_t *d_labels, const double *d_inv_n, int R, long long C, double *d_scores,
                    int2 *d_list, int *d_count, int cap, int *d_overflow) {
   if (C <= 0 || G <= 0) return FGS_OK;
   dim3 grid(ceil_div(G, SM_BG), ceil_div(C, SM_BN));
-  s2n_mma_kernel<<<grid, 256, 0, c->stream>>>(d_xc, d_tot, n, G, d_labels, d_n1n2, R, C, (n + 31) / 32,
+  s2n_mma_kernel<<<grid, 256, 0, c->stream>>>(d_xc, d_tot, n, G, d_labels, d_inv_n, R, C, (n + 31) / 32,
                                               d_scores, d_list, d_count, cap, d_overflow);
   c->launches++;
   FGS_CUDA(cudaGetLastError());
