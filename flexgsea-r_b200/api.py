@@ -670,6 +670,7 @@ def flexgsea(x, y, gene_sets, gene_score_fn=flexgsea_s2n, es_fn=flexgsea_weighte
             pm_local = None
     want_null_host = ("es_null" in return_values) or not builtin_sig or not builtin_es
     if builtin_score and builtin_es:
+        failed = None
         try:
             if grouped:
                 null_local = ctx.perm_null(gene_score_fn.kind, es_fn.kind, nperm, perm=pm_local, seed=seed or 0,
@@ -678,7 +679,15 @@ def flexgsea(x, y, gene_sets, gene_score_fn=flexgsea_s2n, es_fn=flexgsea_weighte
                 null_local = ctx.perm_null(gene_score_fn.kind, es_fn.kind, local, perm=pm_local, seed=seed or 0,
                                            perm_id0=lo, abs_flag=abs, want_host=want_null_host)
         except nat.NonFiniteScoreError:
-            raise ValueError("Gene scoring function returned NA or Inf.")  # :401
+            failed = ValueError("Gene scoring function returned NA or Inf.")  # :401
+        except nat.FlexgseaError as e:
+            failed = e
+        # a rank whose shard failed must not leave the others waiting in the exchange: everybody learns of it first
+        if shard.world > 1 and int(shard.all_reduce_sum(np.array([0 if failed is None else 1], dtype=np.int64))[0]):
+            raise failed if failed is not None else ValueError(
+                "Gene scoring function returned NA or Inf. (on another rank's share of the permutations)")
+        if failed is not None:
+            raise failed
     elif builtin_es and not builtin_score:
         # A user-defined gene.score.fn (limma's moderated t, say) runs on the host per permutation
         # (:383-394); its scores go to the device in tiles of block.size permutations, and the
