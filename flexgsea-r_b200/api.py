@@ -514,6 +514,27 @@ class _Shard:
         return t.cpu().numpy()
 
 
+def _gather_null(ctx, shard, null_local, nperm_total):
+    """the whole es.null [S, R, P] on every rank (return_values = 'es_null', or a user sig.fun):
+    device to device through the library's communicator when it is attached
+    (fgs_comm_allgather_null; spans may differ by one permutation), else through the host"""
+    if shard.world == 1:
+        return null_local
+    lo, hi = shard.span(nperm_total)
+    if ctx.comm_info() == (shard.world, shard.rank) and ctx.null_device_ptr()[3] == hi - lo:
+        return ctx.allgather_null(nperm_total)     # (the resident null still is this rank's span)
+    S, R, Pl = null_local.shape
+    width = -(-nperm_total // shard.world)             # equal shapes for the host all-gather: pad to the widest span
+    padded = np.zeros((S, R, width), order="F")
+    padded[:, :, :Pl] = null_local
+    parts = shard.all_gather(np.ascontiguousarray(padded))
+    out = []
+    for r in range(shard.world):
+        lo, hi = (nperm_total * r) // shard.world, (nperm_total * (r + 1)) // shard.world
+        out.append(parts[r][:, :, :hi - lo])
+    return np.asfortranarray(np.concatenate(out, axis=2))
+
+
 def sharded_sig(ctx, shard, sig_fun, es, response, abs, nperm_total):
     """flexgsea_calc_sig over a null whose permutations are sharded over ranks:
     all-gather of the per-set double-double null sums (combined in rank order),
@@ -738,7 +759,7 @@ def flexgsea(x, y, gene_sets, gene_score_fn=flexgsea_s2n, es_fn=flexgsea_weighte
                 res = sharded_sig(ctx, shard, sig_fun, es[:, r], r, abs, nperm)
             cols = sig_fun.columns(es[:, r], res, abs)
         else:
-            full = null_local if shard.world == 1 else np.concatenate(list(shard.all_gather(null_local)), axis=2)
+            full = _gather_null(ctx, shard, null_local, nperm)
             tab = sig_fun(es[:, r], np.ascontiguousarray(full[:, r, :]), verbose=verbose, abs=abs)
             cols = {k: np.asarray(tab[k]) for k in (tab.columns if hasattr(tab, "columns") else tab)}
         for k, v in extra_stats.items():  # :334-338
@@ -748,10 +769,7 @@ def flexgsea(x, y, gene_sets, gene_score_fn=flexgsea_s2n, es_fn=flexgsea_weighte
 
     res = {"table": dict(zip(responses, sig))}
     if "es_null" in return_values:  # :342-344
-        full = null_local
-        if shard.world > 1:
-            full = np.concatenate(list(shard.all_gather(np.ascontiguousarray(null_local))), axis=2)
-        res["es_null"] = full
+        res["es_null"] = _gather_null(ctx, shard, null_local, nperm)
         res["es_null_dimnames"] = (set_names, list(responses))
     if "gene_names" in return_values:
         res["gene_names"] = gene_names

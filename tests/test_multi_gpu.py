@@ -153,3 +153,58 @@ def test_one_process_per_gpu_comm_equals_single_gpu(tmp_path):
         assert np.array_equal(got["full"], null, equal_nan=True)
         for k in SIG_KEYS:
             assert np.array_equal(got[k], sig[k], equal_nan=True), (r, k)
+
+
+_DIST_WORKER = r'''
+import os, sys, numpy as np
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as dist
+rank = int(os.environ["RANK"]); torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+import flexgsea_r_b200 as fg
+from flexgsea_r_b200 import synth
+G, n, S = 1500, 24, 120
+off, idx = synth.gene_sets_csr(G, S, (10, 120), "loguniform", seed=5)
+x, y = synth.two_class(G, n, off, idx, seed=6)
+names = ["g%%d" %% i for i in range(G)]
+sets = {"s%%d" %% k: [names[i - 1] for i in idx[off[k]:off[k + 1]]] for k in range(S)}
+res = fg.flexgsea(x, y[:, 0], sets, gene_names=names, nperm=301, gs_size_min=1, gs_size_max=500, verbose=False,
+                  seed=9, return_values=["es_null"], device=rank)
+assert fg.get_context(rank).comm_info() == (2, rank)      # the library's own communicator was attached
+t = res["table"]["Response 1"]
+np.savez(os.path.join(sys.argv[1], "d%%d.npz" %% rank), es_null=res["es_null"],
+         **{c: np.asarray(t[c]) for c in ("es", "p", "nes", "fdr", "fwer")})
+dist.destroy_process_group()
+'''
+
+
+def test_flexgsea_under_torch_distributed_equals_one_gpu(tmp_path):
+    """one process per GPU (the torchrun layout): flexgsea() shards the permutations over the ranks of
+    torch.distributed, attaches the library's NCCL communicator (id broadcast through torch) and
+    returns the single-GPU result on every rank."""
+    _need(2)
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "d.py"
+    script.write_text(_DIST_WORKER % {"root": ROOT})
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), str(tmp_path)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=600)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    G, n, S = 1500, 24, 120
+    off, idx = synth.gene_sets_csr(G, S, (10, 120), "loguniform", seed=5)
+    x, y = synth.two_class(G, n, off, idx, seed=6)
+    names = ["g%d" % i for i in range(G)]
+    sets = {"s%d" % k: [names[i - 1] for i in idx[off[k]:off[k + 1]]] for k in range(S)}
+    one = fg.flexgsea(x, y[:, 0], sets, gene_names=names, nperm=301, gs_size_min=1, gs_size_max=500, verbose=False,
+                      seed=9, return_values=["es_null"])
+    t = one["table"]["Response 1"]
+    for r in range(2):
+        got = np.load(os.path.join(tmp_path, "d%d.npz" % r))
+        assert np.array_equal(got["es_null"], one["es_null"], equal_nan=True)
+        for c in ("es", "p", "nes", "fdr", "fwer"):
+            assert np.array_equal(got[c], np.asarray(t[c]), equal_nan=True), (r, c)
