@@ -111,7 +111,8 @@ flexgsea_native_observed <- function(st, gene.scores, responses, return_stats, r
 # perm.fun of the GPU path: the signature flexgsea() calls (R/flexgsea.R:305-307),
 #   perm.fun(x, y, gene.sets, gene.names, nperm, block.size, gene.score.fn, es.fn, responses,
 #            abs=abs, verbose=verbose)
-# block.size is accepted and unused (the device path sizes its own blocks).
+# block.size: the built-in score functions size their own blocks on the device; with a user-defined
+# gene.score.fn it is the number of permutations scored in R per tile handed to the GPUs.
 flexgsea_perm_native <- function(x, y, gene.sets, gene.names, nperm, block.size, gene.score.fn, es.fn,
                                  responses, abs=F, verbose=T) {
     st <- .fgs$session

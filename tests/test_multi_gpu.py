@@ -208,3 +208,49 @@ def test_flexgsea_under_torch_distributed_equals_one_gpu(tmp_path):
         assert np.array_equal(got["es_null"], one["es_null"], equal_nan=True)
         for c in ("es", "p", "nes", "fdr", "fwer"):
             assert np.array_equal(got[c], np.asarray(t[c]), equal_nan=True), (r, c)
+
+
+def test_few_samples_dedup_and_user_score_tiles_over_two_gpus(oracle):
+    """(1) six samples: every GPU deduplicates the labellings of ITS share, routed by the total
+    permutation count -- same tables as one GPU, counts identical to the oracle; (2) tiles of a
+    user gene.score.fn go to the GPU whose span they fall into (a tile may straddle two)."""
+    _need(2)
+    G, n, S, P = 3000, 6, 200, 400
+    off, idx = synth.gene_sets_csr(G, S, (10, 200), "loguniform", seed=31)
+    x, y = synth.two_class(G, n, off, idx, seed=32)
+    perm = synth.perm_matrix(n, P, seed=34)
+    grp = nat.Group(2)
+    one = fg.Context(0)
+    try:
+        for eng in (one, grp):
+            eng.set_x(x); eng.set_gene_sets(off, idx); eng.set_response_s2n(y)
+        res = []
+        for eng in (one, grp):
+            sc = eng.score_observed(nat.SCORE_S2N)
+            es = eng.observed_es(nat.ES_WEIGHTED_KS, sc, ragged=False)["es"][:, 0]
+            null = eng.perm_null(nat.SCORE_S2N, nat.ES_WEIGHTED_KS, P, perm=perm)
+            res.append((null, eng.calc_sig(es)))
+        assert one.get_stat("dedup_labellings") == 20 and grp.ctx[1].get_stat("dedup_labellings") == 20
+        assert np.array_equal(res[0][0], res[1][0], equal_nan=True)
+        _same_sig(res[0][1], res[1][1])
+        rc, want = oracle.perm_null(x, oracle.SCORE_S2N, y, False, perm, off, idx, oracle.ES_WKS)
+        osig = oracle.calc_sig(es, want[:, 0, :])
+        assert rc == 0 and np.array_equal(res[1][1]["p_counts"], osig["p_counts"])
+        assert np.array_equal(res[1][1]["fdr_counts"], osig["fdr_counts"])
+        # user-score tiles over the group: 90 permutations in tiles of 25 (the 2nd tile straddles the spans 45 | 45)
+        rng = np.random.default_rng(35)
+        scu = rng.normal(size=(G, 2, 90))
+        ref = one.es_from_scores(nat.ES_WEIGHTED_KS, scu)
+        for t0 in range(0, 90, 25):
+            grp.es_from_scores_tile(nat.ES_WEIGHTED_KS, np.asfortranarray(scu[:, :, t0:t0 + 25]), t0, 90)
+        got = grp.null_finish()
+        assert np.array_equal(got, ref, equal_nan=True)
+        assert [c.null_device_ptr()[3] for c in grp.ctx] == [45, 45]
+        es2 = rng.normal(size=S) * 0.3
+        a = grp.calc_sig(es2, 1)
+        one.set_null(ref[:, 1, :])
+        b = one.calc_sig(es2, 0)
+        for k in ("p_counts", "fdr_counts", "glob_counts", "nes", "fdr"):
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
+    finally:
+        grp.close(); one.close()
