@@ -277,7 +277,13 @@ def run_gpu(args):
     launches = ctx.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([dev_ms, wall_ms, null_ms, coll_ms], dtype=torch.float64, device="cuda")
+    per_rank = None
     if dist is not None:
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)     # what every rank saw: the spread is the wait inside the collectives
+        per_rank = {"step_ms": [float(p[0]) / args.steps for p in parts],
+                    "null_loop_ms": [float(p[2]) / args.steps for p in parts],
+                    "collective_ms": [float(p[3]) / args.steps for p in parts]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, wall_ms, null_ms, coll_ms = (float(v) for v in t)
     lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
@@ -411,6 +417,7 @@ def run_gpu(args):
                         "(CUDA events on the library's stream), max over ranks",
         "null_loop_ms_per_step": null_ms / args.steps,
         "collective_ms_per_step": coll_ms / args.steps,
+        "per_rank": per_rank,
         "wall_ms_per_step": wall_ms / args.steps,
         "e2e": {"value": float(S) * R * P / e2e_s, "unit": "ES/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
