@@ -545,6 +545,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
+    lws = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    if args.impl == "native" and lws > 1 and "CUDA_VISIBLE_DEVICES" not in os.environ:
+        # A job on N GPUs of a bigger box sees only those N (set before CUDA initialises; local rank r still
+        # is device r).  With all eight visible, two NCCL ranks measured 4.8 ms per step of extra wait on one
+        # rank (profiles/README.md "N = 2 on the 8-GPU box"); with the two visible, 0.27 ms.
+        os.environ["CUDA_VISIBLE_DEVICES"] = ",".join(str(i) for i in range(lws))
     if args.impl == "reference":
         run_reference(args)
     elif args.gpus > 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:

@@ -24,10 +24,11 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
-int launch_sig_means(fgs_ctx *c, const double *d_sums_parts, int nparts, const long long *d_counts,
+int launch_sig_means(fgs_ctx *c, const double *d_sums_parts, int nparts, size_t stride, const long long *d_counts,
                      const double *d_es, int S, long long P_total, int split_p, int calc_nes,
                      int abs_flag, double *d_p, double *d_ph, double *d_pl, double *d_mpos,
                      double *d_mneg, double *d_nes, double *d_fwer);
+int launch_sig_sum_counts(fgs_ctx *c, const double *d_parts, int nparts, size_t stride, int S, long long *d_counts);
 int launch_bh(fgs_ctx *c, const double *d_p, int S, double *d_fdr);
 
 }  // namespace fgs (reopened below)
@@ -1368,7 +1369,7 @@ int fgs_sig_stage2(fgs_ctx *c, const double *es, int response, int split_p, int 
     FGS_TRY(h2d(c, d_es, es, S));
     FGS_TRY(h2d(c, d_parts, sums_parts, (size_t)n_parts * S * 4));
     FGS_TRY(h2d(c, d_cnt, counts_total, (size_t)S * 6));
-    FGS_TRY(launch_sig_means(c, d_parts, n_parts, d_cnt, d_es, S, n_perm_total, split_p, calc_nes,
+    FGS_TRY(launch_sig_means(c, d_parts, n_parts, (size_t)S * 4, d_cnt, d_es, S, n_perm_total, split_p, calc_nes,
                              abs_flag, d_p, d_ph, d_pl, d_mp, d_mn, d_nes, d_fw));
     if (calc_nes)
       FGS_TRY(launch_sig_stage2(c, c->es_null.p, S, c->null_R, c->null_P, response, d_es, abs_flag,
@@ -1424,22 +1425,26 @@ int calc_sig_core(fgs_ctx *c, const double *es, int response, int split_p, int c
   auto coll_begin = [&]() { if (sharded && n_coll < 3) cudaEventRecord(c->sig_ev[2 + 2 * n_coll], c->stream); };
   auto coll_end = [&]() { if (sharded && n_coll < 3) cudaEventRecord(c->sig_ev[3 + 2 * n_coll], c->stream); n_coll++; };
   auto body = [&]() -> int {
-    // doubles: es parts[nparts*4S] p ph pl mpos mneg nes fwer fdr
-    FGS_TRY(d.ensure((size_t)S * (9 + 4 * (size_t)nparts))); FGS_TRY(di.ensure((size_t)S * 9 + 8));
-    double *d_es = d.p, *d_parts = d_es + S, *d_p = d_parts + (size_t)nparts * S * 4, *d_ph = d_p + S, *d_pl = d_ph + S,
+    // doubles: es parts[nparts * 10 S] p ph pl mpos mneg nes fwer fdr.  A rank's part is its stage-1
+    // sums [S x 4 doubles] with its counts [S x 6 int64] right behind: ONE all-gather carries both
+    // (the counts are summed over the parts here; the sums are combined in rank order).
+    const size_t part_dbl = (size_t)S * 10;
+    FGS_TRY(d.ensure((size_t)S * 9 + part_dbl * (size_t)nparts)); FGS_TRY(di.ensure((size_t)S * 9 + 8));
+    double *d_es = d.p, *d_parts = d_es + S, *d_p = d_parts + part_dbl * (size_t)nparts, *d_ph = d_p + S, *d_pl = d_ph + S,
            *d_mp = d_pl + S, *d_mn = d_mp + S, *d_nes = d_mn + S, *d_fw = d_nes + S, *d_fdr = d_fw + S;
     long long *d_cnt = di.p, *d_nc = d_cnt + (size_t)S * 6, *d_gl = d_nc + S, *d_fc = d_gl + 2, *d_gc = d_fc + (size_t)S * 2;
     FGS_CUDA(cudaEventRecord(c->sig_ev[0], c->stream));
     FGS_TRY(h2d(c, d_es, es, S));
-    double *d_sums = d_parts + (size_t)part * S * 4;  // this rank's slot: the all-gather is in place
-    FGS_TRY(launch_sig_stage1(c, c->es_null.p, S, c->null_R, P, response, d_es, split_p, abs_flag, d_sums, d_cnt));
+    double *d_sums = d_parts + (size_t)part * part_dbl;  // this rank's slot: the all-gather is in place
+    FGS_TRY(launch_sig_stage1(c, c->es_null.p, S, c->null_R, P, response, d_es, split_p, abs_flag, d_sums,
+                              (long long *)(d_sums + (size_t)S * 4)));
     if (sharded) {
       coll_begin();
-      if (calc_nes) FGS_TRY(comm_allgather_f64(c, d_sums, d_parts, (size_t)S * 4));
-      FGS_TRY(comm_allreduce_i64(c, d_cnt, (size_t)S * 6));
+      FGS_TRY(comm_allgather_f64(c, d_sums, d_parts, part_dbl));
       coll_end();
     }
-    FGS_TRY(launch_sig_means(c, d_parts, nparts, d_cnt, d_es, S, P_total, split_p, calc_nes, abs_flag, d_p, d_ph,
+    FGS_TRY(launch_sig_sum_counts(c, d_parts, nparts, part_dbl, S, d_cnt));
+    FGS_TRY(launch_sig_means(c, d_parts, nparts, part_dbl, d_cnt, d_es, S, P_total, split_p, calc_nes, abs_flag, d_p, d_ph,
                              d_pl, d_mp, d_mn, d_nes, d_fw));
     if (calc_nes) {
       FGS_TRY(launch_sig_stage2(c, c->es_null.p, S, c->null_R, P, response, d_es, abs_flag, d_mp, d_mn,

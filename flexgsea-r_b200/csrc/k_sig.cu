@@ -151,7 +151,24 @@ int launch_sig_stage1(fgs_ctx *c, const double *d_null, int S, int R, int P, int
 // ---- means, p-values, NES, FWER from combined sums / counts ----------------
 // sums_parts [nparts][S][4] (one part per GPU, combined here in part order),
 // counts [S][6] (already summed).  Outputs [S].
-__global__ void sig_means_kernel(const double *__restrict__ sums_parts, int nparts,
+// counts[s][k] = sum over the parts of the counts every rank appended to its sums (one all-gather
+// carries both: part layout [S x 4 doubles | S x 6 int64], `stride` doubles apart)
+__global__ void sig_sum_counts_kernel(const double *__restrict__ parts, int nparts, size_t stride, int S,
+                                      long long *__restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * SIG_NC) return;
+  long long t = 0;
+  for (int k = 0; k < nparts; k++) t += ((const long long *)(parts + (size_t)k * stride + (size_t)S * SIG_NF))[i];
+  counts[i] = t;
+}
+int launch_sig_sum_counts(fgs_ctx *c, const double *d_parts, int nparts, size_t stride, int S, long long *d_counts) {
+  sig_sum_counts_kernel<<<ceil_div((long long)S * SIG_NC, 256), 256, 0, c->stream>>>(d_parts, nparts, stride, S, d_counts);
+  c->launches++;
+  FGS_CUDA(cudaGetLastError());
+  return FGS_OK;
+}
+
+__global__ void sig_means_kernel(const double *__restrict__ sums_parts, int nparts, size_t stride,
                                  const long long *__restrict__ counts,
                                  const double *__restrict__ es, int S, long long P_total,
                                  int split_p, int calc_nes, int abs_flag, double *__restrict__ p_out,
@@ -179,7 +196,7 @@ __global__ void sig_means_kernel(const double *__restrict__ sums_parts, int npar
   if (calc_nes) {
     dd sp = {0.0, 0.0}, sn = {0.0, 0.0};
     for (int k = 0; k < nparts; k++) {
-      const double *ps = sums_parts + ((size_t)k * S + s) * SIG_NF;
+      const double *ps = sums_parts + (size_t)k * stride + (size_t)s * SIG_NF;
       sp = dd_add_dd(sp, {ps[0], ps[1]});
       sn = dd_add_dd(sn, {ps[2], ps[3]});
     }
@@ -520,11 +537,11 @@ __global__ void clamp1_kernel(double *__restrict__ v, int n) {
   if (i < n) v[i] = fmin(v[i], 1.0);
 }
 
-int launch_sig_means(fgs_ctx *c, const double *d_sums_parts, int nparts, const long long *d_counts,
+int launch_sig_means(fgs_ctx *c, const double *d_sums_parts, int nparts, size_t stride, const long long *d_counts,
                      const double *d_es, int S, long long P_total, int split_p, int calc_nes,
                      int abs_flag, double *d_p, double *d_ph, double *d_pl, double *d_mpos,
                      double *d_mneg, double *d_nes, double *d_fwer) {
-  sig_means_kernel<<<ceil_div(S, 128), 128, 0, c->stream>>>(d_sums_parts, nparts, d_counts, d_es, S,
+  sig_means_kernel<<<ceil_div(S, 128), 128, 0, c->stream>>>(d_sums_parts, nparts, stride, d_counts, d_es, S,
                                                             P_total, split_p, calc_nes, abs_flag,
                                                             d_p, d_ph, d_pl, d_mpos, d_mneg, d_nes,
                                                             d_fwer);

@@ -203,9 +203,10 @@ int fgs_sig_finish(fgs_ctx *ctx, const double *nes, const long long *null_counts
  * (x, the gene sets and the observed ES are replicated; Philox streams are keyed
  * by the global permutation id, so the null does not depend on N), and the one
  * exchange step happens inside the library over NCCL (NVLink / NVSwitch):
- *   - ncclAllGather of the per-set double-double null sums [S x 4], combined in
- *     rank order on every rank => the NES means are bit-identical for any N;
- *   - ncclAllReduce (int64) of the p-value counts [S x 6];
+ *   - ONE ncclAllGather of every rank's per-set double-double null sums [S x 4]
+ *     with its p-value counts [S x 6] behind them; the sums are combined in rank
+ *     order on every rank (=> the NES means are bit-identical for any N), the
+ *     counts summed;
  *   - ncclAllReduce (int64) of the pooled-FDR exceedance counts [S + 2] -- the
  *     exact equivalent of all-gathering the null NES (calc_fdr_nes :500-533
  *     only counts), S*8 bytes instead of S*P*8;
