@@ -83,7 +83,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "250"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -258,7 +258,7 @@ def run_gpu(args):
         step()
     sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
+    if rank == 0 and not os.environ.get("FGS_BENCH_NO_SAMPLER"):   # (diagnostic switch; the contract wants the samples)
         sampler.start()
     l0 = ctx.launch_count()
     dev_ms, null_ms, coll_ms = 0.0, 0.0, 0.0
@@ -545,12 +545,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
-    lws = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
-    if args.impl == "native" and lws > 1 and "CUDA_VISIBLE_DEVICES" not in os.environ:
-        # A job on N GPUs of a bigger box sees only those N (set before CUDA initialises; local rank r still
-        # is device r).  With all eight visible, two NCCL ranks measured 4.8 ms per step of extra wait on one
-        # rank (profiles/README.md "N = 2 on the 8-GPU box"); with the two visible, 0.27 ms.
-        os.environ["CUDA_VISIBLE_DEVICES"] = ",".join(str(i) for i in range(lws))
+    if args.impl == "native" and (args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1):
+        # The exchange is a few hundred KB: NVLink-SHARP (NVLS) multicast buys nothing, and with it enabled
+        # every nvidia-smi query of the clock sampler stalled the sampled rank for milliseconds (two ranks on an
+        # 8-GPU box: 3.7 ms per step of waiting in the collectives; 0.35 ms with NVLS off, 0.14 ms without the
+        # sampler -- profiles/README.md).  Set before any NCCL communicator exists.
+        os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
     if args.impl == "reference":
         run_reference(args)
     elif args.gpus > 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:

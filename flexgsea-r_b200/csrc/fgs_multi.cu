@@ -51,6 +51,11 @@ const NcclApi *nccl() {
     // FLEXGSEA_NCCL_LIB: an explicit copy (a process that will load a NEWER NCCL later -- torch's
     // bundled one, say -- must either load that first or name it here: both answer to the soname
     // libnccl.so.2 and the first one loaded serves everybody)
+    // The exchanges are S-length arrays (hundreds of KB): NVLS multicast buys nothing for them, and with it
+    // enabled an nvidia-smi query against a GPU of the communicator stalled that rank for milliseconds
+    // (profiles/README.md).  Only a default: an NCCL_NVLS_ENABLE the user set wins, and a copy of NCCL that
+    // was initialised earlier in the process keeps its own setting.
+    setenv("NCCL_NVLS_ENABLE", "0", 0);
     const char *names[] = {getenv("FLEXGSEA_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     for (const char *nm : names) {
       if (!nm || !*nm) continue;
