@@ -71,19 +71,22 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The process is started before the
+    warm-up (it needs a few hundred ms to enumerate the box) and every line is stamped on arrival; stop() keeps the
+    samples that arrived between begin() and stop().  When the timed region is shorter than one sampling period
+    and holds none, the samples of the warm-up (same work, same load) are reported and "window" says so."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t0 = index, None, [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "250"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -91,11 +94,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.perf_counter()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -103,7 +110,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        timed = [ln for (ts, ln) in self.lines if self.t0 is None or self.t0 <= ts <= t1]
+        window = "timed" if timed else "warmup"
+        for ln in (timed or [ln for (_, ln) in self.lines]):
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -115,7 +124,7 @@ class ClockSampler:
                 if f[3 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def workload(config, seed=1):
@@ -254,12 +263,13 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0 and not os.environ.get("FGS_BENCH_NO_SAMPLER"):   # (diagnostic switch; the contract wants the samples)
-        sampler.start()
+    sampler.begin()
     l0 = ctx.launch_count()
     dev_ms, null_ms, coll_ms = 0.0, 0.0, 0.0
     stage_ms, stage_launch = {"perm": 0.0, "score": 0.0, "rank": 0.0, "es": 0.0}, None
@@ -475,10 +485,11 @@ def run_gpu_group(args):
         t = grp.last_timings()
         return t["step"], t["null"], coll, sig
 
-    for _ in range(args.warmup):
-        step()
     sampler = ClockSampler(0)
     sampler.start()
+    for _ in range(args.warmup):
+        step()
+    sampler.begin()
     l0 = sum(cx.launch_count() for cx in grp.ctx)
     dev_ms = null_ms = coll_ms = 0.0
     w0 = time.perf_counter()
