@@ -584,6 +584,7 @@ int fgs_set_option(fgs_ctx *c, const char *name, long long value) {
   else if (!strcmp(name, "es_exact_small")) c->opt_exact_small = (int)value;
   else if (!strcmp(name, "tail_split")) c->opt_tail_split = (int)value;
   else if (!strcmp(name, "dedup_labels")) c->opt_dedup = (int)value;
+  else if (!strcmp(name, "bulk_stage")) c->opt_bulk_stage = (int)value;
   else if (!strcmp(name, "arrange_members")) { c->opt_arrange = (int)value; c->invgm_G = -1; }
   else if (!strcmp(name, "nperm_total")) c->opt_nperm_total = value > 0 ? value : 0;
   else if (!strcmp(name, "cert_cap")) c->opt_cert_cap = value > 2 ? (int)value : 2;

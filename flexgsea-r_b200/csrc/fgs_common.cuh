@@ -106,6 +106,7 @@ struct fgs_ctx {
   int opt_cert_cap = 4 << 20;  // entries per certification list (epilogue list, tie list)
   int opt_score_ppt = 0;
   long long opt_nperm_total = 0;  // permutations over ALL ranks when the caller shards them (0: this call's)
+  int opt_bulk_stage = 1;      // weight / score columns staged by cp.async.bulk (0: the ld.global / st.shared loop)
   int opt_arrange = 1;         // member blocks dealt out by bank for the maxmean / mean gathers (arrange_idx16_kernel)
   int opt_tail_split = 1;      // split the columns of a partial last round over the idle SMs (ES kernels)
 
@@ -323,5 +324,35 @@ __device__ __forceinline__ double hit_weight(double a, double p_exp) {
 // largest set the in-register weighted-KS kernel takes (64 ranks per lane on a whole warp)
 constexpr int ES_MAX_SET = 2048;
 __host__ __device__ inline size_t pitch_of(int G) { return ((size_t)G + 7) & ~(size_t)7; }
+
+#ifdef __CUDACC__
+// Bulk copies global -> shared by the copy engine (cp.async.bulk, SASS UBLKCP) with an mbarrier that
+// counts the bytes: ONE thread issues the copy of a whole column and the CTA's threads do other
+// staging work until they wait for it, instead of every thread looping over ld.global / st.shared.
+// Source, destination and size are multiples of 16 bytes.
+__device__ __forceinline__ void bulk_bar_init(uint64_t *bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// (called by one thread, after a __syncthreads() behind the last generic-proxy access of `dst`)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar), d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void bulk_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}" ::"r"(b), "r"(parity) : "memory");
+}
+#endif
 
 }  // namespace fgs

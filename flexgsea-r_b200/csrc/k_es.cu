@@ -354,14 +354,17 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
               const double *__restrict__ set_invgm, int S, double *__restrict__ es_out,
               int2 *__restrict__ tie_list, int *__restrict__ tie_ctr, int tie_cap,
               const double *__restrict__ obs, const int *__restrict__ ident, int R,
-              const int2 *__restrict__ groups, int n_groups, int tail_split) {
+              const int2 *__restrict__ groups, int n_groups, int tail_split, int bulk) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31;
   const size_t Gp = pitch_of(G);
   uint16_t *s_rank = (uint16_t *)smem;                    // [Gp + 8]: 0-based ranks, pad gene at [G]
   double *s_abs = (double *)(smem + (Gp + 8) * 2);
   __shared__ int s_next;  // next group of the column (see below)
+  __shared__ __align__(8) uint64_t s_bar;  // counts the bytes of the weight column in flight (bulk copy)
   if (W_SMEM && tid < 8) s_abs[G + tid] = 0.0;  // zero slot(s) behind the weights: the pads' weight
+  __shared__ uint32_t s_phase;             // its phase: flips once per column of this CTA
+  if (W_SMEM && bulk && tid == 0) { bulk_bar_init(&s_bar); s_phase = 0; }
 
   // Whole rounds of one column per CTA, then the tail round: the C % gridDim.x columns left over
   // are split `tail_split` ways (every CTA stages the column, the groups go round by `part`), so
@@ -380,7 +383,10 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
       col = C_full + t / tail_split;
     }
     __syncthreads();
-    {  // stage the column: 16-byte vector copies (rows are 16-byte aligned), ranks made 0-based
+    {  // stage the column.  The weights are a plain copy: the copy engine takes them (one bulk copy of
+      // the G & ~1 doubles, rows are 64-byte aligned) while the threads turn the ranks 0-based
+      // with 16-byte vector copies; without `bulk` the threads copy the weights too.
+      if (W_SMEM && bulk && tid == 0) bulk_g2s(s_abs, sabs + (size_t)col * Gp, (uint32_t)(G & ~1) * 8u, &s_bar);
       const uint4 *src = (const uint4 *)(rank16 + (size_t)col * Gp);
       uint4 *dst = (uint4 *)s_rank;
       for (int i = tid; i < (int)(Gp / 8); i += blockDim.x) {
@@ -390,12 +396,18 @@ es_wks_kernel(const uint16_t *__restrict__ rank16, const double *__restrict__ sa
         dst[i] = r;
       }
       if (W_SMEM) {
-        for (int i = tid; i < G; i += blockDim.x) s_abs[i] = __ldg(sabs + (size_t)col * Gp + i);
+        if (bulk) {
+          if ((G & 1) && tid == 32) s_abs[G - 1] = __ldg(sabs + (size_t)col * Gp + G - 1);
+          bulk_wait(&s_bar, s_phase);  // (s_phase is flipped between the two barriers below)
+        } else {
+          for (int i = tid; i < G; i += blockDim.x) s_abs[i] = __ldg(sabs + (size_t)col * Gp + i);
+        }
       }
     }
     __syncthreads();
     if (tid == 0) {
       s_rank[G] = (uint16_t)G; s_next = 0;  // the pad gene's key (inside the staged row when G < Gp)
+      if (W_SMEM && bulk) s_phase ^= 1u;
       const bool in_tail = w >= C_full;
       s_part[0] = in_tail ? (w - C_full) % tail_split : 0;
       s_part[1] = in_tail ? tail_split : 1;
@@ -925,7 +937,7 @@ static int launch_es_wks_inner(fgs_ctx *c, const uint16_t *d_rank16, const doubl
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
   const size_t Gp = pitch_of(G);
   const size_t budget = (size_t)c->smem_optin;
-  if (Gp * 2 + 16 + 16 > budget)  // the rank array does not fit on chip: the order-free kernel does everything
+  if (Gp * 2 + 16 + 48 > budget)  // (48: the kernel's static shared memory) the rank array does not fit on chip: the order-free kernel does everything
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
   if (G > 65534)  // the pad key G must fit a uint16 next to the ranks
     return launch_es_wks_generic(c, d_rank16, d_sabs, G, C, nullptr, c->S, d_es);
@@ -933,7 +945,7 @@ static int launch_es_wks_inner(fgs_ctx *c, const uint16_t *d_rank16, const doubl
   const int tail = (int)(C % grid);
   const int tail_split = (tail && c->opt_tail_split) ? std::max(1, std::min(8, grid / tail)) : 1;
   // rank (2 B) + weight (8 B) per gene on chip, + pad gene, + zero weight slots
-  const bool w_smem = Gp * 10 + 16 + 64 + 16 <= budget;  // 16: the kernel's static shared memory
+  const bool w_smem = Gp * 10 + 16 + 64 + 48 <= budget;  // 48: the kernel's static shared memory
   const size_t smem = w_smem ? Gp * 10 + 16 + 64 : Gp * 2 + 16;
   FGS_TRY(ensure_set_blocks(c, G));
   // groups [0, n_wide) are single sets on a whole warp, the rest packed sets of up to 512 members
@@ -943,7 +955,7 @@ static int launch_es_wks_inner(fgs_ctx *c, const uint16_t *d_rank16, const doubl
     kern<<<grid, threads, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx16.p,
                                              c->set_invgm.p, c->S, d_es, c->tie_list.p, c->tie_ctr.p,
                                              c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R, groups, n,
-                                             tail_split);
+                                             tail_split, c->opt_bulk_stage);
     c->launches++;
     FGS_CUDA(cudaGetLastError());
     return FGS_OK;
@@ -1094,13 +1106,18 @@ es_mean_smem_kernel(const double *__restrict__ scores, int G, long long C,
                     const int4 *__restrict__ set_info, const uint16_t *__restrict__ idx16, int S,
                     int abs_flag, double *__restrict__ es_out, int2 *__restrict__ tie_list,
                     int *__restrict__ tie_ctr, int tie_cap, const double *__restrict__ obs,
-                    const int *__restrict__ ident, int R, int tail_split) {
+                    const int *__restrict__ ident, int R, int tail_split, int bulk) {
   extern __shared__ __align__(16) unsigned char smem[];
   double *s_sc = (double *)smem;  // [G + 1]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int seg = lane >> 3, ls = lane & 7;
   const int nquads = (S + 3) >> 2;
-  if (tid == 0) s_sc[G] = 0.0;  // the pad gene
+  __shared__ __align__(8) uint64_t s_bar;
+  // the column is a plain copy unless |.| is taken on the way in: one bulk copy by the copy engine
+  // (columns have pitch G: 16-byte aligned when G is even)
+  bulk = bulk && !abs_flag && !(G & 1);
+  if (tid == 0) { s_sc[G] = 0.0; if (bulk) bulk_bar_init(&s_bar); }  // the pad gene
+  uint32_t phase = 0;
   const long long C_full = (C / gridDim.x) * gridDim.x;  // then the tail round, split (see es_wks_kernel)
   for (long long w = blockIdx.x;; w += gridDim.x) {
     long long col = w;
@@ -1112,9 +1129,15 @@ es_mean_smem_kernel(const double *__restrict__ scores, int G, long long C,
     }
     __syncthreads();
     const double *sc = scores + (size_t)col * G;
-    for (int i = tid; i < G; i += blockDim.x) {
-      const double v = __ldg(sc + i);
-      s_sc[i] = abs_flag ? fabs(v) : v;
+    if (bulk) {
+      if (tid == 0) bulk_g2s(s_sc, sc, (uint32_t)G * 8u, &s_bar);
+      bulk_wait(&s_bar, phase);
+      phase ^= 1u;
+    } else {
+      for (int i = tid; i < G; i += blockDim.x) {
+        const double v = __ldg(sc + i);
+        s_sc[i] = abs_flag ? fabs(v) : v;
+      }
     }
     __syncthreads();
     double *es_col = es_out + (size_t)col * S;
@@ -1193,7 +1216,7 @@ int launch_es_mean(fgs_ctx *c, const double *d_scores, int G, long long C, int e
     return FGS_OK;  // launch_es_mean_exact (all units) follows
   }
   const size_t smem = ((size_t)G + 2) * 8;
-  if (smem <= (size_t)c->smem_optin && G <= 65534) {
+  if (smem + 32 <= (size_t)c->smem_optin && G <= 65534) {  // (32: the kernel's static shared memory)
     const int grid = c->num_sms;
     const int tail = (int)(C % grid);
     const int tail_split = (tail && c->opt_tail_split) ? std::max(1, std::min(8, grid / tail)) : 1;
@@ -1202,12 +1225,14 @@ int launch_es_mean(fgs_ctx *c, const double *d_scores, int G, long long C, int e
       auto k = es_mean_smem_kernel<true>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k<<<grid, ESM_THREADS, smem, c->stream>>>(d_scores, G, C, c->set_info.p, c->set_idx16.p, c->S, abs_flag, d_es,
-                                                c->tie_list.p, c->tie_ctr.p, c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R, tail_split);
+                                                c->tie_list.p, c->tie_ctr.p, c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R, tail_split,
+                                                c->opt_bulk_stage);
     } else {
       auto k = es_mean_smem_kernel<false>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k<<<grid, ESM_THREADS, smem, c->stream>>>(d_scores, G, C, c->set_info.p, c->set_idx16.p, c->S, abs_flag, d_es,
-                                                c->tie_list.p, c->tie_ctr.p, c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R, tail_split);
+                                                c->tie_list.p, c->tie_ctr.p, c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R, tail_split,
+                                                c->opt_bulk_stage);
     }
   } else {  // column does not fit on chip: gather through L1/L2
     long long units = (long long)c->S * C;

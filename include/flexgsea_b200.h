@@ -347,6 +347,10 @@ int fgs_set_progress(fgs_ctx *ctx, fgs_progress_fn cb, void *user);
  * es_exact_small do not depend on the shard -- the groups do it themselves),
  * "tail_split" (1, default: the ES kernels split the columns of a partial last
  * round over the idle SMs),
+ * "bulk_stage" (1, default: the ES kernels stage a column's weights / scores in
+ * shared memory with one cp.async.bulk copy; 0: a load / store loop),
+ * "arrange_members" (1, default: member blocks of the mean / maxmean kernels
+ * dealt out by shared-memory bank),
  * "dedup_labels" (1, default: with few samples -- at most 32, and fewer distinct
  * class labellings than half the permutations -- fgs_perm_null computes every
  * distinct labelling once and copies its column to the permutations that share

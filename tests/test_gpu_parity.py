@@ -859,6 +859,34 @@ def test_flexgsea_lm_structure(ctx):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("G", [3001, 3000, 20000])
+def test_bulk_copy_staging_same_bits(ctx, oracle, G):
+    """The ES kernels stage a column's weights / scores with one bulk copy by the copy engine
+    (cp.async.bulk + mbarrier; option bulk_stage) instead of a load / store loop per thread.  More
+    columns than SMs, so every CTA takes several columns and the barrier's phase flips; odd G (the
+    last weight goes by hand; the mean kernels' columns are then not 16-byte aligned and keep the
+    loop).  Same bits either way, and the oracle's values."""
+    rng = np.random.default_rng(77 + G)
+    P = 330 if G < 20000 else 160
+    sc = np.asfortranarray(rng.normal(size=(G, 1, P)))
+    off, idx = synth.gene_sets_csr(G, 60, (5, 600), "loguniform", seed=5)
+    ctx.set_gene_sets(off, idx)
+    try:
+        for kind, ok in ((nat.ES_WEIGHTED_KS, oracle.ES_WKS), (nat.ES_MAXMEAN, oracle.ES_MAXMEAN),
+                         (nat.ES_MEAN, oracle.ES_MEAN)):
+            ctx.set_option("bulk_stage", 1)
+            a = ctx.es_from_scores(kind, sc)
+            ctx.set_option("bulk_stage", 0)
+            b = ctx.es_from_scores(kind, sc)
+            assert a.tobytes() == b.tobytes(), kind
+            if G < 20000:
+                rc, want = oracle.es_from_scores(ok, sc[:, :, :40], off, idx)
+                assert rc == 0 and np.abs(a[:, :, :40] - want).max() <= ES_TOL
+    finally:
+        ctx.set_option("bulk_stage", 1)
+
+
+@pytest.mark.gpu
 def test_user_scores_stream_in_blocks(ctx, oracle):
     """user score columns arrive block by block (upload of block k+1 while block k is ranked,
     two score buffers): every block count, incl. a ragged last block, gives the one-block result"""
