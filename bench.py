@@ -432,7 +432,7 @@ def run_gpu(args):
         "e2e": {"value": float(S) * R * P / e2e_s, "unit": "ES/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
                 "what": "set_x + set_gene_sets + set_response + observed scores/ES(+extras) + null loop "
-                        "(host permutation matrix) + calc_sig (sharded: NCCL exchange); pinned host buffers; "
+                        "(host permutation matrix) + calc_sig" + (" (sharded: NCCL exchange)" if world > 1 else "") + "; pinned host buffers; "
                         "result table read back on every rank"},
         "gpu_launches": int(launches),
         "roofline": roofline,

@@ -3,6 +3,7 @@ include/flexgsea_b200.h declares (no compute without a GPU), and the host logic
 that mirrors the reference's R API (GMT ingest, gene-set filtering, CSR packing,
 response encoding, R's RNG stream, permutation sharding)."""
 import os
+import time
 import re
 import subprocess
 import sys
@@ -216,3 +217,26 @@ def test_limma_style_client_on_the_host():
         fg.flexgsea_limma(E, D)
     assert api._call_score(lambda x, y, t_x=False, abs=False: t_x, None, None, True, False) is True
     assert api._call_score(lambda x, y, abs=False: "no t_x", None, None, True, False) == "no t_x"
+
+
+def test_bench_clock_sampler_keeps_the_timed_window():
+    """bench.py's nvidia-smi sampler runs from before the warm-up; only the lines that arrived inside
+    the timed region count, and a region shorter than one sampling period reports the warm-up's
+    samples and says so"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+
+    class Proc:
+        def terminate(self): pass
+        def wait(self, timeout=None): pass
+    s = bench.ClockSampler(0)
+    s.proc = Proc()
+    s.lines = [(time.perf_counter(), "1200, 1965, 300.0, Not Active, Not Active, Not Active, Active")]
+    time.sleep(0.002)
+    s.begin()
+    r = s.stop()
+    assert r["window"] == "warmup" and r["samples"] == 1 and r["reasons"] == ["sw_power_cap"]
+    s.lines.append((time.perf_counter(), "1965, 1965, 900.0, Not Active, Not Active, Not Active, Not Active"))
+    r = s.stop()
+    assert r == {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 1, "window": "timed"}
