@@ -955,7 +955,7 @@ static int launch_es_wks_inner(fgs_ctx *c, const uint16_t *d_rank16, const doubl
     kern<<<grid, threads, smem, c->stream>>>(d_rank16, d_sabs, G, C, c->set_info.p, c->set_idx16.p,
                                              c->set_invgm.p, c->S, d_es, c->tie_list.p, c->tie_ctr.p,
                                              c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R, groups, n,
-                                             tail_split, c->opt_bulk_stage);
+                                             tail_split, (c->opt_bulk_stage && G >= 2) ? 1 : 0);
     c->launches++;
     FGS_CUDA(cudaGetLastError());
     return FGS_OK;
@@ -1226,13 +1226,13 @@ int launch_es_mean(fgs_ctx *c, const double *d_scores, int G, long long C, int e
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k<<<grid, ESM_THREADS, smem, c->stream>>>(d_scores, G, C, c->set_info.p, c->set_idx16.p, c->S, abs_flag, d_es,
                                                 c->tie_list.p, c->tie_ctr.p, c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R, tail_split,
-                                                c->opt_bulk_stage);
+                                                (c->opt_bulk_stage && G >= 2) ? 1 : 0);
     } else {
       auto k = es_mean_smem_kernel<false>;
       FGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k<<<grid, ESM_THREADS, smem, c->stream>>>(d_scores, G, C, c->set_info.p, c->set_idx16.p, c->S, abs_flag, d_es,
                                                 c->tie_list.p, c->tie_ctr.p, c->tie_cap, c->cur_obs, c->cur_ident, c->cur_obs_R, tail_split,
-                                                c->opt_bulk_stage);
+                                                (c->opt_bulk_stage && G >= 2) ? 1 : 0);
     }
   } else {  // column does not fit on chip: gather through L1/L2
     long long units = (long long)c->S * C;
