@@ -1,4 +1,6 @@
 # N = 2 on the 8-GPU box: what makes rank 0 late by 3.7 ms per step?
+# (ran against commit d94a12d plus two diagnostic switches in bench.py, since removed: FGS_BENCH_NO_CVD = do not
+# restrict CUDA_VISIBLE_DEVICES inside the process, FGS_BENCH_NO_SAMPLER = no nvidia-smi clock sampler)
 set -x
 mkdir -p gpurun_out
 run() { tag=$1; shift; env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $((29800 + RANDOM % 100)) bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r2w_$tag.json 2> gpurun_out/r2w_$tag.err; }
